@@ -1,0 +1,442 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark of the pragma-dsp FFT/spectrum hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Metric (BASELINE.json): batched N=1024 FFT frames/s (+ achieved HBM GB/s).  A "step" is one pass
+of the fused kernel (frame build + window + FFT + amplitude + peak) over one batch of synthetic
+multi-tone frames.  Default workload = BASELINE configs[1] ("c2"): 65,536 frames x N=1024 fp32,
+Hann, one-sided amplitude + peak @ 48 kHz per GPU (weak scaling: every rank owns a batch of that
+size; with N>1 the per-frame peaks are all-gathered over NCCL on a side stream, overlapped with
+the next step's kernel).  Other workloads: "north_star" (fp64 Hann FFT + one-sided magnitude),
+"c5" (fp64 window + FFT + peak only).
+
+One JSON line on stdout (rank 0).  `value` = whole-job frames/s with inputs resident in HBM;
+`e2e` = the same metric through the public host API (pragma_dsp_b200.spectrum_batch ->
+pdsp_spectrum) from pinned host buffers, H2D and D2H inside the timed region.
+`--impl reference` times the CPU oracle port of the reference algorithm (the reference is
+TypeScript and cannot run here) on all host threads over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 1337
+WORKLOADS = {
+    # name: (precision, sample dtype, window, outputs, frames/GPU, N, description)
+    "c2": dict(prec="f32", sdtype="f32", window="hann", outputs=("amplitude", "peak"), frames=65536, n=1024,
+               desc="spectrum() batched: 65536 frames x N=1024 fp32, Hann, one-sided amplitude + peak @48kHz"),
+    "north_star": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude",), frames=65536, n=1024,
+                       desc="fp64 Hann-windowed FFT + one-sided magnitude, 65536 frames x N=1024"),
+    "c5": dict(prec="f64", sdtype="f64", window="hann", outputs=("peak",), frames=131072, n=1024,
+               desc="fp64 window + FFT + peak argmax only, frame-sharded"),
+}
+
+
+def algorithmic_bytes_per_frame(w) -> int:
+    """compulsory HBM traffic per frame; cached tables excluded."""
+    es = 8 if w["sdtype"] == "f64" else 4
+    os_ = 8 if w["prec"] == "f64" else 4
+    bins = w["n"] // 2 + 1
+    b = w["n"] * es
+    if "amplitude" in w["outputs"]:
+        b += bins * os_
+    if "phase" in w["outputs"]:
+        b += bins * os_
+    if "peak" in w["outputs"]:
+        b += 32 if w["prec"] == "f64" else 16
+    return b
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, w):
+    """The reference's own CPU implementation of the path, restated in C (oracle/), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    threads = oracle.max_threads()
+    n = w["n"]
+    # bounded sample: about 0.5 s of all-core work per step
+    sample = int(min(w["frames"], max(2048, 12000 * threads)))
+    x = synth_frames_numpy(sample, n, np.float64 if w["sdtype"] == "f64" else np.float32)
+
+    def step():
+        oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window=w["window"], sides="one",
+                              want_amplitude=True, want_phase=True, threads=threads)  # spectrum() computes all of it
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, w),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames/step of the same synthetic workload; oracle/pragma_oracle.c "
+                                   f"(op-for-op C port of src/core/fft.ts + spectrum.ts: window, radix-2 FFT, hypot, atan2, "
+                                   f"scaling, findPeak), gcc -O2 -ffp-contract=off, OpenMP static split"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, w):
+    return {"workload": args.workload, "description": w["desc"], "fft_size": w["n"], "frames_per_gpu": w["frames"],
+            "window": w["window"], "sides": "one", "sample_rate": 48000, "outputs": list(w["outputs"]),
+            "sample_dtype": w["sdtype"], "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
+            "parallelism": f"frames sharded x{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def synth_frames_numpy(frames, n, dtype, seed=SEED):
+    """Multi-tone frames per SURVEY 8(d): 3 tones, dominant A1=1, off-bin by at most a quarter bin."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((frames, n), dtype=dtype)
+    t = np.arange(n, dtype=np.float64)
+    for lo in range(0, frames, 4096):
+        hi = min(frames, lo + 4096)
+        b = hi - lo
+        k = rng.integers(8, n // 2 - 8, size=(b, 3)) + rng.uniform(-0.25, 0.25, size=(b, 3))
+        a = np.concatenate([np.ones((b, 1)), rng.uniform(0.1, 0.5, size=(b, 2))], axis=1)
+        ph = rng.uniform(0, 2 * np.pi, size=(b, 3))
+        acc = np.zeros((b, n))
+        for j in range(3):
+            acc += a[:, j, None] * np.sin(2 * np.pi * k[:, j, None] * t[None, :] / n + ph[:, j, None])
+        out[lo:hi] = acc.astype(dtype)
+    return out
+
+
+def synth_frames_torch(torch, frames, n, dtype, device, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((frames, n), dtype=dtype, device=device)
+    t = torch.arange(n, dtype=torch.float64, device=device)
+    for lo in range(0, frames, 8192):
+        hi = min(frames, lo + 8192)
+        b = hi - lo
+        k = torch.randint(8, n // 2 - 8, (b, 3), generator=g, device=device).double()
+        k += torch.rand((b, 3), generator=g, device=device, dtype=torch.float64) * 0.5 - 0.25
+        a = torch.cat([torch.ones((b, 1), device=device, dtype=torch.float64),
+                       torch.rand((b, 2), generator=g, device=device, dtype=torch.float64) * 0.4 + 0.1], dim=1)
+        ph = torch.rand((b, 3), generator=g, device=device, dtype=torch.float64) * (2 * np.pi)
+        acc = torch.zeros((b, n), dtype=torch.float64, device=device)
+        for j in range(3):
+            acc += a[:, j, None] * torch.sin(2 * np.pi * k[:, j, None] * t[None, :] / n + ph[:, j, None])
+        out[lo:hi] = acc.to(dtype)
+    return out
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- b200 arm
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from pragma_dsp_b200 import _lib, spectrum_batch
+    from pragma_dsp_b200._lib import F32, F64, PEAK_F32, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _lib.Context(local)
+    n, frames = w["n"], args.frames or w["frames"]
+    prec = F64 if w["prec"] == "f64" else F32
+    tdt = torch.float64 if w["prec"] == "f64" else torch.float32
+    sdt = torch.float64 if w["sdtype"] == "f64" else torch.float32
+    plan = ctx.plan(n, prec)
+    bins = n // 2 + 1
+    pk_bytes = 32 if prec == F64 else 16
+
+    x = synth_frames_torch(torch, frames, n, sdt, dev, SEED + rank)
+    amp = torch.empty((frames, bins), dtype=tdt, device=dev) if "amplitude" in w["outputs"] else None
+    ph = torch.empty((frames, bins), dtype=tdt, device=dev) if "phase" in w["outputs"] else None
+    want_peak = "peak" in w["outputs"]
+    peaks = [torch.zeros((frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] if want_peak else None
+    gathered = [torch.zeros((world * frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] \
+        if (want_peak and world > 1) else None
+    desc = SpectrumDesc(sample_dtype=F64 if w["sdtype"] == "f64" else F32, frame_len=n, hop=n, batch=frames,
+                        window=WINDOWS[w["window"]], sides=SIDES["one"], sample_rate=48000.0, raw_magnitude=0)
+    compute = torch.cuda.Stream(device=dev)
+    comm = torch.cuda.Stream(device=dev) if gathered else None
+    L = lib()
+
+    def vp(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    kernel_events = []
+
+    def step(i, timed=False):
+        pb = peaks[i & 1] if want_peak else None
+        with torch.cuda.stream(compute):
+            if comm is not None and i >= 2:
+                compute.wait_event(gather_done[i & 1])  # the gather that last read this peaks buffer
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(compute)
+            check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), C.c_void_p(compute.cuda_stream)))
+            if timed:
+                e1.record(compute)
+                kernel_events.append((e0, e1))
+            if comm is not None:
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    dist.all_gather_into_tensor(gathered[i & 1], pb)
+                    gather_done[i & 1].record(comm)
+
+    gather_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- warm-up, then the timed region: EXACTLY K steps, device time, max over ranks
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    launches0 = ctx.launch_count
+    if sampler:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(compute)
+    for i in range(args.steps):
+        step(i, timed=True)
+    if comm is not None:
+        compute.wait_stream(comm)
+    t_end.record(compute)
+    barrier()
+    launches = ctx.launch_count - launches0
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    if world > 1:
+        tt = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms, kern_ms = float(tt[0]), float(tt[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+
+    # ---- sustained probe: same launches for ~0.6 s so NVML sees the clocks this kernel runs at
+    if sampler and not args.quick:
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.6:
+            for i in range(50):
+                check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(peaks[0]) if want_peak else None,
+                                          C.c_void_p(compute.cuda_stream)))
+            compute.synchronize()
+    if sampler:
+        sampler.stop()
+    barrier()
+
+    # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
+    e2e_steps = max(2, min(args.steps, 10)) if not args.quick else 1
+    hx = torch.empty((frames, n), dtype=sdt).pin_memory()
+    hx.copy_(x.cpu())
+    hx_np = hx.numpy()
+    outs = tuple(w["outputs"])
+    h2d = frames * n * hx.element_size()
+    d2h = frames * ((bins * (8 if prec == F64 else 4) if "amplitude" in outs else 0) +
+                    (bins * (8 if prec == F64 else 4) if "phase" in outs else 0) + (pk_bytes if want_peak else 0))
+    # pinned output buffers handed to the C-ABI directly (what createComplexArray-style pinned arrays give JS)
+    h_amp = torch.empty((frames, bins), dtype=tdt).pin_memory() if "amplitude" in outs else None
+    h_ph = torch.empty((frames, bins), dtype=tdt).pin_memory() if "phase" in outs else None
+    h_pk = torch.empty((frames, pk_bytes), dtype=torch.uint8).pin_memory() if want_peak else None
+
+    def e2e_step():
+        check(L.pdsp_spectrum(plan, C.byref(desc), C.c_void_p(hx.data_ptr()),
+                              C.c_void_p(h_amp.data_ptr()) if h_amp is not None else None,
+                              C.c_void_p(h_ph.data_ptr()) if h_ph is not None else None,
+                              C.c_void_p(h_pk.data_ptr()) if h_pk is not None else None))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt[0])
+    e2e_fps = frames * world * e2e_steps / e2e_s
+
+    # ---- parity spot check (outside every timed region): first 256 frames vs the oracle
+    parity = None
+    cpu_baseline = None
+    if rank == 0:
+        import oracle
+        sub = hx_np[:256]
+        got = spectrum_batch(sub, sampleRate=48000.0, fftSize=n, window=w["window"], precision=w["prec"], context=ctx)
+        ref = oracle.spectrum_batch(sub, fftSize=n, sampleRate=48000.0, window=w["window"])
+        parity = {"frames": 256, "peak_index_equal": bool((got["peaks"]["index"] == ref["peaks"]["index"]).all()),
+                  "amp_max_abs_err": float(np.abs(got["amplitude"] - ref["amplitude"]).max())}
+        if world == 1 and not args.quick:
+            sample = min(frames, 65536)
+            t0 = time.perf_counter()
+            oracle.spectrum_batch(hx_np[:sample], fftSize=n, sampleRate=48000.0, window=w["window"], threads=1)
+            one = sample / (time.perf_counter() - t0)
+            thr = oracle.max_threads()
+            t0 = time.perf_counter()
+            oracle.spectrum_batch(hx_np[:sample], fftSize=n, sampleRate=48000.0, window=w["window"], threads=thr)
+            allc = sample / (time.perf_counter() - t0)
+            cpu_baseline = {"value": one, "unit": "frames/s", "cores": 1, "kind": "port",
+                            "sample": f"first {sample} frames of the same batch through oracle/pragma_oracle.c "
+                                      f"(single thread, like the single-threaded JS reference); all {thr} host threads: "
+                                      f"{allc:.0f} frames/s"}
+
+    if rank == 0:
+        total_frames = frames * world
+        fps = total_frames * args.steps / (elapsed_ms * 1e-3)
+        bpf = algorithmic_bytes_per_frame(w)
+        peak, peak_src = measured_hbm_peak()
+        achieved = bpf * frames / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": w["prec"], "data": "synthetic",
+            "config": workload_config(args, w),
+            "hbm_gbs": fps * bpf / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "r2c_kernel",
+                         "algorithmic_bytes_per_frame": bpf, "kernel_ms": kern_ms},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "pdsp_spectrum (host pinned buffers)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary() if sampler else None,
+            "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the clock probe, CPU baseline, shorten e2e")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.frames:
+        w["frames"] = args.frames
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_b200(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

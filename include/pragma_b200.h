@@ -1,0 +1,132 @@
+/*
+ * pragma_b200.h - C ABI of libpragma_b200.so, the B200 (sm_100a) implementation of
+ * pragma-dsp's FFT/spectrum hot path.
+ *
+ * The reference (eliesgalvira/pragma-dsp v0.1.0) is pure TypeScript and has no FFI seam; the
+ * seams a drop-in replaces are its ES-module exports.  Every entry point below cites the
+ * reference interface it stands behind (paths relative to the reference root).  The Node-API
+ * addon (napi/pragma_napi.cc) and the Python host (pragma_dsp_b200/) are thin shims over
+ * exactly these symbols; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pdsp_last_error() returns the
+ *     message of the calling thread's last failure ("pragma-dsp/b200: ...").
+ *   - argument validation that carries the reference's error messages (power-of-two size,
+ *     input length) stays in the host language; the library re-checks and fails with its own text.
+ *   - "host" entry points take ordinary host pointers (JS typed-array memory), stage through
+ *     pinned buffers owned by the context, run on the context's stream and return after the
+ *     results are in the caller's arrays (the reference is synchronous).
+ *   - "dev" entry points take device pointers and a CUDA stream and only enqueue work.
+ *   - there is no CPU execution path: without a CUDA device pdsp_ctx_create fails.
+ */
+#ifndef PRAGMA_B200_H
+#define PRAGMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDSP_ABI_VERSION 1
+
+typedef struct pdsp_ctx pdsp_ctx;   /* one per device: stream, pinned + device staging, plan cache */
+typedef struct pdsp_plan pdsp_plan; /* one per (size, precision): device twiddle / window tables */
+
+enum pdsp_precision { PDSP_F32 = 0, PDSP_F64 = 1 };                                  /* compute + output type */
+enum pdsp_window { PDSP_WIN_RECT = 0, PDSP_WIN_HANN = 1, PDSP_WIN_HAMMING = 2, PDSP_WIN_BLACKMAN = 3 };
+enum pdsp_sides { PDSP_SIDES_ONE = 0, PDSP_SIDES_TWO = 1 };
+
+/* findPeak result (src/public/spectrum.ts:15-20 SpectrumPeak).  Layout by plan precision. */
+typedef struct { int32_t index; int32_t _pad; double frequency, amplitude, phase; } pdsp_peak_f64; /* 32 B */
+typedef struct { int32_t index; float frequency, amplitude, phase; } pdsp_peak_f32;                /* 16 B */
+
+/* spectrum() options (src/public/spectrum.ts:29-34 SpectrumOptions; src/effect/index.ts:53-58) plus
+ * the batch addressing the reference leaves to the caller (spectrumStream frames). */
+typedef struct {
+  int32_t sample_dtype;  /* pdsp_precision of the samples buffer (Float32Array / Float64Array) */
+  int32_t frame_len;     /* samples per frame; < fft size zero-pads, > fft size truncates (buildFrame) */
+  int64_t hop;           /* distance between frame starts, in samples (= frame_len for disjoint frames) */
+  int64_t batch;         /* number of frames */
+  int32_t window;        /* pdsp_window */
+  int32_t sides;         /* pdsp_sides */
+  double sample_rate;    /* > 0 */
+  int32_t raw_magnitude; /* 1: amplitude output is the unscaled |X| (magnitude(), xform/fourier.ts:98-109) */
+  int32_t _reserved;
+} pdsp_spectrum_desc;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int pdsp_abi_version(void);
+const char* pdsp_last_error(void);
+int pdsp_device_count(int* count);
+int pdsp_ctx_create(int device, pdsp_ctx** ctx);
+int pdsp_ctx_destroy(pdsp_ctx* ctx);
+int pdsp_ctx_sync(pdsp_ctx* ctx);
+int pdsp_ctx_device(const pdsp_ctx* ctx);
+int pdsp_ctx_sm_count(const pdsp_ctx* ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+int64_t pdsp_ctx_launch_count(const pdsp_ctx* ctx);
+
+/* ---- pure host helpers (no device work) -------------------------------------------------- */
+/* src/core/fft.ts:16 isPowerOfTwo, :18-23 nextPowerOfTwo */
+int pdsp_is_power_of_two(int32_t n);
+int32_t pdsp_next_power_of_two(int32_t n);
+/* src/xform/fourier.ts:14-52 createWindow(type, size) -> out[size] (binary64, symmetric form) */
+int pdsp_create_window(int window, int32_t size, double* out);
+/* src/xform/fourier.ts:147-165 binFrequencies(size, sampleRate, sides) -> out[bins]; *bins is set */
+int pdsp_bin_frequencies(int32_t size, double sample_rate, int sides, double* out, int32_t* bins);
+
+/* ---- plans: new Radix2Fft(size) / new FFT(size) (src/core/fft.ts:68-75, xform/fourier.ts:73-79);
+ *      cached per context like FourierLive's Map (src/effect/index.ts:30-40) ------------------ */
+int pdsp_plan_get(pdsp_ctx* ctx, int32_t size, int precision, pdsp_plan** plan);
+int32_t pdsp_plan_size(const pdsp_plan* plan);
+int pdsp_plan_precision(const pdsp_plan* plan);
+
+/* ---- Radix2Fft / FFT methods, host buffers ------------------------------------------------- */
+/* forward(input, out) (src/core/fft.ts:77-79): `batch` real frames of plan size, contiguous;
+ * in_dtype says whether `in` is float or double; out planes are double[batch*size], all N bins. */
+int pdsp_fft_forward_real(pdsp_plan* plan, const void* in, int in_dtype, int64_t batch, double* out_re,
+                          double* out_im);
+/* forwardComplex(input, out) (src/core/fft.ts:81-83) */
+int pdsp_fft_forward_complex(pdsp_plan* plan, const double* in_re, const double* in_im, int64_t batch,
+                             double* out_re, double* out_im);
+/* inverse(input, out) (src/core/fft.ts:85-87): conjugate transform times 1/N */
+int pdsp_fft_inverse(pdsp_plan* plan, const double* in_re, const double* in_im, int64_t batch, double* out_re,
+                     double* out_im);
+/* magnitude(c, out) / phase(c, out) (src/xform/fourier.ts:98-120): elementwise over n values */
+int pdsp_magnitude(pdsp_ctx* ctx, const double* re, const double* im, int64_t n, double* out);
+int pdsp_phase(pdsp_ctx* ctx, const double* re, const double* im, int64_t n, double* out);
+
+/* ---- spectrum() / spectrumFx / spectrumStream chunk, host buffers -------------------------
+ * (src/public/spectrum.ts:107-142, src/effect/index.ts:143-194).  Outputs are in the plan's
+ * precision (float for PDSP_F32, double for PDSP_F64), dense rows of `bins` = N/2+1 (one) or N
+ * (two) per frame; amplitude / phase / peaks may each be NULL. peaks points to pdsp_peak_f32[batch]
+ * or pdsp_peak_f64[batch]. */
+int pdsp_spectrum(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* samples, void* amplitude,
+                  void* phase, void* peaks);
+
+/* ---- device-resident variants: pointers are device memory, work is enqueued on `stream`
+ *      (a cudaStream_t passed as void*; NULL = the context's stream) ------------------------- */
+int pdsp_spectrum_dev(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* d_samples, void* d_amplitude,
+                      void* d_phase, void* d_peaks, void* stream);
+/* real forward: out planes in plan precision; full != 0 writes all N bins, else N/2+1 */
+int pdsp_fft_forward_real_dev(pdsp_plan* plan, const void* d_in, int in_dtype, int64_t batch, void* d_out_re,
+                              void* d_out_im, int full, void* stream);
+/* complex forward / inverse on planar arrays in plan precision; d_in_im may be NULL */
+int pdsp_fft_complex_dev(pdsp_plan* plan, const void* d_in_re, const void* d_in_im, int64_t batch, void* d_out_re,
+                         void* d_out_im, int inverse, void* stream);
+
+/* ---- device / pinned-host buffers owned by the library (what createComplexArray hands out
+ *      behind the addon: src/core/fft.ts:6-14) ------------------------------------------------ */
+int pdsp_dev_alloc(pdsp_ctx* ctx, size_t bytes, void** d_ptr);
+int pdsp_dev_free(pdsp_ctx* ctx, void* d_ptr);
+int pdsp_host_alloc(pdsp_ctx* ctx, size_t bytes, void** h_ptr); /* pinned */
+int pdsp_host_free(pdsp_ctx* ctx, void* h_ptr);
+int pdsp_memcpy_h2d(pdsp_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, void* stream);
+int pdsp_memcpy_d2h(pdsp_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRAGMA_B200_H */

@@ -1,0 +1,100 @@
+"""Builds libpragma_b200.so in-tree with nvcc for sm_100a (no GPU needed to compile).
+
+    python -m pragma_dsp_b200.build [--force] [--jobs N]
+
+Every kernel instantiation range listed in csrc/inst_groups.h becomes one object file
+(inst.cu compiled with different -D flags) so the unrolled FFT kernels compile in parallel.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpragma_b200.so")
+NVCC = os.environ.get("PDSP_NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+                "-ccbin", "/usr/bin/g++"]
+
+
+def groups():
+    txt = open(os.path.join(CSRC, "inst_groups.h")).read()
+    out = []
+    for m in re.finditer(r"X\((\d), (\w+), (\w+), (\d+), (\d+)\)", txt):
+        kind, tag, ctype, lo, hi = m.groups()
+        if tag == "typetag":
+            continue
+        name = f"launch_{'r2c' if kind == '0' else 'c2c'}_{tag}_{lo}_{hi}"
+        out.append((int(kind), ctype, int(lo), int(hi), name))
+    return out
+
+
+def _digest(paths, extra):
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def _compile(args):
+    src, obj, defs, stamp = args
+    cmd = [NVCC] + FLAGS + defs + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return obj, r.returncode, r.stdout + r.stderr
+    open(obj + ".stamp", "w").write(stamp)
+    return obj, 0, r.stderr
+
+
+def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "pragma_b200.h"))
+    tasks = []
+    objs = []
+    units = [(os.path.join(CSRC, "pragma_b200.cu"), os.path.join(OBJ, "pragma_b200.o"), [])]
+    for kind, ctype, lo, hi, name in groups():
+        defs = [f"-DPDSP_INST_KIND={kind}", f"-DPDSP_INST_T={ctype}", f"-DPDSP_INST_LO={lo}", f"-DPDSP_INST_HI={hi}",
+                f"-DPDSP_INST_NAME={name}"]
+        units.append((os.path.join(CSRC, "inst.cu"), os.path.join(OBJ, name + ".o"), defs))
+    for src, obj, defs in units:
+        stamp = _digest(headers + [src], " ".join(FLAGS + defs))
+        objs.append(obj)
+        old = open(obj + ".stamp").read() if os.path.exists(obj + ".stamp") and os.path.exists(obj) else ""
+        if force or old != stamp:
+            tasks.append((src, obj, defs, stamp))
+    if tasks:
+        if verbose:
+            print(f"[pragma_dsp_b200.build] compiling {len(tasks)} unit(s) for sm_100a ...", flush=True)
+        with cf.ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
+            for obj, rc, log in ex.map(_compile, tasks):
+                if rc != 0:
+                    sys.stderr.write(log)
+                    raise RuntimeError(f"nvcc failed for {obj}")
+                if verbose and log.strip():
+                    print(log.strip())
+    if tasks or not os.path.exists(LIB):
+        cmd = [NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+        if verbose:
+            print(f"[pragma_dsp_b200.build] linked {LIB}")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    a = ap.parse_args()
+    build(force=a.force, jobs=a.jobs)

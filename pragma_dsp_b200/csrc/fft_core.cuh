@@ -1,0 +1,203 @@
+// fft_core.cuh - register/shared-memory Stockham FFT engine (sm_100a), shared by all kernels.
+//
+// Replaces the reference's in-place radix-2 sweep `Radix2Fft.transform`
+// (/root/reference/src/core/fft.ts:89-151) with an autosort (Stockham) mixed-radix FFT:
+//   * one frame of M = 2^LOG2M complex points is held by TF = M/P threads, P = 2^LOG2P
+//     points per thread in registers (thread t holds elements t + TF*q, q = 0..P-1, on entry
+//     and on exit, natural order - no bit-reversal pass, no `rev[]` table);
+//   * each pass runs P/R radix-R butterflies per thread (R = 2..32, constant twiddles folded
+//     at compile time), multiplies by table twiddles, and exchanges through padded shared
+//     memory (conflict-free for the radix-8/16 first pass);
+//   * sign/normalisation follow the reference: forward e^{-2*pi*i*k*n/N}, unnormalised.
+#pragma once
+#include <type_traits>
+
+#include "simt.h"
+
+namespace pdsp {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cx {
+  T x, y;
+};
+
+template <typename T>
+PDSP_DEVICE cx<T> cadd(cx<T> a, cx<T> b) {
+  return cx<T>{a.x + b.x, a.y + b.y};
+}
+template <typename T>
+PDSP_DEVICE cx<T> csub(cx<T> a, cx<T> b) {
+  return cx<T>{a.x - b.x, a.y - b.y};
+}
+template <typename T>
+PDSP_DEVICE cx<T> cmul(cx<T> a, cx<T> w) {
+  return cx<T>{a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x};
+}
+
+// read-only (non-coherent) load of a table entry
+#if defined(__CUDACC__) && !defined(PDSP_EMU)
+PDSP_DEVICE cx<double> ldg_cx(const cx<double>* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return cx<double>{v.x, v.y};
+}
+PDSP_DEVICE cx<float> ldg_cx(const cx<float>* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return cx<float>{v.x, v.y};
+}
+#else
+template <typename T>
+PDSP_DEVICE cx<T> ldg_cx(const cx<T>* p) {
+  return *p;
+}
+#endif
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+PDSP_DEVICE void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+constexpr int bitrev(int k, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((k >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+
+// cos(pi*k/16), k = 0..8 (round-to-nearest binary64 literals)
+constexpr double cos16(int k) {
+  switch (k) {
+    case 0: return 1.0;
+    case 1: return 0.98078528040323044912618223613424;
+    case 2: return 0.92387953251128675612818318939679;
+    case 3: return 0.83146961230254523707878837761791;
+    case 4: return 0.70710678118654752440084436210485;
+    case 5: return 0.55557023301960222474283081394853;
+    case 6: return 0.38268343236508977172845998403040;
+    case 7: return 0.19509032201612826784828486847702;
+    default: return 0.0;
+  }
+}
+// W32^K = exp(-2*pi*i*K/32) = (wr, wi), K in [0, 16)
+constexpr double w32_re(int K) { return K <= 8 ? cos16(K) : -cos16(16 - K); }
+constexpr double w32_im(int K) { return K <= 8 ? -cos16(8 - K) : -cos16(K - 8); }
+
+// d * W32^K with the trivial cases folded
+template <int K, typename T>
+PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
+  static_assert(K >= 0 && K < 16, "twiddle index");
+  if constexpr (K == 0) {
+    return d;
+  } else if constexpr (K == 8) {  // -i
+    return cx<T>{d.y, -d.x};
+  } else if constexpr (K == 4) {  // (1-i)/sqrt2
+    constexpr T c = (T)cos16(4);
+    return cx<T>{(d.x + d.y) * c, (d.y - d.x) * c};
+  } else if constexpr (K == 12) {  // (-1-i)/sqrt2
+    constexpr T c = (T)cos16(4);
+    return cx<T>{(d.y - d.x) * c, -(d.x + d.y) * c};
+  } else {
+    constexpr T wr = (T)w32_re(K);
+    constexpr T wi = (T)w32_im(K);
+    return cx<T>{d.x * wr - d.y * wi, d.x * wi + d.y * wr};
+  }
+}
+
+// In-register radix-R DFT, decimation in frequency: natural order in, X[k] left in
+// a[bitrev(k, log2 R)].  R in {1, 2, 4, 8, 16, 32}.
+template <typename T, int R>
+PDSP_DEVICE void dif_butterfly(cx<T> (&a)[R]) {
+  constexpr int LR = ilog2(R);
+  static_for<0, LR>([&](auto st) {
+    constexpr int h = R >> (decltype(st)::value + 1);
+    static_for<0, R / 2>([&](auto bi) {
+      constexpr int g = (decltype(bi)::value / h) * 2 * h;
+      constexpr int i = decltype(bi)::value % h;
+      constexpr int K = i * 16 / h;
+      const cx<T> x = a[g + i];
+      const cx<T> y = a[g + i + h];
+      a[g + i] = cadd(x, y);
+      a[g + i + h] = mul_w32<K>(csub(x, y));
+    });
+  });
+}
+
+// How the threads of one frame synchronise around a shared-memory exchange.
+template <int TF>
+PDSP_DEVICE void frame_sync(int slot, int slots_per_cta) {
+  if constexpr (TF <= 32) {
+    simt::sync_warp();  // a frame never spans warps
+  } else {
+    if (slots_per_cta == 1)
+      simt::sync_block();
+    else
+      simt::sync_named(1 + slot, TF);
+  }
+}
+
+template <typename T, int LOG2M, int LOG2P, int MAXRB>
+struct FftEngine {
+  static_assert(LOG2P <= LOG2M, "points per thread cannot exceed the frame");
+  static_assert(MAXRB >= 1 && MAXRB <= 5, "radix 2..32");
+  static constexpr int M = 1 << LOG2M;
+  static constexpr int P = 1 << LOG2P;
+  static constexpr int TF = M / P;
+  static constexpr int RB = LOG2P == 0 ? 1 : (MAXRB < LOG2P ? MAXRB : LOG2P);  // log2 radix of a full pass
+  static constexpr int NPASS = LOG2M == 0 ? 0 : (LOG2M + RB - 1) / RB;
+  static constexpr int pass_bits(int i) { return i < NPASS - 1 ? RB : LOG2M - RB * (NPASS - 1); }
+  // one padding element per PAD_UNIT elements: stride of the first-pass scatter becomes odd
+  static constexpr int ROW = 128 / (int)sizeof(cx<T>);
+  static constexpr int PAD_UNIT = (1 << RB) > ROW ? (1 << RB) : ROW;
+  static constexpr int PAD_SHIFT = ilog2(PAD_UNIT);
+  static constexpr int SMEM_ELEMS = M + (M >> PAD_SHIFT) + 1;  // per frame slot
+  static constexpr bool NEEDS_SMEM = NPASS > 1;
+  PDSP_DEVICE static int pad(int i) { return i + (i >> PAD_SHIFT); }
+
+  // v[q] holds element t + TF*q (natural order) on entry and the transform on exit.
+  // tw: table exp(-2*pi*i*k/NT), NT = M * tw_stride.
+  PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int tw_stride,
+                              int slot, int slots_per_cta) {
+    static_for<0, NPASS>([&](auto pi) {
+      constexpr int pass = decltype(pi)::value;
+      constexpr int b = pass_bits(pass);
+      constexpr int R = 1 << b;
+      constexpr int BPT = P / R;  // butterflies per thread
+      constexpr int NSL = RB * pass;  // log2 Ns
+      constexpr int NS = 1 << NSL;
+      constexpr bool last = pass == NPASS - 1;
+      static_for<0, BPT>([&](auto ui) {
+        constexpr int u = decltype(ui)::value;
+        cx<T> a[R];
+        static_for<0, R>([&](auto s) { a[decltype(s)::value] = v[u + decltype(s)::value * BPT]; });
+        [[maybe_unused]] const int j = t + TF * u;
+        if constexpr (NSL > 0) {
+          const int r = j & (NS - 1);
+          // W_{Ns*R}^{s*r} = tw[s*r*(M/(Ns*R))*tw_stride]
+          const int step = r * ((M >> (NSL + b)) * tw_stride);
+          static_for<1, R>([&](auto s) {
+            const cx<T> w = ldg_cx(tw + decltype(s)::value * step);
+            a[decltype(s)::value] = cmul(a[decltype(s)::value], w);
+          });
+        }
+        dif_butterfly<T, R>(a);
+        if constexpr (last) {
+          static_for<0, R>([&](auto k) { v[u + decltype(k)::value * BPT] = a[bitrev(decltype(k)::value, b)]; });
+        } else {
+          const int base = ((j >> NSL) << (NSL + b)) + (j & (NS - 1));
+          static_for<0, R>(
+              [&](auto k) { sm[pad(base + (decltype(k)::value << NSL))] = a[bitrev(decltype(k)::value, b)]; });
+        }
+      });
+      if constexpr (!last) {
+        frame_sync<TF>(slot, slots_per_cta);
+        static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
+        frame_sync<TF>(slot, slots_per_cta);
+      }
+    });
+  }
+};
+
+}  // namespace pdsp

@@ -1,0 +1,374 @@
+// fft_kernels.cuh - the batched hot-path kernels built on FftEngine.
+//
+//   r2c_kernel : one launch = buildFrame (zero-pad/truncate, f32->compute widen) + applyWindow +
+//                Radix2Fft.forward on a real frame + magnitude/phase + amplitude scaling + findPeak
+//                i.e. the whole of spectrum() (/root/reference/src/public/spectrum.ts:107-142) and of
+//                Radix2Fft.forward (/root/reference/src/core/fft.ts:77-79) for a batch of frames.
+//                The N real samples are packed as M = N/2 complex points, transformed, and split
+//                with the Hermitian post-pass; the partner bin Z[M-k] comes from a warp shuffle
+//                when a frame fits a warp, from shared memory otherwise.
+//   c2c_kernel : Radix2Fft.forwardComplex / inverse (/root/reference/src/core/fft.ts:81-87) on planar
+//                (split real/imag) arrays - the reference's ComplexArray layout (:1-4).
+#pragma once
+#include "fft_core.cuh"
+
+namespace pdsp {
+
+enum : int { DT_F32 = 0, DT_F64 = 1 };
+
+template <typename T>
+struct PeakRec;
+template <>
+struct PeakRec<double> {  // 32 B
+  int32_t index;
+  int32_t pad;
+  double frequency, amplitude, phase;
+};
+template <>
+struct PeakRec<float> {  // 16 B
+  int32_t index;
+  float frequency, amplitude, phase;
+};
+
+struct R2CParams {
+  // input: frame f starts at samples + f*hop (elements), frame_len samples are valid
+  const void* samples;
+  int sample_dtype;  // DT_F32 / DT_F64
+  int vec_ok;        // pairs (2e, 2e+1) may be loaded as one aligned vector
+  int frame_len;
+  long long hop;
+  long long batch;
+  const void* window;  // T[N] or nullptr (rect)
+  const void* tw;      // cx<T>[N]: exp(-2*pi*i*k/N)
+  const void* post;    // cx<T>[M/2+1]: (wi/2, -wr/2) of W_N^k
+  // outputs, any may be null.  All in T.
+  void* out_re;  // complex spectrum, planar; pitch = cbins
+  void* out_im;
+  int cfull;     // 1: all N bins (mirror written as conjugate), 0: N/2+1 bins
+  void* amp;     // |X| * scale; pitch = bins
+  void* phase;   // atan2(im, re); pitch = bins
+  void* peaks;   // PeakRec<T>[batch]
+  int two_sided;      // bins = N (mirror bins written) else N/2+1
+  double scale_edge;  // amplitude scale of DC and Nyquist
+  double scale_mid;   // amplitude scale of every other bin
+  double bin_hz;      // sampleRate / N
+};
+
+struct C2CParams {
+  const void* in_re;  // T planar, frame stride N; in_im may be null (zero imaginary plane)
+  const void* in_im;
+  void* out_re;
+  void* out_im;
+  long long batch;
+  const void* tw;  // cx<T>[N]
+  int inverse;     // conjugate transform and multiply by 1/N
+};
+
+template <typename T>
+PDSP_DEVICE T t_sqrt(T v);
+template <>
+PDSP_DEVICE float t_sqrt<float>(float v) {
+  return sqrtf(v);
+}
+template <>
+PDSP_DEVICE double t_sqrt<double>(double v) {
+  return sqrt(v);
+}
+PDSP_DEVICE_NOINLINE float t_atan2(float y, float x) { return atan2f(y, x); }
+PDSP_DEVICE_NOINLINE double t_atan2(double y, double x) { return atan2(y, x); }
+PDSP_DEVICE_NOINLINE float t_hypot_slow(float x, float y) { return hypotf(x, y); }
+PDSP_DEVICE_NOINLINE double t_hypot_slow(double x, double y) { return hypot(x, y); }
+
+// |re + i*im|: sqrt(re^2+im^2), falling back to hypot() when the sum of squares leaves the
+// comfortably-normal range (0, subnormal, huge, inf/nan) so extreme inputs behave like Math.hypot.
+PDSP_DEVICE double t_mag(double re, double im) {
+  const double s = re * re + im * im;
+  const unsigned hi = (unsigned)__double2hiint(s);
+  if ((hi - 0x00400000u) >= (0x7fd00000u - 0x00400000u)) return t_hypot_slow(re, im);
+  return t_sqrt<double>(s);
+}
+PDSP_DEVICE float t_mag(float re, float im) {
+  const float s = re * re + im * im;
+  const unsigned b = (unsigned)__float_as_int(s);
+  if ((b - 0x01000000u) >= (0x7e800000u - 0x01000000u)) return t_hypot_slow(re, im);
+  return t_sqrt<float>(s);
+}
+
+template <typename T>
+struct PeakCand {
+  T v;     // scaled amplitude of the best non-DC bin so far (0 = none)
+  int k;   // its bin (0 = none)
+  T re, im;
+};
+
+// findPeak ordering (/root/reference/src/public/spectrum.ts:74-105): strict '>' scanning upward,
+// so among equal values the lowest index wins; a candidate needs v > 0; NaN never wins.
+template <typename T>
+PDSP_DEVICE bool peak_better(T v, int k, T bv, int bk) {
+  return (v > bv) || (v == bv && v > (T)0 && k < bk);
+}
+
+template <typename T, int LOG2M, int LOG2P, int MAXRB, bool PHASE, int THREADS>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
+  using E = FftEngine<T, LOG2M, LOG2P, MAXRB>;
+  constexpr int M = E::M, P = E::P, TF = E::TF, N = 2 * M;
+  constexpr int SLOTS = THREADS / TF;
+  static_assert(THREADS % TF == 0 && SLOTS >= 1, "CTA must hold whole frames");
+  constexpr bool POST_SMEM = TF > 32;  // partner bin via shared memory instead of shuffle
+  constexpr int SLOT_ELEMS = (E::NEEDS_SMEM || POST_SMEM) ? E::SMEM_ELEMS : 0;
+
+  const int tid = simt::tid();
+  const int slot = tid / TF;
+  const int t = tid % TF;
+  cx<T>* sm = reinterpret_cast<cx<T>*>(simt::smem()) + (size_t)slot * SLOT_ELEMS;
+  const cx<T>* PDSP_RESTRICT tw = static_cast<const cx<T>*>(p.tw);
+  const cx<T>* PDSP_RESTRICT post = static_cast<const cx<T>*>(p.post);
+  const T* PDSP_RESTRICT win = static_cast<const T*>(p.window);
+  const int lim = p.frame_len < N ? p.frame_len : N;
+  const int bins = p.two_sided ? N : M + 1;
+  const int cbins = p.cfull ? N : M + 1;
+  const T s_edge = (T)p.scale_edge, s_mid = (T)p.scale_mid;
+  const bool want_cplx = p.out_re != nullptr;
+  const bool want_amp = p.amp != nullptr;
+  const bool want_peak = p.peaks != nullptr;
+  const bool need_mag = want_amp || want_peak;
+
+  for (long long f0 = (long long)simt::bid() * SLOTS; f0 < p.batch; f0 += (long long)simt::nblocks() * SLOTS) {
+    const long long f = f0 + slot;
+    const bool valid = f < p.batch;
+
+    // ---- buildFrame + applyWindow fused into the load (spectrum.ts:36-43, fourier.ts:54-67)
+    cx<T> v[P];
+    {
+      const long long base = valid ? f * p.hop : 0;
+      const int lim_f = valid ? lim : 0;
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        const int i0 = 2 * (t + TF * q);
+        T x0 = (T)0, x1 = (T)0;
+        if (p.sample_dtype == DT_F32) {
+          const float* s = static_cast<const float*>(p.samples) + base;
+          if (p.vec_ok && i0 + 1 < lim_f) {
+            const cx<float> pr = *reinterpret_cast<const cx<float>*>(s + i0);
+            x0 = (T)pr.x;
+            x1 = (T)pr.y;
+          } else {
+            if (i0 < lim_f) x0 = (T)s[i0];
+            if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
+          }
+        } else {
+          const double* s = static_cast<const double*>(p.samples) + base;
+          if (p.vec_ok && i0 + 1 < lim_f) {
+            const cx<double> pr = *reinterpret_cast<const cx<double>*>(s + i0);
+            x0 = (T)pr.x;
+            x1 = (T)pr.y;
+          } else {
+            if (i0 < lim_f) x0 = (T)s[i0];
+            if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
+          }
+        }
+        if (win != nullptr) {
+          const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win + i0));
+          x0 *= w.x;
+          x1 *= w.y;
+        }
+        v[q] = cx<T>{x0, x1};
+      });
+    }
+
+    // ---- M-point complex FFT of the packed frame
+    E::fft(v, t, sm, tw, 2, slot, SLOTS);
+
+    // ---- Hermitian split + fused epilogue
+    T* o_re = valid && want_cplx ? static_cast<T*>(p.out_re) + f * cbins : nullptr;
+    T* o_im = valid && want_cplx ? static_cast<T*>(p.out_im) + f * cbins : nullptr;
+    T* o_amp = valid && want_amp ? static_cast<T*>(p.amp) + f * bins : nullptr;
+    T* o_ph = valid && PHASE && p.phase != nullptr ? static_cast<T*>(p.phase) + f * bins : nullptr;
+    PeakCand<T> best{(T)0, 0, (T)0, (T)0};
+    T dc_re = (T)0, dc_amp = (T)0;
+
+    // emit one bin k in [0, M] with value X
+    auto emit = [&](int k, cx<T> X) {
+      if (o_re != nullptr) {
+        o_re[k] = X.x;
+        o_im[k] = X.y;
+        if (p.cfull && k != 0 && k != M) {
+          o_re[N - k] = X.x;
+          o_im[N - k] = -X.y;
+        }
+      }
+      if (need_mag) {
+        const T a = t_mag(X.x, X.y) * ((k == 0 || k == M) ? s_edge : s_mid);
+        if (o_amp != nullptr) {
+          o_amp[k] = a;
+          if (p.two_sided && k != 0 && k != M) o_amp[N - k] = a;
+        }
+        if (k == 0) {
+          dc_re = X.x;
+          dc_amp = a;
+        } else if (peak_better(a, k, best.v, best.k)) {
+          best.v = a;
+          best.k = k;
+          best.re = X.x;
+          best.im = X.y;
+        }
+      }
+      if constexpr (PHASE) {
+        if (o_ph != nullptr) {
+          const T ph = t_atan2(X.y, X.x);
+          o_ph[k] = ph;
+          if (p.two_sided && k != 0 && k != M) o_ph[N - k] = -ph;
+        }
+      }
+    };
+
+    if constexpr (M == 1) {
+      // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
+      emit(0, cx<T>{v[0].x + v[0].y, (T)0});
+      emit(1, cx<T>{v[0].x - v[0].y, (T)0});
+    } else {
+      if constexpr (POST_SMEM) {
+        static_for<0, P>([&](auto q) { sm[E::pad(t + TF * decltype(q)::value)] = v[decltype(q)::value]; });
+        frame_sync<TF>(slot, SLOTS);
+      }
+      static_for<0, P / 2>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        const int k = t + TF * q;  // 0 <= k < M/2
+        cx<T> zp;                  // Z[(M - k) % M]
+        if constexpr (POST_SMEM) {
+          zp = sm[E::pad((M - k) & (M - 1))];
+        } else if constexpr (TF == 1) {
+          zp = v[(P - q) % P];
+        } else {
+          const cx<T> mine = v[P - 1 - q];
+          cx<T> got;
+          got.x = simt::shfl(mine.x, (TF - t) & (TF - 1), TF);
+          got.y = simt::shfl(mine.y, (TF - t) & (TF - 1), TF);
+          zp = (t == 0) ? v[(P - q) % P] : got;
+        }
+        const cx<T> a = v[q];
+        const cx<T> sum{a.x + zp.x, a.y - zp.y};   // A + conj(Zp)
+        const cx<T> dif{a.x - zp.x, a.y + zp.y};   // A - conj(Zp)
+        const cx<T> w = ldg_cx(post + k);        // (wi/2, -wr/2): W_N^k * (-i/2)
+        const cx<T> tt = cmul(dif, w);
+        cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};           // X[k]
+        cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};        // X[M-k] = conj(E - W*O)
+        if constexpr (q == 0) {
+          // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
+          // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
+          if (t == 0) {
+            xa.y = (T)0;
+            xb.y = (T)0;
+          }
+        }
+        emit(k, xa);
+        emit(M - k, xb);
+      });
+      if (t == 0) emit(M / 2, cx<T>{v[P / 2].x, -v[P / 2].y});  // self-paired bin: conj(Z[M/2])
+      if constexpr (POST_SMEM) frame_sync<TF>(slot, SLOTS);  // partner reads done before smem is reused
+    }
+
+    // ---- findPeak: (value desc, index asc) reduction over the frame's threads
+    if (want_peak) {
+      T bv = best.v;
+      int bk = best.k;
+      constexpr int W = TF < 32 ? TF : 32;
+      PDSP_UNROLL
+      for (int m = W / 2; m >= 1; m >>= 1) {
+        const T ov = simt::shfl_xor(bv, m, W);
+        const int ok = simt::shfl_xor(bk, m, W);
+        if (peak_better(ov, ok, bv, bk)) {
+          bv = ov;
+          bk = ok;
+        }
+      }
+      if constexpr (TF > 32) {
+        // cross-warp stage through shared memory (reuses the exchange buffer)
+        constexpr int NW = TF / 32;
+        T* rv = reinterpret_cast<T*>(sm);
+        int* rk = reinterpret_cast<int*>(rv + NW);
+        if ((t & 31) == 0) {
+          rv[t >> 5] = bv;
+          rk[t >> 5] = bk;
+        }
+        frame_sync<TF>(slot, SLOTS);
+        bv = rv[0];
+        bk = rk[0];
+        for (int w = 1; w < NW; ++w) {
+          const T ov = rv[w];
+          const int ok = rk[w];
+          if (peak_better(ov, ok, bv, bk)) {
+            bv = ov;
+            bk = ok;
+          }
+        }
+        frame_sync<TF>(slot, SLOTS);
+      }
+      // the thread that owns the winning bin writes the record; no non-DC bin > 0 -> bin 0
+      const bool owner = bk != 0 ? (best.k == bk) : (t == 0);
+      if (valid && owner) {
+        PeakRec<T> rec;
+        rec.index = bk;
+        rec.frequency = (T)((double)bk * p.bin_hz);
+        if (bk != 0) {
+          rec.amplitude = best.v;
+          rec.phase = t_atan2(best.im, best.re);
+        } else {
+          rec.amplitude = dc_amp;
+          rec.phase = t_atan2((T)0, dc_re);
+        }
+        if constexpr (sizeof(T) == 8) rec.pad = 0;
+        static_cast<PeakRec<T>*>(p.peaks)[f] = rec;
+      }
+    }
+  }
+}
+
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) c2c_kernel(const C2CParams p) {
+  using E = FftEngine<T, LOG2M, LOG2P, MAXRB>;
+  constexpr int M = E::M, P = E::P, TF = E::TF;
+  constexpr int SLOTS = THREADS / TF;
+  static_assert(THREADS % TF == 0 && SLOTS >= 1, "CTA must hold whole frames");
+  constexpr int SLOT_ELEMS = E::NEEDS_SMEM ? E::SMEM_ELEMS : 0;
+  const int tid = simt::tid();
+  const int slot = tid / TF;
+  const int t = tid % TF;
+  cx<T>* sm = reinterpret_cast<cx<T>*>(simt::smem()) + (size_t)slot * SLOT_ELEMS;
+  const cx<T>* PDSP_RESTRICT tw = static_cast<const cx<T>*>(p.tw);
+  const T scale = (T)(1.0 / (double)M);
+
+  for (long long f0 = (long long)simt::bid() * SLOTS; f0 < p.batch; f0 += (long long)simt::nblocks() * SLOTS) {
+    const long long f = f0 + slot;
+    const bool valid = f < p.batch;
+    cx<T> v[P];
+    const T* ire = static_cast<const T*>(p.in_re) + (valid ? f * M : 0);
+    const T* iim = p.in_im != nullptr ? static_cast<const T*>(p.in_im) + (valid ? f * M : 0) : nullptr;
+    static_for<0, P>([&](auto qi) {
+      constexpr int q = decltype(qi)::value;
+      const int e = t + TF * q;
+      const T re = valid ? ire[e] : (T)0;
+      const T im = (valid && iim != nullptr) ? iim[e] : (T)0;
+      // inverse = swap(FFT(swap(x))) / N
+      v[q] = p.inverse ? cx<T>{im, re} : cx<T>{re, im};
+    });
+    E::fft(v, t, sm, tw, 1, slot, SLOTS);
+    if (valid) {
+      T* ore = static_cast<T*>(p.out_re) + f * M;
+      T* oim = static_cast<T*>(p.out_im) + f * M;
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        const int e = t + TF * q;
+        if (p.inverse) {
+          ore[e] = v[q].y * scale;
+          oim[e] = v[q].x * scale;
+        } else {
+          ore[e] = v[q].x;
+          oim[e] = v[q].y;
+        }
+      });
+    }
+  }
+}
+
+}  // namespace pdsp

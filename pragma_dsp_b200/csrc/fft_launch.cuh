@@ -1,0 +1,92 @@
+// fft_launch.cuh - per-size kernel configuration and persistent-grid launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fft_config.h"
+#include "fft_kernels.cuh"
+
+namespace pdsp {
+
+struct LaunchCtx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+};
+
+constexpr int kMaxDevices = 16;
+
+template <typename KernelT>
+inline cudaError_t persistent_grid(KernelT kern, int threads, size_t smem, const LaunchCtx& lc, int* bps_cache,
+                                   long long groups, int* grid_out) {
+  if (lc.device < 0 || lc.device >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (bps_cache[lc.device] == 0) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    int bps = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (bps < 1) return cudaErrorLaunchOutOfResources;
+    bps_cache[lc.device] = bps;
+  }
+  long long cap = (long long)bps_cache[lc.device] * lc.sm_count;
+  *grid_out = (int)(groups < cap ? groups : cap);
+  return cudaSuccess;
+}
+
+template <typename T, int LOG2M, bool PHASE>
+cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
+  using C = KCfg<T, LOG2M>;
+  using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
+  constexpr int THREADS = C::THREADS;
+  constexpr int SLOTS = THREADS / E::TF;
+  constexpr bool POST_SMEM = E::TF > 32;
+  constexpr size_t SMEM = (E::NEEDS_SMEM || POST_SMEM) ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
+  auto kern = r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, PHASE, THREADS>;
+  static int bps[kMaxDevices] = {0};
+  if (p.batch <= 0) return cudaSuccess;
+  int grid = 0;
+  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, THREADS, SMEM, lc.stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <typename T, int LOG2M>
+cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
+  using C = KCfg<T, LOG2M>;
+  using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
+  constexpr int THREADS = C::THREADS;
+  constexpr int SLOTS = THREADS / E::TF;
+  constexpr size_t SMEM = E::NEEDS_SMEM ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
+  auto kern = c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS>;
+  static int bps[kMaxDevices] = {0};
+  if (p.batch <= 0) return cudaSuccess;
+  int grid = 0;
+  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, THREADS, SMEM, lc.stream>>>(p);
+  return cudaGetLastError();
+}
+
+// One translation unit instantiates a contiguous range [LO, HI] of sizes (see inst.cu).
+template <typename T, int L, int LO, int HI>
+cudaError_t r2c_case(bool phase, const R2CParams& p, const LaunchCtx& lc) {
+  if constexpr (L >= LO && L <= HI)
+    return phase ? launch_r2c_t<T, L, true>(p, lc) : launch_r2c_t<T, L, false>(p, lc);
+  else
+    return cudaErrorInvalidValue;
+}
+template <typename T, int L, int LO, int HI>
+cudaError_t c2c_case(const C2CParams& p, const LaunchCtx& lc) {
+  if constexpr (L >= LO && L <= HI)
+    return launch_c2c_t<T, L>(p, lc);
+  else
+    return cudaErrorInvalidValue;
+}
+
+typedef cudaError_t (*r2c_group_fn)(int log2m, bool phase, const R2CParams& p, const LaunchCtx& lc);
+typedef cudaError_t (*c2c_group_fn)(int log2m, const C2CParams& p, const LaunchCtx& lc);
+
+}  // namespace pdsp

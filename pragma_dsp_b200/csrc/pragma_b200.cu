@@ -1,0 +1,849 @@
+// pragma_b200.cu - C ABI (include/pragma_b200.h): contexts, plans, staging pipeline, dispatch.
+//
+// Host-side responsibilities only: validate, build tables once per plan (K3: twiddles
+// /root/reference/src/core/fft.ts:45-61 and windows src/xform/fourier.ts:14-52 are per-plan
+// constants, computed in extended precision on the host and uploaded), move bytes between
+// caller memory and HBM through pinned staging on two streams, and launch the kernels in
+// fft_kernels.cuh.  There is no CPU implementation of the transform in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pragma_b200.h"
+#include "fft_launch.cuh"
+#include "inst_groups.h"
+
+#define PDSP_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace pdsp {
+// launchers defined in the inst.cu translation units
+#define X(kind, tag, ctype, lo, hi) PDSP_DECL_##kind(tag, lo, hi)
+#define PDSP_DECL_0(tag, lo, hi) \
+  cudaError_t launch_r2c_##tag##_##lo##_##hi(int, bool, const R2CParams&, const LaunchCtx&);
+#define PDSP_DECL_1(tag, lo, hi) cudaError_t launch_c2c_##tag##_##lo##_##hi(int, const C2CParams&, const LaunchCtx&);
+PDSP_GROUPS(X)
+#undef X
+
+static cudaError_t dispatch_r2c(bool f64, int log2m, bool phase, const R2CParams& p, const LaunchCtx& lc) {
+#define X(kind, tag, ctype, lo, hi) PDSP_TRY_R_##kind(tag, ctype, lo, hi)
+#define PDSP_TRY_R_0(tag, ctype, lo, hi)                                   \
+  if (f64 == (sizeof(ctype) == 8) && log2m >= lo && log2m <= hi)           \
+    return launch_r2c_##tag##_##lo##_##hi(log2m, phase, p, lc);
+#define PDSP_TRY_R_1(tag, ctype, lo, hi)
+  PDSP_GROUPS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+static cudaError_t dispatch_c2c(bool f64, int log2m, const C2CParams& p, const LaunchCtx& lc) {
+#define X(kind, tag, ctype, lo, hi) PDSP_TRY_C_##kind(tag, ctype, lo, hi)
+#define PDSP_TRY_C_0(tag, ctype, lo, hi)
+#define PDSP_TRY_C_1(tag, ctype, lo, hi)                                   \
+  if (f64 == (sizeof(ctype) == 8) && log2m >= lo && log2m <= hi)           \
+    return launch_c2c_##tag##_##lo##_##hi(log2m, p, lc);
+  PDSP_GROUPS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// ---- small elementwise kernels: magnitude()/phase() on caller arrays, N = 1 frames ----------
+__global__ void k_magnitude(const double* __restrict__ re, const double* __restrict__ im, long long n,
+                            double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = hypot(re[i], im[i]);
+}
+__global__ void k_phase(const double* __restrict__ re, const double* __restrict__ im, long long n,
+                        double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = atan2(im[i], re[i]);
+}
+// N = 1: X[0] = x[0] * w[0] (createWindow(size 1) = [1]); one thread per frame
+template <typename T>
+__global__ void k_r2c_n1(const R2CParams p) {
+  for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < p.batch;
+       f += (long long)gridDim.x * blockDim.x) {
+    T x = (T)0;
+    if (p.frame_len >= 1)
+      x = p.sample_dtype == DT_F32 ? (T) static_cast<const float*>(p.samples)[f * p.hop]
+                                   : (T) static_cast<const double*>(p.samples)[f * p.hop];
+    if (p.out_re) {
+      static_cast<T*>(p.out_re)[f] = x;
+      static_cast<T*>(p.out_im)[f] = (T)0;
+    }
+    const T a = fabs(x) * (T)p.scale_edge;
+    const T ph = atan2((T)0, x);
+    if (p.amp) static_cast<T*>(p.amp)[f] = a;
+    if (p.phase) static_cast<T*>(p.phase)[f] = ph;
+    if (p.peaks) {
+      PeakRec<T> r;
+      memset(&r, 0, sizeof(r));
+      r.index = 0;
+      r.frequency = (T)0;
+      r.amplitude = a;
+      r.phase = ph;
+      static_cast<PeakRec<T>*>(p.peaks)[f] = r;
+    }
+  }
+}
+}  // namespace pdsp
+
+using namespace pdsp;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = std::string("pragma-dsp/b200: ") + buf;
+  return 1;
+}
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) return fail("%s: %s", #call, cudaGetErrorString(e_));         \
+  } while (0)
+
+// ------------------------------------------------------------------------------ objects
+static const int kSlots = 3;  // staging pipeline depth (chunks in flight)
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  void* d_in = nullptr;
+  size_t d_in_cap = 0;
+  void* d_out = nullptr;
+  size_t d_out_cap = 0;
+  void* h_in = nullptr;
+  size_t h_in_cap = 0;
+  void* h_out = nullptr;
+  size_t h_out_cap = 0;
+  // pending copy-out of a pageable destination: (dst, src in h_out, bytes)
+  struct Flush {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<Flush> flush;
+  bool busy = false;
+};
+
+struct pdsp_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  Slot slots[kSlots];
+  std::mutex mu;
+  std::map<std::pair<int, int>, pdsp_plan*> plans;
+  std::atomic<long long> launches{0};
+};
+
+struct pdsp_plan {
+  pdsp_ctx* ctx;
+  int n;
+  int log2n;
+  int precision;
+  void* d_tw = nullptr;    // cx<T>[n]
+  void* d_post = nullptr;  // cx<T>[n/4 + 1]
+  void* d_win[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+static int set_device(const pdsp_ctx* c) {
+  CU(cudaSetDevice(c->device));
+  return 0;
+}
+
+static int ensure(void** p, size_t* cap, size_t need, bool host) {
+  if (*cap >= need) return 0;
+  if (*p) {
+    if (host)
+      CU(cudaFreeHost(*p));
+    else
+      CU(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+  }
+  size_t sz = need + need / 4 + 256;
+  if (host)
+    CU(cudaHostAlloc(p, sz, cudaHostAllocDefault));
+  else
+    CU(cudaMalloc(p, sz));
+  *cap = sz;
+  return 0;
+}
+
+static bool is_device_visible(const void* p) {
+  // true when `p` can be the source/target of an async DMA without staging (pinned or registered host memory)
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// exp(-2*pi*i*k/n) with exact values on the axes and octant symmetry, evaluated in long double
+static void twiddle(int k, int n, long double* re, long double* im) {
+  // reduce k/n to the first octant
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  int q = (int)(((long long)k * 8) / n);  // octant 0..7
+  long long kk = k;
+  auto cs = [&](long long j, long double* c, long double* s) {  // angle 2*pi*j/n, 0 <= j <= n/8
+    if (j == 0) {
+      *c = 1.0L;
+      *s = 0.0L;
+    } else if (8 * j == n) {
+      *c = *s = 0.707106781186547524400844362104849039L;
+    } else {
+      long double a = two_pi * (long double)j / (long double)n;
+      *c = cosl(a);
+      *s = sinl(a);
+    }
+  };
+  long double c, s;  // cos/sin of the positive angle theta = 2*pi*k/n
+  switch (q) {
+    case 0: cs(kk, &c, &s); break;
+    case 1: { long double a, b; cs(n / 4 - kk, &a, &b); c = b; s = a; } break;
+    case 2: { long double a, b; cs(kk - n / 4, &a, &b); c = -b; s = a; } break;
+    case 3: { long double a, b; cs(n / 2 - kk, &a, &b); c = -a; s = b; } break;
+    case 4: { long double a, b; cs(kk - n / 2, &a, &b); c = -a; s = -b; } break;
+    case 5: { long double a, b; cs(3 * (long long)n / 4 - kk, &a, &b); c = -b; s = -a; } break;
+    case 6: { long double a, b; cs(kk - 3 * (long long)n / 4, &a, &b); c = b; s = -a; } break;
+    default: { long double a, b; cs(n - kk, &a, &b); c = a; s = -b; } break;
+  }
+  *re = c;
+  *im = -s;
+}
+
+template <typename T>
+static int upload_tables(pdsp_plan* pl) {
+  const int n = pl->n;
+  std::vector<cx<T>> tw((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    long double re, im;
+    if (n >= 8) {
+      twiddle(k, n, &re, &im);
+    } else {  // n = 1, 2, 4: axis points only
+      static const long double c4[4] = {1, 0, -1, 0}, s4[4] = {0, -1, 0, 1};
+      int idx = k * (4 / n);
+      re = c4[idx];
+      im = s4[idx];
+    }
+    tw[k] = cx<T>{(T)re, (T)im};
+  }
+  const int m = n / 2;
+  const int np = m / 2 + 1;
+  std::vector<cx<T>> post((size_t)np);
+  for (int k = 0; k < np; ++k) {
+    long double re = 1, im = 0;
+    if (n >= 8) {
+      twiddle(k, n, &re, &im);
+    } else if (n == 4) {
+      static const long double c4[4] = {1, 0, -1, 0}, s4[4] = {0, -1, 0, 1};
+      re = c4[k];
+      im = s4[k];
+    }
+    post[k] = cx<T>{(T)(im / 2), (T)(-re / 2)};
+  }
+  CU(cudaMalloc(&pl->d_tw, sizeof(cx<T>) * (size_t)n));
+  CU(cudaMalloc(&pl->d_post, sizeof(cx<T>) * (size_t)np));
+  CU(cudaMemcpy(pl->d_tw, tw.data(), sizeof(cx<T>) * (size_t)n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(pl->d_post, post.data(), sizeof(cx<T>) * (size_t)np, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int window_host(int window, int size, double* out) {
+  // src/xform/fourier.ts:14-52, same formulas and operation order, binary64
+  if (size <= 0) return fail("Window size must be positive, got %d", size);
+  if (window < 0 || window > 3) return fail("Unsupported window type: %d", window);
+  if (size == 1) {
+    out[0] = 1.0;
+    return 0;
+  }
+  const double pi = 3.141592653589793;
+  for (int i = 0; i < size; ++i) {
+    const double f = (2 * pi * i) / (size - 1);
+    switch (window) {
+      case PDSP_WIN_RECT: out[i] = 1.0; break;
+      case PDSP_WIN_HANN: out[i] = 0.5 * (1 - cos(f)); break;
+      case PDSP_WIN_HAMMING: out[i] = 0.54 - 0.46 * cos(f); break;
+      default: out[i] = 0.42 - 0.5 * cos(f) + 0.08 * cos(2 * f); break;
+    }
+  }
+  return 0;
+}
+
+static int plan_window(pdsp_plan* pl, int window, const void** d_win) {
+  if (window < 0 || window > 3) return fail("Unsupported window type: %d", window);
+  if (window == PDSP_WIN_RECT) {  // multiply by 1 is skipped in the kernel
+    *d_win = nullptr;
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  if (!pl->d_win[window]) {
+    std::vector<double> w((size_t)pl->n);
+    if (window_host(window, pl->n, w.data())) return 1;
+    void* d = nullptr;
+    if (pl->precision == PDSP_F64) {
+      CU(cudaMalloc(&d, sizeof(double) * w.size()));
+      CU(cudaMemcpy(d, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice));
+    } else {
+      std::vector<float> wf(w.begin(), w.end());
+      CU(cudaMalloc(&d, sizeof(float) * wf.size()));
+      CU(cudaMemcpy(d, wf.data(), sizeof(float) * wf.size(), cudaMemcpyHostToDevice));
+    }
+    pl->d_win[window] = d;
+  }
+  *d_win = pl->d_win[window];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ kernel launches
+static size_t esize(int dtype) { return dtype == PDSP_F64 ? 8 : 4; }
+
+struct SpecGeom {
+  int n, bins;
+  size_t in_elems_per_frame_stride;  // hop
+  size_t out_esize, peak_size;
+};
+
+static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, long long batch,
+                           void* d_amp, void* d_phase, void* d_peaks, void* d_cre, void* d_cim, int cfull,
+                           cudaStream_t st) {
+  pdsp_ctx* c = pl->ctx;
+  const int n = pl->n;
+  R2CParams p;
+  memset(&p, 0, sizeof p);
+  p.samples = d_samples;
+  p.sample_dtype = d->sample_dtype == PDSP_F64 ? DT_F64 : DT_F32;
+  const size_t es = esize(d->sample_dtype);
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(d_samples) % (2 * es)) == 0 && (d->hop % 2) == 0) ? 1 : 0;
+  p.frame_len = d->frame_len;
+  p.hop = d->hop;
+  p.batch = batch;
+  const void* win = nullptr;
+  if (plan_window(pl, d->window, &win)) return 1;
+  p.window = win;
+  p.tw = pl->d_tw;
+  p.post = pl->d_post;
+  p.out_re = d_cre;
+  p.out_im = d_cim;
+  p.cfull = cfull;
+  p.amp = d_amp;
+  p.phase = d_phase;
+  p.peaks = d_peaks;
+  p.two_sided = d->sides == PDSP_SIDES_TWO;
+  if (d->raw_magnitude) {
+    p.scale_edge = p.scale_mid = 1.0;
+  } else if (p.two_sided) {
+    p.scale_edge = p.scale_mid = 1.0 / (double)n;  // mag / size (spectrum.ts:63-72), exact for 2^k
+  } else {
+    p.scale_edge = 1.0 / (double)n;  // mag / size for DC and Nyquist (spectrum.ts:52-55)
+    p.scale_mid = 2.0 / (double)n;   // (2 * mag) / size, identical bits for power-of-two size
+  }
+  p.bin_hz = d->sample_rate / (double)n;  // binFrequencies: quotient first (fourier.ts:160)
+  LaunchCtx lc{c->device, c->sm_count, st};
+  cudaError_t e;
+  if (n == 1) {
+    const int threads = 128;
+    long long blocks = (batch + threads - 1) / threads;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (pl->precision == PDSP_F64)
+      k_r2c_n1<double><<<(int)blocks, threads, 0, st>>>(p);
+    else
+      k_r2c_n1<float><<<(int)blocks, threads, 0, st>>>(p);
+    e = cudaGetLastError();
+  } else {
+    e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, d_phase != nullptr, p, lc);
+  }
+  if (e != cudaSuccess) return fail("r2c launch (n=%d): %s", n, cudaGetErrorString(e));
+  c->launches++;
+  return 0;
+}
+
+static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
+                      int inverse, cudaStream_t st) {
+  pdsp_ctx* c = pl->ctx;
+  if (pl->log2n > kMaxLog2M)
+    return fail("complex transforms above %d points are not supported by the in-CTA path", 1 << kMaxLog2M);
+  C2CParams p;
+  memset(&p, 0, sizeof p);
+  p.in_re = d_re;
+  p.in_im = d_im;
+  p.out_re = d_ore;
+  p.out_im = d_oim;
+  p.batch = batch;
+  p.tw = pl->d_tw;
+  p.inverse = inverse;
+  LaunchCtx lc{c->device, c->sm_count, st};
+  cudaError_t e = dispatch_c2c(pl->precision == PDSP_F64, pl->log2n, p, lc);
+  if (e != cudaSuccess) return fail("c2c launch (n=%d): %s", pl->n, cudaGetErrorString(e));
+  c->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ staging pipeline
+// Moves `chunks` pieces of a host job through HBM: H2D (direct DMA when the caller's memory is
+// pinned, through the slot's pinned buffer otherwise), kernel, D2H, on kSlots streams so the
+// copies of neighbouring chunks overlap the kernel.
+struct HostIO {
+  const void* src;  // host input for this chunk
+  size_t src_bytes;
+  struct Out {
+    void* dst;
+    size_t bytes;
+    size_t d_off;  // offset inside slot.d_out
+  };
+  Out outs[4];
+  int n_outs;
+};
+
+static int slot_wait(Slot& s) {
+  if (!s.busy) return 0;
+  CU(cudaEventSynchronize(s.done));
+  for (auto& f : s.flush) memcpy(f.dst, f.src, f.bytes);
+  s.flush.clear();
+  s.busy = false;
+  return 0;
+}
+
+static int slot_in(Slot& s, const void* src, size_t bytes, bool src_pinned, size_t d_extra = 0) {
+  if (ensure(&s.d_in, &s.d_in_cap, bytes + d_extra, false)) return 1;
+  if (bytes == 0) return 0;
+  if (src_pinned) {
+    CU(cudaMemcpyAsync(s.d_in, src, bytes, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    if (ensure(&s.h_in, &s.h_in_cap, bytes, true)) return 1;
+    memcpy(s.h_in, src, bytes);
+    CU(cudaMemcpyAsync(s.d_in, s.h_in, bytes, cudaMemcpyHostToDevice, s.stream));
+  }
+  return 0;
+}
+
+static int slot_out(Slot& s, const HostIO::Out* outs, int n, const bool* pinned) {
+  size_t stage = 0;
+  for (int i = 0; i < n; ++i)
+    if (!pinned[i]) stage += (outs[i].bytes + 255) & ~(size_t)255;
+  if (stage && ensure(&s.h_out, &s.h_out_cap, stage, true)) return 1;
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (outs[i].bytes == 0) continue;
+    const char* dsrc = static_cast<const char*>(s.d_out) + outs[i].d_off;
+    if (pinned[i]) {
+      CU(cudaMemcpyAsync(outs[i].dst, dsrc, outs[i].bytes, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      char* h = static_cast<char*>(s.h_out) + off;
+      CU(cudaMemcpyAsync(h, dsrc, outs[i].bytes, cudaMemcpyDeviceToHost, s.stream));
+      s.flush.push_back({outs[i].dst, h, outs[i].bytes});
+      off += (outs[i].bytes + 255) & ~(size_t)255;
+    }
+  }
+  CU(cudaEventRecord(s.done, s.stream));
+  s.busy = true;
+  return 0;
+}
+
+static int drain(pdsp_ctx* c) {
+  for (int i = 0; i < kSlots; ++i)
+    if (slot_wait(c->slots[i])) return 1;
+  return 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static long long pick_chunk(long long batch, size_t bytes_per_frame) {
+  // ~24 MB of traffic per chunk keeps three chunks in flight without hoarding HBM or pinned memory
+  const size_t target = 24u << 20;
+  long long c = (long long)(target / (bytes_per_frame ? bytes_per_frame : 1));
+  if (c < 1) c = 1;
+  if (c > batch) c = batch;
+  // small jobs: still split in two so H2D of the second half overlaps the first kernel
+  return c;
+}
+
+// ------------------------------------------------------------------------------ C ABI
+PDSP_EXPORT int pdsp_abi_version(void) { return PDSP_ABI_VERSION; }
+PDSP_EXPORT const char* pdsp_last_error(void) { return g_err.c_str(); }
+
+PDSP_EXPORT int pdsp_device_count(int* count) {
+  if (!count) return fail("null argument");
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_ctx_create(int device, pdsp_ctx** out) {
+  if (!out) return fail("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail("no CUDA device available (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev || device >= kMaxDevices) return fail("device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail("device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+  pdsp_ctx* c = new pdsp_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < kSlots; ++i) {
+    CU(cudaStreamCreateWithFlags(&c->slots[i].stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming));
+  }
+  *out = c;
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
+  if (!c) return 0;
+  if (set_device(c)) return 1;
+  cudaDeviceSynchronize();
+  for (auto& kv : c->plans) {
+    pdsp_plan* pl = kv.second;
+    cudaFree(pl->d_tw);
+    cudaFree(pl->d_post);
+    for (int i = 0; i < 4; ++i) cudaFree(pl->d_win[i]);
+    delete pl;
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = c->slots[i];
+    cudaFree(s.d_in);
+    cudaFree(s.d_out);
+    cudaFreeHost(s.h_in);
+    cudaFreeHost(s.h_out);
+    cudaEventDestroy(s.done);
+    cudaStreamDestroy(s.stream);
+  }
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_ctx_sync(pdsp_ctx* c) {
+  if (!c) return fail("null context");
+  if (set_device(c)) return 1;
+  if (drain(c)) return 1;
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+PDSP_EXPORT int pdsp_ctx_device(const pdsp_ctx* c) { return c ? c->device : -1; }
+PDSP_EXPORT int pdsp_ctx_sm_count(const pdsp_ctx* c) { return c ? c->sm_count : 0; }
+PDSP_EXPORT int64_t pdsp_ctx_launch_count(const pdsp_ctx* c) { return c ? (int64_t)c->launches.load() : 0; }
+
+PDSP_EXPORT int pdsp_is_power_of_two(int32_t n) { return n > 0 && (n & (n - 1)) == 0; }
+PDSP_EXPORT int32_t pdsp_next_power_of_two(int32_t n) {
+  if (n <= 1) return 1;
+  int32_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+PDSP_EXPORT int pdsp_create_window(int window, int32_t size, double* out) {
+  if (!out && size > 0) return fail("null argument");
+  return window_host(window, size, out);
+}
+PDSP_EXPORT int pdsp_bin_frequencies(int32_t size, double sample_rate, int sides, double* out, int32_t* bins) {
+  if (size <= 0) return fail("FFT size must be positive, got %d", size);
+  if (!(sample_rate > 0)) return fail("Sample rate must be positive, got %g", sample_rate);
+  const int32_t b = sides == PDSP_SIDES_ONE ? size / 2 + 1 : size;
+  if (bins) *bins = b;
+  if (out) {
+    const double scale = sample_rate / size;
+    for (int32_t i = 0; i < b; ++i) out[i] = i * scale;
+  }
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_plan** out) {
+  if (!c || !out) return fail("null argument");
+  *out = nullptr;
+  if (!pdsp_is_power_of_two(size)) return fail("FFT size must be power of two, got %d", size);
+  if (precision != PDSP_F32 && precision != PDSP_F64) return fail("unknown precision %d", precision);
+  int log2n = 0;
+  while ((1 << log2n) < size) ++log2n;
+  if (log2n - 1 > kMaxLog2M)
+    return fail("FFT size %d exceeds the in-CTA limit %d (four-step path not built yet)", size, 2 << kMaxLog2M);
+  if (set_device(c)) return 1;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto key = std::make_pair((int)size, precision);
+  auto it = c->plans.find(key);
+  if (it != c->plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  pdsp_plan* pl = new pdsp_plan();
+  pl->ctx = c;
+  pl->n = size;
+  pl->log2n = log2n;
+  pl->precision = precision;
+  int rc = precision == PDSP_F64 ? upload_tables<double>(pl) : upload_tables<float>(pl);
+  if (rc) {
+    delete pl;
+    return 1;
+  }
+  c->plans[key] = pl;
+  *out = pl;
+  return 0;
+}
+PDSP_EXPORT int32_t pdsp_plan_size(const pdsp_plan* p) { return p ? p->n : 0; }
+PDSP_EXPORT int pdsp_plan_precision(const pdsp_plan* p) { return p ? p->precision : -1; }
+
+static int check_desc(const pdsp_plan* pl, const pdsp_spectrum_desc* d) {
+  if (!pl || !d) return fail("null argument");
+  if (d->batch < 0) return fail("negative batch");
+  if (d->frame_len < 0) return fail("negative frame length");
+  if (d->hop < 0) return fail("negative hop");
+  if (!(d->sample_rate > 0)) return fail("Sample rate must be positive, got %g", d->sample_rate);
+  if (d->window < 0 || d->window > 3) return fail("Unsupported window type: %d", d->window);
+  if (d->sides != PDSP_SIDES_ONE && d->sides != PDSP_SIDES_TWO) return fail("unknown sides %d", d->sides);
+  if (d->sample_dtype != PDSP_F32 && d->sample_dtype != PDSP_F64) return fail("unknown sample dtype %d", d->sample_dtype);
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_spectrum_dev(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, void* d_amp,
+                                  void* d_phase, void* d_peaks, void* stream) {
+  if (check_desc(pl, d)) return 1;
+  if (set_device(pl->ctx)) return 1;
+  if (d->batch == 0) return 0;
+  if (!d_samples && d->frame_len > 0) return fail("null samples");
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
+  return launch_spectrum(pl, d, d_samples, d->batch, d_amp, d_phase, d_peaks, nullptr, nullptr, 0, st);
+}
+
+PDSP_EXPORT int pdsp_fft_forward_real_dev(pdsp_plan* pl, const void* d_in, int in_dtype, int64_t batch, void* d_ore,
+                                          void* d_oim, int full, void* stream) {
+  if (!pl || !d_in || !d_ore || !d_oim) return fail("null argument");
+  if (set_device(pl->ctx)) return 1;
+  if (batch <= 0) return batch == 0 ? 0 : fail("negative batch");
+  pdsp_spectrum_desc d;
+  memset(&d, 0, sizeof d);
+  d.sample_dtype = in_dtype;
+  d.frame_len = pl->n;
+  d.hop = pl->n;
+  d.batch = batch;
+  d.window = PDSP_WIN_RECT;
+  d.sides = PDSP_SIDES_ONE;
+  d.sample_rate = 1.0;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
+  return launch_spectrum(pl, &d, d_in, batch, nullptr, nullptr, nullptr, d_ore, d_oim, full ? 1 : 0, st);
+}
+
+PDSP_EXPORT int pdsp_fft_complex_dev(pdsp_plan* pl, const void* d_re, const void* d_im, int64_t batch, void* d_ore,
+                                     void* d_oim, int inverse, void* stream) {
+  if (!pl || !d_re || !d_ore || !d_oim) return fail("null argument");
+  if (set_device(pl->ctx)) return 1;
+  if (batch <= 0) return batch == 0 ? 0 : fail("negative batch");
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
+  return launch_c2c(pl, d_re, d_im, batch, d_ore, d_oim, inverse, st);
+}
+
+// ---- host-buffer spectrum: chunked, pipelined over kSlots streams
+PDSP_EXPORT int pdsp_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* samples, void* amplitude,
+                              void* phase, void* peaks) {
+  if (check_desc(pl, d)) return 1;
+  pdsp_ctx* c = pl->ctx;
+  if (set_device(c)) return 1;
+  if (d->batch == 0) return 0;
+  if (!samples && d->frame_len > 0) return fail("null samples");
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int n = pl->n;
+  const int bins = d->sides == PDSP_SIDES_TWO ? n : n / 2 + 1;
+  const size_t es = esize(d->sample_dtype), os = esize(pl->precision);
+  const size_t pk = pl->precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
+  const size_t out_per_frame = (amplitude ? bins * os : 0) + (phase ? bins * os : 0) + (peaks ? pk : 0);
+  const size_t in_per_frame = (size_t)(d->hop > 0 ? (d->hop < d->frame_len ? d->hop : d->frame_len) : 0) * es;
+  const long long chunk = pick_chunk(d->batch, in_per_frame + out_per_frame);
+  const bool src_pinned = samples ? is_device_visible(samples) : true;
+  const bool pin[3] = {amplitude ? is_device_visible(amplitude) : true, phase ? is_device_visible(phase) : true,
+                       peaks ? is_device_visible(peaks) : true};
+  int si = 0;
+  int rc = 0;
+  for (long long f0 = 0; f0 < d->batch && !rc; f0 += chunk, si = (si + 1) % kSlots) {
+    Slot& s = c->slots[si];
+    const long long nb = d->batch - f0 < chunk ? d->batch - f0 : chunk;
+    if ((rc = slot_wait(s))) break;
+    // input span of this chunk: frames f0 .. f0+nb-1
+    const size_t span = d->frame_len > 0 ? ((size_t)(nb - 1) * (size_t)d->hop + (size_t)d->frame_len) * es : 0;
+    const char* src = static_cast<const char*>(samples) + (size_t)f0 * (size_t)d->hop * es;
+    if ((rc = slot_in(s, src, span, src_pinned))) break;
+    const size_t a_bytes = amplitude ? (size_t)nb * bins * os : 0;
+    const size_t p_bytes = phase ? (size_t)nb * bins * os : 0;
+    const size_t k_bytes = peaks ? (size_t)nb * pk : 0;
+    const size_t a_off = 0, p_off = align256(a_bytes), k_off = p_off + align256(p_bytes);
+    if ((rc = ensure(&s.d_out, &s.d_out_cap, k_off + align256(k_bytes) + 256, false))) break;
+    char* dout = static_cast<char*>(s.d_out);
+    pdsp_spectrum_desc dd = *d;
+    dd.batch = nb;
+    if ((rc = launch_spectrum(pl, &dd, s.d_in, nb, amplitude ? dout + a_off : nullptr, phase ? dout + p_off : nullptr,
+                              peaks ? dout + k_off : nullptr, nullptr, nullptr, 0, s.stream)))
+      break;
+    HostIO::Out outs[3] = {
+        {amplitude ? static_cast<char*>(amplitude) + (size_t)f0 * bins * os : nullptr, a_bytes, a_off},
+        {phase ? static_cast<char*>(phase) + (size_t)f0 * bins * os : nullptr, p_bytes, p_off},
+        {peaks ? static_cast<char*>(peaks) + (size_t)f0 * pk : nullptr, k_bytes, k_off}};
+    rc = slot_out(s, outs, 3, pin);
+  }
+  if (drain(c)) rc = 1;
+  return rc;
+}
+
+// ---- host-buffer transforms (fp64 plans: the reference's ComplexArray is Float64Array planes)
+static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, int in_dtype, int64_t batch,
+                          double* out_re, double* out_im, int mode /*0 real fwd, 1 complex fwd, 2 inverse*/) {
+  if (!pl || !in_re || !out_re || !out_im) return fail("null argument");
+  if (mode != 0 && !in_im) return fail("null argument");
+  if (pl->precision != PDSP_F64) return fail("host transform entry points need a PDSP_F64 plan (Float64Array planes)");
+  if (batch < 0) return fail("negative batch");
+  pdsp_ctx* c = pl->ctx;
+  if (set_device(c)) return 1;
+  if (batch == 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t n = (size_t)pl->n;
+  const size_t es = mode == 0 ? esize(in_dtype) : 8;
+  const size_t in_per_frame = n * es * (mode == 0 ? 1 : 2);
+  const long long chunk = pick_chunk(batch, in_per_frame + 16 * n);
+  const bool pin_re = is_device_visible(in_re), pin_im = in_im ? is_device_visible(in_im) : true;
+  const bool pin[2] = {is_device_visible(out_re), is_device_visible(out_im)};
+  int si = 0, rc = 0;
+  for (long long f0 = 0; f0 < batch && !rc; f0 += chunk, si = (si + 1) % kSlots) {
+    Slot& s = c->slots[si];
+    const long long nb = batch - f0 < chunk ? batch - f0 : chunk;
+    if ((rc = slot_wait(s))) break;
+    const size_t plane = (size_t)nb * n * es;
+    const size_t plane_al = align256(plane);
+    // d_in holds [re plane | im plane]; pageable sources are staged in h_in the same way
+    if ((rc = ensure(&s.d_in, &s.d_in_cap, 2 * plane_al, false))) break;
+    if ((!pin_re || !pin_im) && (rc = ensure(&s.h_in, &s.h_in_cap, 2 * plane_al, true))) break;
+    if ((rc = slot_in(s, static_cast<const char*>(in_re) + (size_t)f0 * n * es, plane, pin_re, plane_al))) break;
+    if (mode != 0) {
+      const char* im_src = static_cast<const char*>(in_im) + (size_t)f0 * n * 8;
+      char* d_im = static_cast<char*>(s.d_in) + plane_al;
+      if (pin_im) {
+        CU(cudaMemcpyAsync(d_im, im_src, plane, cudaMemcpyHostToDevice, s.stream));
+      } else {
+        char* h = static_cast<char*>(s.h_in) + plane_al;
+        memcpy(h, im_src, plane);
+        CU(cudaMemcpyAsync(d_im, h, plane, cudaMemcpyHostToDevice, s.stream));
+      }
+    }
+    const size_t oplane = (size_t)nb * n * 8, oplane_al = align256(oplane);
+    if ((rc = ensure(&s.d_out, &s.d_out_cap, 2 * oplane_al, false))) break;
+    char* dout = static_cast<char*>(s.d_out);
+    if (mode == 0) {
+      pdsp_spectrum_desc dd;
+      memset(&dd, 0, sizeof dd);
+      dd.sample_dtype = in_dtype;
+      dd.frame_len = pl->n;
+      dd.hop = pl->n;
+      dd.batch = nb;
+      dd.window = PDSP_WIN_RECT;
+      dd.sample_rate = 1.0;
+      rc = launch_spectrum(pl, &dd, s.d_in, nb, nullptr, nullptr, nullptr, dout, dout + oplane_al, 1, s.stream);
+    } else {
+      rc = launch_c2c(pl, s.d_in, static_cast<char*>(s.d_in) + plane_al, nb, dout, dout + oplane_al, mode == 2, s.stream);
+    }
+    if (rc) break;
+    HostIO::Out outs[2] = {{reinterpret_cast<char*>(out_re) + (size_t)f0 * n * 8, oplane, 0},
+                           {reinterpret_cast<char*>(out_im) + (size_t)f0 * n * 8, oplane, oplane_al}};
+    rc = slot_out(s, outs, 2, pin);
+  }
+  if (drain(c)) rc = 1;
+  return rc;
+}
+
+PDSP_EXPORT int pdsp_fft_forward_real(pdsp_plan* pl, const void* in, int in_dtype, int64_t batch, double* out_re,
+                                      double* out_im) {
+  if (in_dtype != PDSP_F32 && in_dtype != PDSP_F64) return fail("unknown input dtype %d", in_dtype);
+  return host_transform(pl, in, nullptr, in_dtype, batch, out_re, out_im, 0);
+}
+PDSP_EXPORT int pdsp_fft_forward_complex(pdsp_plan* pl, const double* in_re, const double* in_im, int64_t batch,
+                                         double* out_re, double* out_im) {
+  return host_transform(pl, in_re, in_im, PDSP_F64, batch, out_re, out_im, 1);
+}
+PDSP_EXPORT int pdsp_fft_inverse(pdsp_plan* pl, const double* in_re, const double* in_im, int64_t batch, double* out_re,
+                                 double* out_im) {
+  return host_transform(pl, in_re, in_im, PDSP_F64, batch, out_re, out_im, 2);
+}
+
+static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out, bool mag) {
+  if (!c || !re || !im || !out) return fail("null argument");
+  if (n < 0) return fail("negative length");
+  if (set_device(c)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  Slot& s = c->slots[0];
+  if (slot_wait(s)) return 1;
+  const size_t bytes = (size_t)n * 8, al = align256(bytes);
+  if (ensure(&s.d_in, &s.d_in_cap, 2 * al, false)) return 1;
+  if (ensure(&s.d_out, &s.d_out_cap, al, false)) return 1;
+  char* din = static_cast<char*>(s.d_in);
+  CU(cudaMemcpyAsync(din, re, bytes, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(din + al, im, bytes, cudaMemcpyHostToDevice, s.stream));
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
+  if (mag)
+    k_magnitude<<<(int)blocks, 256, 0, s.stream>>>((const double*)din, (const double*)(din + al), n, (double*)s.d_out);
+  else
+    k_phase<<<(int)blocks, 256, 0, s.stream>>>((const double*)din, (const double*)(din + al), n, (double*)s.d_out);
+  CU(cudaGetLastError());
+  c->launches++;
+  CU(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+PDSP_EXPORT int pdsp_magnitude(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out) {
+  return host_elementwise(c, re, im, n, out, true);
+}
+PDSP_EXPORT int pdsp_phase(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out) {
+  return host_elementwise(c, re, im, n, out, false);
+}
+
+PDSP_EXPORT int pdsp_dev_alloc(pdsp_ctx* c, size_t bytes, void** p) {
+  if (!c || !p) return fail("null argument");
+  if (set_device(c)) return 1;
+  CU(cudaMalloc(p, bytes ? bytes : 1));
+  return 0;
+}
+PDSP_EXPORT int pdsp_dev_free(pdsp_ctx* c, void* p) {
+  if (!c) return fail("null argument");
+  if (set_device(c)) return 1;
+  CU(cudaFree(p));
+  return 0;
+}
+PDSP_EXPORT int pdsp_host_alloc(pdsp_ctx* c, size_t bytes, void** p) {
+  if (!c || !p) return fail("null argument");
+  if (set_device(c)) return 1;
+  CU(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+PDSP_EXPORT int pdsp_host_free(pdsp_ctx* c, void* p) {
+  if (!c) return fail("null argument");
+  if (set_device(c)) return 1;
+  CU(cudaFreeHost(p));
+  return 0;
+}
+PDSP_EXPORT int pdsp_memcpy_h2d(pdsp_ctx* c, void* d, const void* h, size_t bytes, void* stream) {
+  if (!c) return fail("null argument");
+  if (set_device(c)) return 1;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+PDSP_EXPORT int pdsp_memcpy_d2h(pdsp_ctx* c, void* h, const void* d, size_t bytes, void* stream) {
+  if (!c) return fail("null argument");
+  if (set_device(c)) return 1;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+  return 0;
+}

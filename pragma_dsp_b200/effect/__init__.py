@@ -1,0 +1,125 @@
+"""Effect rung: mirrors /root/reference/src/effect/index.ts (FourierService, Fourier, FourierLive,
+spectrumFx, spectrumStream) without the `effect` runtime, which has no Python equivalent:
+
+* ``FourierLive()`` builds the service - two caches, ``fft(size)`` and ``window(type, size)``, whose
+  returned instances are identity-stable like the reference's Maps (:30-48); used as a context
+  manager it scopes the device plans the way ``Effect.provide(FourierLive)`` scopes the Layer.
+* ``spectrumFx(samples, options)`` returns a function of the service (the Effect's "run").
+* ``spectrumStream(frames, options)`` maps an iterable of frames to per-frame results, in order,
+  1:1, empty in -> empty out (:190-194) - but groups ``chunk`` frames per launch so the stream is
+  one batched kernel per chunk instead of one transform per fiber.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Iterator
+
+import numpy as np
+
+from .. import _lib
+from ..core import nextPowerOfTwo
+from ..public.spectrum import spectrum_batch
+from ..xform.fourier import FFT, createWindow
+
+
+class FourierService:
+    """src/effect/index.ts:17-20"""
+
+    def __init__(self, context=None):
+        self._ctx = context or _lib.default_context()
+        self._fft: dict[int, FFT] = {}
+        self._win: dict[str, np.ndarray] = {}
+
+    def fft(self, size: int) -> FFT:
+        cached = self._fft.get(size)
+        if cached is not None:
+            return cached
+        created = FFT(size, context=self._ctx)
+        self._fft[size] = created
+        return created
+
+    def window(self, type: str, size: int) -> np.ndarray:
+        key = f"{type}:{size}"
+        cached = self._win.get(key)
+        if cached is not None:
+            return cached
+        created = createWindow(type, size)
+        self._win[key] = created
+        return created
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self._fft.clear()
+        self._win.clear()
+        return False
+
+
+Fourier = FourierService  # the Context.Tag ("pragma-dsp/Fourier", :22-25) is the class itself here
+
+
+def FourierLive(context=None) -> FourierService:
+    """src/effect/index.ts:27-51"""
+    return FourierService(context)
+
+
+def _one(service: FourierService, samples, options: dict):
+    x = np.asarray(samples)
+    size = options.get("fftSize")
+    size = nextPowerOfTwo(x.shape[0]) if size is None else size
+    service.fft(size)  # plan cached for the service's lifetime, like fftCache
+    r = spectrum_batch(x.reshape(1, -1) if x.size else np.zeros((1, 0)), sampleRate=options.get("sampleRate", 1),
+                       fftSize=size, window=options.get("window", "rect"), sides=options.get("sides", "one"),
+                       precision=options.get("precision", "f64"), context=service._ctx)
+    return _result(r, 0)
+
+
+def _result(r, i):
+    pk = r["peaks"][i]
+    return {"frequencies": r["frequencies"], "amplitude": r["amplitude"][i], "phase": r["phase"][i],
+            "peak": {"index": int(pk["index"]), "frequency": float(pk["frequency"]),
+                     "amplitude": float(pk["amplitude"]), "phase": float(pk["phase"])}}
+
+
+def spectrumFx(samples, options: dict | None = None) -> Callable[[FourierService], dict]:
+    """src/effect/index.ts:181-188 - returns the effect; run it with a service: spectrumFx(x, o)(service)."""
+    opts = dict(options or {})
+    return lambda service: _one(service, samples, opts)
+
+
+def spectrumStream(frames: Iterable, options: dict | None = None, *, service: FourierService | None = None,
+                   chunk: int = 4096) -> Iterator[dict]:
+    """src/effect/index.ts:190-194 - ordered 1:1 map over a stream of (Float32Array) frames.
+
+    Frames of equal length are stacked `chunk` at a time into one batched launch; a frame of a
+    different length flushes the pending chunk first so order is preserved."""
+    opts = dict(options or {})
+    svc = service or FourierService()
+    pending: list[np.ndarray] = []
+
+    def flush():
+        if not pending:
+            return
+        block = np.stack(pending)
+        size = opts.get("fftSize")
+        size = nextPowerOfTwo(block.shape[1]) if size is None else size
+        svc.fft(size)
+        r = spectrum_batch(block, sampleRate=opts.get("sampleRate", 1), fftSize=size, window=opts.get("window", "rect"),
+                           sides=opts.get("sides", "one"), precision=opts.get("precision", "f64"), context=svc._ctx)
+        for i in range(block.shape[0]):
+            yield _result(r, i)
+        pending.clear()
+
+    for frame in frames:
+        f = np.asarray(frame)
+        if f.dtype != np.float32 and f.dtype != np.float64:
+            f = f.astype(np.float64)
+        if pending and (f.shape != pending[0].shape or f.dtype != pending[0].dtype):
+            yield from flush()
+        pending.append(f)
+        if len(pending) >= chunk:
+            yield from flush()
+    yield from flush()
+
+
+__all__ = ["FourierService", "Fourier", "FourierLive", "spectrumFx", "spectrumStream"]

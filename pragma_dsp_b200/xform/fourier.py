@@ -1,0 +1,87 @@
+"""Power rung: mirrors /root/reference/src/xform/fourier.ts (FFT, createWindow, magnitude, phase,
+binFrequencies) on top of the C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import SIDES, WINDOWS, check, lib, ptr
+from ..core import ComplexArray, Radix2Fft, createComplexArray, isPowerOfTwo
+
+WindowType = str  # "rect" | "hann" | "hamming" | "blackman"
+FftSides = str    # "one" | "two"
+
+
+def createWindow(type: WindowType, size: int) -> np.ndarray:
+    """src/xform/fourier.ts:14-52 - symmetric window as a fresh float64 array."""
+    if size <= 0:
+        raise ValueError(f"Window size must be positive, got {size}")
+    if type not in WINDOWS:
+        raise ValueError(f"Unsupported window type: {type}")
+    out = np.empty(int(size), dtype=np.float64)
+    check(lib().pdsp_create_window(WINDOWS[type], int(size), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+class FFT:
+    """src/xform/fourier.ts:69-96 - facade over Radix2Fft."""
+
+    def __init__(self, size: int, *, context: "_lib.Context | None" = None):
+        if not isPowerOfTwo(size):
+            raise ValueError(f"FFT size must be power of two, got {size}")
+        self.size = int(size)
+        self._kernel = Radix2Fft(size, context=context)
+
+    def forward(self, input, out: ComplexArray | None = None) -> ComplexArray:
+        return self._kernel.forward(input, out)
+
+    def forwardComplex(self, input: ComplexArray, out: ComplexArray | None = None) -> ComplexArray:
+        return self._kernel.forwardComplex(input, out)
+
+    def inverse(self, input: ComplexArray, out: ComplexArray | None = None) -> ComplexArray:
+        return self._kernel.inverse(input, out)
+
+    def createComplexArray(self, fill: float = 0) -> ComplexArray:
+        return createComplexArray(self.size, fill)
+
+    def forward_batch(self, frames):
+        return self._kernel.forward_batch(frames)
+
+    def complex_batch(self, re, im, inverse=False):
+        return self._kernel.complex_batch(re, im, inverse)
+
+
+def _elementwise(fn, input: ComplexArray, out):
+    re = np.ascontiguousarray(input.real, dtype=np.float64)
+    im = np.ascontiguousarray(input.imag, dtype=np.float64)
+    result = out if out is not None else np.empty(re.shape[0], dtype=np.float64)
+    check(fn(_lib.default_context().h, ptr(re), ptr(im), re.shape[0], ptr(result)))
+    return result
+
+
+def magnitude(input: ComplexArray, out: np.ndarray | None = None) -> np.ndarray:
+    """src/xform/fourier.ts:98-109 - hypot(re, im) for all bins."""
+    return _elementwise(lib().pdsp_magnitude, input, out)
+
+
+def phase(input: ComplexArray, out: np.ndarray | None = None) -> np.ndarray:
+    """src/xform/fourier.ts:111-120 - atan2(im, re) for all bins."""
+    return _elementwise(lib().pdsp_phase, input, out)
+
+
+def binFrequencies(size: int, sampleRate: float, sides: FftSides = "one") -> np.ndarray:
+    """src/xform/fourier.ts:147-165"""
+    if size <= 0:
+        raise ValueError(f"FFT size must be positive, got {size}")
+    if not sampleRate > 0:
+        raise ValueError(f"Sample rate must be positive, got {sampleRate}")
+    bins = size // 2 + 1 if sides == "one" else size
+    out = np.empty(bins, dtype=np.float64)
+    check(lib().pdsp_bin_frequencies(int(size), float(sampleRate), SIDES[sides],
+                                     out.ctypes.data_as(C.POINTER(C.c_double)), None))
+    return out
+
+
+__all__ = ["FFT", "createWindow", "magnitude", "phase", "binFrequencies", "WindowType", "FftSides"]

@@ -1,0 +1,136 @@
+"""Host SIMT emulator harness (TEST ONLY): runs the real kernel source (fft_kernels.cuh) on the CPU.
+
+See emu.cpp.  Used by tests/test_kernel_emulation.py to check the kernels' index math,
+synchronisation and epilogue logic against the oracle where no GPU exists.  Not part of the
+product: pragma_dsp_b200 never imports it and libpragma_b200.so does not contain it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpdsp_emu.so")
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "pragma_dsp_b200", "csrc")
+
+
+class R2CParams(C.Structure):
+    _fields_ = [("samples", C.c_void_p), ("sample_dtype", C.c_int), ("vec_ok", C.c_int), ("frame_len", C.c_int),
+                ("hop", C.c_longlong), ("batch", C.c_longlong), ("window", C.c_void_p), ("tw", C.c_void_p),
+                ("post", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p), ("cfull", C.c_int),
+                ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int),
+                ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double)]
+
+
+class C2CParams(C.Structure):
+    _fields_ = [("in_re", C.c_void_p), ("in_im", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p),
+                ("batch", C.c_longlong), ("tw", C.c_void_p), ("inverse", C.c_int)]
+
+
+PEAK64 = np.dtype([("index", "<i4"), ("_pad", "<i4"), ("frequency", "<f8"), ("amplitude", "<f8"), ("phase", "<f8")])
+PEAK32 = np.dtype([("index", "<i4"), ("frequency", "<f4"), ("amplitude", "<f4"), ("phase", "<f4")])
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_HERE, "emu.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
+                                                   if f.endswith((".h", ".cuh"))]
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+            subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
+                            "-o", _SO, os.path.join(_HERE, "emu.cpp")], check=True)
+        L = C.CDLL(_SO)
+        assert L.emu_params_size(0) == C.sizeof(R2CParams), (L.emu_params_size(0), C.sizeof(R2CParams))
+        assert L.emu_params_size(1) == C.sizeof(C2CParams)
+        _lib = L
+    return _lib
+
+
+def tables(n, dtype):
+    """Twiddle and post-pass tables as pragma_b200.cu::upload_tables builds them."""
+    k = np.arange(n, dtype=np.longdouble)
+    ang = -2 * np.longdouble(np.pi) * k / np.longdouble(n)
+    re, im = np.cos(ang), np.sin(ang)
+    for kk in range(n):  # exact axis / diagonal points
+        if (8 * kk) % n == 0:
+            o = (8 * kk) // n
+            s = np.sqrt(np.longdouble(0.5))
+            re[kk] = [1, s, 0, -s, -1, -s, 0, s][o]
+            im[kk] = [0, -s, -1, -s, 0, s, 1, s][o]
+    tw = np.empty((n, 2), dtype=dtype)
+    tw[:, 0], tw[:, 1] = re.astype(dtype), im.astype(dtype)
+    m = n // 2
+    post = np.empty((m // 2 + 1, 2), dtype=dtype)
+    for kk in range(m // 2 + 1):
+        r, i = (re[kk], im[kk]) if n >= 4 else (np.longdouble(1), np.longdouble(0))
+        post[kk] = (i / 2, -r / 2)
+    return np.ascontiguousarray(tw), np.ascontiguousarray(post)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, window=None, sides="one",
+        sample_rate=1.0, raw=False, want=("complex", "amp", "phase", "peak"), cfull=True, nblocks=1):
+    """Run r2c_kernel under the emulator. samples: 1-D float32/float64 array."""
+    samples = np.ascontiguousarray(samples)
+    assert samples.dtype in (np.float32, np.float64)
+    frame_len = n if frame_len is None else frame_len
+    hop = frame_len if hop is None else hop
+    batch = 1 if batch is None else batch
+    m = n // 2
+    log2m = m.bit_length() - 1
+    tw, post = tables(n, dtype)
+    win = None if window is None else np.ascontiguousarray(window, dtype=dtype)
+    bins = n if sides == "two" else m + 1
+    cb = n if cfull else m + 1
+    out = {}
+    if "complex" in want:
+        out["re"] = np.full((batch, cb), np.nan, dtype=dtype)
+        out["im"] = np.full((batch, cb), np.nan, dtype=dtype)
+    if "amp" in want:
+        out["amp"] = np.full((batch, bins), np.nan, dtype=dtype)
+    if "phase" in want:
+        out["phase"] = np.full((batch, bins), np.nan, dtype=dtype)
+    if "peak" in want:
+        out["peaks"] = np.zeros(batch, dtype=PEAK64 if dtype == np.float64 else PEAK32)
+    p = R2CParams()
+    p.samples = _p(samples)
+    p.sample_dtype = 1 if samples.dtype == np.float64 else 0
+    p.vec_ok = int(samples.ctypes.data % (2 * samples.itemsize) == 0 and hop % 2 == 0)
+    p.frame_len, p.hop, p.batch = frame_len, hop, batch
+    p.window, p.tw, p.post = _p(win), _p(tw), _p(post)
+    p.out_re, p.out_im, p.cfull = _p(out.get("re")), _p(out.get("im")), int(cfull)
+    p.amp, p.phase, p.peaks = _p(out.get("amp")), _p(out.get("phase")), _p(out.get("peaks"))
+    p.two_sided = int(sides == "two")
+    if raw:
+        p.scale_edge = p.scale_mid = 1.0
+    elif sides == "two":
+        p.scale_edge = p.scale_mid = 1.0 / n
+    else:
+        p.scale_edge, p.scale_mid = 1.0 / n, 2.0 / n
+    p.bin_hz = sample_rate / n
+    rc = lib().emu_r2c(int(dtype == np.float64), log2m, C.byref(p), nblocks)
+    assert rc == 0, f"size {n} not instantiated in the emulator"
+    return out
+
+
+def c2c(re, im, n, *, dtype=np.float64, inverse=False, nblocks=1):
+    re = np.ascontiguousarray(re, dtype=dtype)
+    im = None if im is None else np.ascontiguousarray(im, dtype=dtype)
+    batch = re.size // n
+    tw, _ = tables(n, dtype)
+    ore = np.full_like(re, np.nan)
+    oim = np.full_like(re, np.nan)
+    p = C2CParams()
+    p.in_re, p.in_im, p.out_re, p.out_im = _p(re), _p(im), _p(ore), _p(oim)
+    p.batch, p.tw, p.inverse = batch, _p(tw), int(inverse)
+    rc = lib().emu_c2c(int(dtype == np.float64), n.bit_length() - 1, C.byref(p), nblocks)
+    assert rc == 0
+    return ore, oim

@@ -1,0 +1,221 @@
+"""Parity of the CUDA path against the CPU oracle on seeded inputs, through the C-ABI
+(host entry points and device-resident entry points).  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): bin/peak indices exact; complex outputs within relative
+L2 1e-12*log2(N) for fp64 and 1e-5 for fp32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def tol(n, prec):
+    return 1e-12 * max(1.0, np.log2(n)) if prec == "f64" else 1e-5
+
+
+def rel_l2(a, b):
+    s = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (s if s > 0 else 1.0)
+
+
+def multitone(rng, batch, n, dtype=np.float64):
+    t = np.arange(n)
+    k = rng.integers(8, max(9, n // 2 - 8), size=(batch, 3)) + rng.uniform(-0.25, 0.25, size=(batch, 3))
+    a = np.concatenate([np.ones((batch, 1)), rng.uniform(0.1, 0.5, size=(batch, 2))], axis=1)
+    ph = rng.uniform(0, 2 * np.pi, size=(batch, 3))
+    x = np.zeros((batch, n))
+    for j in range(3):
+        x += a[:, j, None] * np.sin(2 * np.pi * k[:, j, None] * t[None, :] / n + ph[:, j, None])
+    return x.astype(dtype)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pragma_dsp_b200 import _lib
+    return _lib.default_context()
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_forward_real_all_sizes(n):
+    from pragma_dsp_b200.core import Radix2Fft
+    rng = np.random.default_rng(n)
+    batch = 37 if n <= 4096 else 5
+    x = rng.standard_normal((batch, n))
+    re, im = Radix2Fft(n).forward_batch(x)
+    rre, rim = oracle.FFT(n).forward(x)
+    for f in range(batch):
+        assert rel_l2(re[f] + 1j * im[f], rre[f] + 1j * rim[f]) <= tol(n, "f64"), (n, f)
+    # Float32Array input is widened exactly (README.md:11)
+    re32, im32 = Radix2Fft(n).forward_batch(x.astype(np.float32))
+    rre, rim = oracle.FFT(n).forward(x.astype(np.float32).astype(np.float64))
+    assert rel_l2(re32 + 1j * im32, rre + 1j * rim) <= tol(n, "f64")
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 32, 64, 512, 1024, 4096, 8192])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_complex_all_sizes(n, inverse):
+    from pragma_dsp_b200.core import Radix2Fft
+    rng = np.random.default_rng(1000 + n)
+    batch = 19 if n <= 1024 else 4
+    re, im = rng.standard_normal((batch, n)), rng.standard_normal((batch, n))
+    ore, oim = Radix2Fft(n).complex_batch(re, im, inverse=inverse)
+    plan = oracle.FFT(n)
+    rre, rim = (plan.inverse if inverse else plan.forwardComplex)(re, im)
+    for f in range(batch):
+        assert rel_l2(ore[f] + 1j * oim[f], rre[f] + 1j * rim[f]) <= tol(n, "f64"), (n, f)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("n,window,sides", [(1024, "hann", "one"), (1024, "rect", "two"), (4096, "hann", "one"),
+                                            (256, "blackman", "one"), (64, "hamming", "two"), (2048, "hamming", "one"),
+                                            (16, "hann", "one"), (2, "rect", "one"), (1, "rect", "one"), (8192, "hann", "one")])
+def test_spectrum_batch_vs_oracle(prec, n, window, sides):
+    from pragma_dsp_b200 import spectrum_batch
+    rng = np.random.default_rng(n * 7 + len(window))
+    batch = 300 if n <= 1024 else 40
+    x = multitone(rng, batch, n) if n >= 64 else rng.standard_normal((batch, n))
+    xs = x.astype(np.float32) if prec == "f32" else x
+    got = spectrum_batch(xs, sampleRate=48000.0, fftSize=n, window=window, sides=sides, precision=prec)
+    ref = oracle.spectrum_batch(xs, fftSize=n, sampleRate=48000.0, window=window, sides=sides)
+    if sides == "one":
+        assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+    else:  # the reference picks k or N-k on 1-ulp noise
+        gi, ri = got["peaks"]["index"], ref["peaks"]["index"]
+        assert ((gi == ri) | (gi == (n - ri) % n)).all()
+    atol = 1e-12 if prec == "f64" else 2e-6
+    scale = np.maximum(1.0, np.abs(ref["amplitude"]).max(axis=1, keepdims=True))
+    assert (np.abs(got["amplitude"] - ref["amplitude"]) <= 10 * atol * scale).all()
+    for f in range(0, batch, 7):
+        assert rel_l2(got["amplitude"][f].astype(np.float64), ref["amplitude"][f]) <= tol(n, prec)
+    mask = ref["amplitude"] > (1e-6 if prec == "f64" else 1e-3) * scale
+    d = np.abs(got["phase"] - ref["phase"])
+    d = np.minimum(d, np.abs(d - 2 * np.pi))
+    assert d[mask].max(initial=0) <= (1e-9 if prec == "f64" else 2e-3)
+    pa = got["peaks"]["amplitude"]
+    assert (np.abs(pa - ref["peaks"]["amplitude"]) <= 10 * atol * scale[:, 0]).all()
+    assert np.allclose(got["peaks"]["frequency"], got["peaks"]["index"] * (48000.0 / n), rtol=1e-6 if prec == "f32" else 1e-15)
+
+
+def test_frame_addressing_host_api():
+    """buildFrame zero-pad / truncate (src/public/spectrum.ts:36-43), STFT hop views, odd alignments."""
+    from pragma_dsp_b200 import spectrum_batch
+    rng = np.random.default_rng(3)
+    sig = rng.standard_normal(40000).astype(np.float32)
+    for n, frame_len, hop, batch in [(256, 100, 37, 900), (4096, 4096, 1024, 30), (128, 300, 301, 100), (64, 0, 5, 3),
+                                     (512, 511, 1, 700), (1024, 1024, 1, 33)]:
+        got = spectrum_batch(sig, fftSize=n, frameLen=frame_len, hop=hop, batch=batch, sampleRate=8000.0, window="hann")
+        ref = oracle.spectrum_batch(sig, fftSize=n, frameLen=frame_len, hop=hop, batch=batch, sampleRate=8000.0, window="hann")
+        assert np.abs(got["amplitude"] - ref["amplitude"]).max() <= 1e-13
+        assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+    # f64 samples at an address that is 8- but not 16-byte aligned (scalar-load path)
+    buf = rng.standard_normal(1024 * 8 + 1)
+    got = spectrum_batch(buf[1:], fftSize=1024, frameLen=1024, hop=1024, batch=8, window="blackman")
+    ref = oracle.spectrum_batch(buf[1:], fftSize=1024, frameLen=1024, hop=1024, batch=8, window="blackman")
+    assert np.abs(got["amplitude"] - ref["amplitude"]).max() <= 1e-13
+
+
+def test_chunked_pipeline_large_batch_pageable_and_pinned(ctx):
+    """Host entry point with a batch that spans many staging chunks; pageable and pinned buffers agree."""
+    import torch
+    from pragma_dsp_b200 import spectrum_batch
+    rng = np.random.default_rng(5)
+    n, batch = 1024, 20000  # ~82 MB in, 3+ chunks
+    x = multitone(rng, batch, n, np.float32)
+    got = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann", precision="f32", outputs=("amplitude", "peak"))
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann", want_phase=False, threads=8)
+    assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+    assert np.abs(got["amplitude"] - ref["amplitude"]).max() <= 2e-5
+    px = torch.from_numpy(x).pin_memory().numpy()
+    got2 = spectrum_batch(px, sampleRate=48000.0, fftSize=n, window="hann", precision="f32", outputs=("amplitude", "peak"))
+    assert (got2["amplitude"] == got["amplitude"]).all() and (got2["peaks"] == got["peaks"]).all()
+
+
+def test_device_resident_entry_points(ctx):
+    """pdsp_spectrum_dev / pdsp_fft_*_dev on torch-owned device memory and torch's stream."""
+    import torch
+    from pragma_dsp_b200._lib import F32, F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+    L = lib()
+    rng = np.random.default_rng(9)
+    n, batch = 1024, 513
+    x = multitone(rng, batch, n)
+    dx = torch.from_numpy(x).cuda()
+    amp = torch.empty((batch, n // 2 + 1), dtype=torch.float64, device="cuda")
+    pk = torch.zeros((batch, 32), dtype=torch.uint8, device="cuda")
+    plan = ctx.plan(n, F64)
+    d = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
+                     sample_rate=48000.0, raw_magnitude=0)
+    st = torch.cuda.current_stream().cuda_stream
+    check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(dx.data_ptr()), C.c_void_p(amp.data_ptr()), None,
+                              C.c_void_p(pk.data_ptr()), C.c_void_p(st)))
+    torch.cuda.synchronize()
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann")
+    assert np.abs(amp.cpu().numpy() - ref["amplitude"]).max() <= 1e-12
+    peaks = pk.cpu().numpy().view(PEAK_F64).reshape(-1)
+    assert (peaks["index"] == ref["peaks"]["index"]).all()
+    # real forward, one-sided planes, then complex inverse of the full spectrum = the signal
+    ore = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    oim = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    check(L.pdsp_fft_forward_real_dev(plan, C.c_void_p(dx.data_ptr()), F64, batch, C.c_void_p(ore.data_ptr()),
+                                      C.c_void_p(oim.data_ptr()), 1, C.c_void_p(st)))
+    bre, bim = torch.empty_like(ore), torch.empty_like(ore)
+    check(L.pdsp_fft_complex_dev(plan, C.c_void_p(ore.data_ptr()), C.c_void_p(oim.data_ptr()), batch,
+                                 C.c_void_p(bre.data_ptr()), C.c_void_p(bim.data_ptr()), 1, C.c_void_p(st)))
+    torch.cuda.synchronize()
+    assert (bre - dx).abs().max().item() <= 1e-13 and bim.abs().max().item() <= 1e-13
+
+
+@pytest.mark.parametrize("prec,frames", [("f32", 65536), ("f64", 65536)])
+def test_full_size_properties(ctx, prec, frames):
+    """BASELINE-size batch (65,536 x 1024), checked through size-independent properties:
+    Parseval, linearity, inverse round trip, and oracle agreement on a strided subset."""
+    import torch
+    from pragma_dsp_b200._lib import F32, F64, PEAK_F32, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+    L = lib()
+    n = 1024
+    P = F64 if prec == "f64" else F32
+    tdt = torch.float64 if prec == "f64" else torch.float32
+    g = torch.Generator(device="cuda").manual_seed(1337)
+    x = torch.randn((frames, n), generator=g, device="cuda", dtype=torch.float64).to(tdt)
+    y = torch.randn((frames, n), generator=g, device="cuda", dtype=torch.float64).to(tdt)
+    plan = ctx.plan(n, P)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fwd(t):
+        re = torch.empty((frames, n), dtype=tdt, device="cuda")
+        im = torch.empty((frames, n), dtype=tdt, device="cuda")
+        check(L.pdsp_fft_forward_real_dev(plan, C.c_void_p(t.data_ptr()), P, frames, C.c_void_p(re.data_ptr()),
+                                          C.c_void_p(im.data_ptr()), 1, st))
+        return re, im
+
+    xr, xi = fwd(x)
+    yr, yi = fwd(y)
+    sr, si = fwd(x + 2 * y)
+    torch.cuda.synchronize()
+    eps = 1e-12 if prec == "f64" else 2e-5
+    # Parseval: sum |X|^2 = N * sum x^2, per frame
+    e_t = (x.double() ** 2).sum(1) * n
+    e_f = (xr.double() ** 2 + xi.double() ** 2).sum(1)
+    assert ((e_f - e_t).abs() / e_t).max().item() <= 50 * eps
+    # linearity
+    num = ((sr - (xr + 2 * yr)).double() ** 2 + (si - (xi + 2 * yi)).double() ** 2).sum(1).sqrt()
+    den = (sr.double() ** 2 + si.double() ** 2).sum(1).sqrt()
+    assert (num / den).max().item() <= 50 * eps
+    # Hermitian symmetry is exact by construction
+    assert (xr[:, 1:n // 2] == xr[:, n // 2 + 1:].flip(1)).all() and (xi[:, 1:n // 2] == -xi[:, n // 2 + 1:].flip(1)).all()
+    # inverse round trip
+    br, bi = torch.empty_like(xr), torch.empty_like(xr)
+    check(L.pdsp_fft_complex_dev(plan, C.c_void_p(xr.data_ptr()), C.c_void_p(xi.data_ptr()), frames,
+                                 C.c_void_p(br.data_ptr()), C.c_void_p(bi.data_ptr()), 1, st))
+    torch.cuda.synchronize()
+    assert (br - x).abs().max().item() <= 100 * eps and bi.abs().max().item() <= 100 * eps
+    # oracle agreement on a strided subset, including the peaks
+    idx = torch.arange(0, frames, 257, device="cuda")
+    sub = x[idx].cpu().numpy()
+    rre, rim = oracle.FFT(n).forward(sub.astype(np.float64))
+    got = (xr[idx].cpu().numpy().astype(np.float64) + 1j * xi[idx].cpu().numpy().astype(np.float64))
+    for f in range(len(idx)):
+        assert rel_l2(got[f], rre[f] + 1j * rim[f]) <= tol(n, prec)
