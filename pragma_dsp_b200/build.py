@@ -65,6 +65,12 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
         defs = [f"-DPDSP_INST_KIND={kind}", f"-DPDSP_INST_T={ctype}", f"-DPDSP_INST_LO={lo}", f"-DPDSP_INST_HI={hi}",
                 f"-DPDSP_INST_NAME={name}"]
         units.append((os.path.join(CSRC, "inst.cu"), os.path.join(OBJ, name + ".o"), defs))
+    nvar = int(re.search(r"kNumVariants = (\d+)", open(os.path.join(CSRC, "fft_config.h")).read()).group(1))
+    for v in range(1, nvar):
+        for tag, ctype in (("f64", "double"), ("f32", "float")):
+            name = f"launch_r2c_var_{tag}_{v}"
+            units.append((os.path.join(CSRC, "inst_var.cu"), os.path.join(OBJ, name + ".o"),
+                          [f"-DPDSP_VAR_T={ctype}", f"-DPDSP_VAR={v}", f"-DPDSP_INST_NAME={name}"]))
     for src, obj, defs in units:
         stamp = _digest(headers + [src], " ".join(FLAGS + defs))
         objs.append(obj)

@@ -3,15 +3,41 @@
 
 namespace pdsp {
 
-constexpr int kMaxLog2M = 13;  // largest in-CTA complex length 8192 (real frames up to 16384)
+constexpr int kMaxLog2M = 13;      // largest in-CTA complex length 8192 (real frames up to 16384)
+constexpr int kMinSpecLog2M = 5;   // sizes below this only get the generic (runtime-flag) kernel
+constexpr int kNumVariants = 8;    // tuning variants compiled for kVariantLog2M (see inst_var.cu)
+constexpr int kVariantLog2M = 9;   // N = 1024, the headline size
 
-// Points per thread / radix / CTA size for a complex length 2^LOG2M.
-template <typename T, int LOG2M>
+// Points per thread / radix / CTA size / occupancy target for a complex length 2^LOG2M.
+// VAR = 0 is what ships for every size; VAR > 0 are alternative mappings of the headline size,
+// selectable at run time with PDSP_VARIANT=<n> so one GPU session can rank them.
+template <typename T, int LOG2M, int VAR = 0>
 struct KCfg {
   static constexpr int LOG2P = LOG2M < 3 ? LOG2M : (LOG2M >= 9 ? 4 : 3);
   static constexpr int MAXRB = 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
   static constexpr int THREADS = TF > 128 ? TF : 128;
+  // register cap via __launch_bounds__: 128 regs/thread for 128-thread CTAs of doubles, 96 for floats
+  static constexpr int MINB = THREADS <= 128 ? (sizeof(T) == 8 ? 4 : 5) : (THREADS <= 256 ? 2 : 1);
 };
+
+#define PDSP_VARIANT(VAR, LP, RB, THR, MB64, MB32)                          \
+  template <typename T>                                                     \
+  struct KCfg<T, kVariantLog2M, VAR> {                                      \
+    static constexpr int LOG2P = LP;                                        \
+    static constexpr int MAXRB = RB;                                        \
+    static constexpr int TF = (1 << kVariantLog2M) >> LOG2P;                \
+    static constexpr int THREADS = THR;                                     \
+    static constexpr int MINB = sizeof(T) == 8 ? MB64 : MB32;               \
+  };
+//           var  log2P radix-bits threads minB(f64) minB(f32)
+PDSP_VARIANT(1, 4, 4, 128, 4, 5)   // 16 x 16 x 2, one warp per frame
+PDSP_VARIANT(2, 5, 5, 64, 4, 8)    // 32 x 16, 16 threads per frame, one exchange
+PDSP_VARIANT(3, 3, 3, 128, 6, 8)   // 8 x 8 x 8, two warps per frame (named barriers)
+PDSP_VARIANT(4, 4, 3, 128, 3, 4)   // baseline mapping with a looser register cap
+PDSP_VARIANT(5, 5, 5, 128, 2, 4)   // 32 x 16, 8 frames per CTA
+PDSP_VARIANT(6, 4, 3, 256, 2, 2)   // baseline mapping, 8 frames per CTA
+PDSP_VARIANT(7, 5, 5, 32, 8, 16)   // 32 x 16, one warp (2 frames) per CTA
+#undef PDSP_VARIANT
 
 }  // namespace pdsp

@@ -108,12 +108,33 @@ PDSP_DEVICE bool peak_better(T v, int k, T bv, int bk) {
   return (v > bv) || (v == bv && v > (T)0 && k < bk);
 }
 
-template <typename T, int LOG2M, int LOG2P, int MAXRB, bool PHASE, int THREADS>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
+// Kernel specialisation.  MD_GENERIC keeps every choice a runtime (warp-uniform) flag and handles
+// ragged frames (zero-pad / truncate / unaligned / tail predicates).  Any other value fixes the
+// outputs at compile time and assumes whole, vector-aligned frames (frame_len >= N, vec_ok), which
+// is what the batched entry points see for the BASELINE workloads; dispatch falls back to
+// MD_GENERIC whenever those assumptions do not hold.
+enum : int {
+  MD_GENERIC = 0,
+  MD_AMP = 1,     // scaled amplitude / raw magnitude rows
+  MD_PHASE = 2,   // phase rows
+  MD_PEAK = 4,    // per-frame findPeak record
+  MD_CPLX = 8,    // complex spectrum, all N bins (Radix2Fft.forward)
+};
+
+template <typename T, typename S>
+PDSP_DEVICE cx<T> load_pair(const S* PDSP_RESTRICT s, int i0) {
+  const cx<S> pr = *reinterpret_cast<const cx<S>*>(s + i0);
+  return cx<T>{(T)pr.x, (T)pr.y};
+}
+
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MINB, int MODE>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) r2c_kernel(const R2CParams p) {
   using E = FftEngine<T, LOG2M, LOG2P, MAXRB>;
   constexpr int M = E::M, P = E::P, TF = E::TF, N = 2 * M;
   constexpr int SLOTS = THREADS / TF;
   static_assert(THREADS % TF == 0 && SLOTS >= 1, "CTA must hold whole frames");
+  constexpr bool GEN = MODE == MD_GENERIC;
+  constexpr bool PHASE = GEN || (MODE & MD_PHASE) != 0;
   constexpr bool POST_SMEM = TF > 32;  // partner bin via shared memory instead of shuffle
   constexpr int SLOT_ELEMS = (E::NEEDS_SMEM || POST_SMEM) ? E::SMEM_ELEMS : 0;
 
@@ -125,12 +146,15 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
   const cx<T>* PDSP_RESTRICT post = static_cast<const cx<T>*>(p.post);
   const T* PDSP_RESTRICT win = static_cast<const T*>(p.window);
   const int lim = p.frame_len < N ? p.frame_len : N;
-  const int bins = p.two_sided ? N : M + 1;
-  const int cbins = p.cfull ? N : M + 1;
+  const bool two_sided = GEN ? p.two_sided != 0 : false;
+  const bool cfull = GEN ? p.cfull != 0 : true;
+  const int bins = two_sided ? N : M + 1;
+  const int cbins = cfull ? N : M + 1;
   const T s_edge = (T)p.scale_edge, s_mid = (T)p.scale_mid;
-  const bool want_cplx = p.out_re != nullptr;
-  const bool want_amp = p.amp != nullptr;
-  const bool want_peak = p.peaks != nullptr;
+  const bool want_cplx = GEN ? p.out_re != nullptr : (MODE & MD_CPLX) != 0;
+  const bool want_amp = GEN ? p.amp != nullptr : (MODE & MD_AMP) != 0;
+  const bool want_phase = GEN ? p.phase != nullptr : (MODE & MD_PHASE) != 0;
+  const bool want_peak = GEN ? p.peaks != nullptr : (MODE & MD_PEAK) != 0;
   const bool need_mag = want_amp || want_peak;
 
   for (long long f0 = (long long)simt::bid() * SLOTS; f0 < p.batch; f0 += (long long)simt::nblocks() * SLOTS) {
@@ -139,7 +163,25 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
 
     // ---- buildFrame + applyWindow fused into the load (spectrum.ts:36-43, fourier.ts:54-67)
     cx<T> v[P];
-    {
+    if constexpr (!GEN) {
+      // whole aligned frames: one vector load per complex point; a tail slot re-reads the last frame
+      const long long base = (valid ? f : p.batch - 1) * p.hop;
+      if (p.sample_dtype == DT_F32) {
+        const float* s = static_cast<const float*>(p.samples) + base;
+        static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
+      } else {
+        const double* s = static_cast<const double*>(p.samples) + base;
+        static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
+      }
+      if (win != nullptr) {
+        static_for<0, P>([&](auto qi) {
+          constexpr int q = decltype(qi)::value;
+          const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
+          v[q].x *= w.x;
+          v[q].y *= w.y;
+        });
+      }
+    } else {
       const long long base = valid ? f * p.hop : 0;
       const int lim_f = valid ? lim : 0;
       static_for<0, P>([&](auto qi) {
@@ -149,9 +191,9 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
         if (p.sample_dtype == DT_F32) {
           const float* s = static_cast<const float*>(p.samples) + base;
           if (p.vec_ok && i0 + 1 < lim_f) {
-            const cx<float> pr = *reinterpret_cast<const cx<float>*>(s + i0);
-            x0 = (T)pr.x;
-            x1 = (T)pr.y;
+            const cx<T> pr = load_pair<T>(s, i0);
+            x0 = pr.x;
+            x1 = pr.y;
           } else {
             if (i0 < lim_f) x0 = (T)s[i0];
             if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
@@ -159,9 +201,9 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
         } else {
           const double* s = static_cast<const double*>(p.samples) + base;
           if (p.vec_ok && i0 + 1 < lim_f) {
-            const cx<double> pr = *reinterpret_cast<const cx<double>*>(s + i0);
-            x0 = (T)pr.x;
-            x1 = (T)pr.y;
+            const cx<T> pr = load_pair<T>(s, i0);
+            x0 = pr.x;
+            x1 = pr.y;
           } else {
             if (i0 < lim_f) x0 = (T)s[i0];
             if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
@@ -183,41 +225,43 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
     T* o_re = valid && want_cplx ? static_cast<T*>(p.out_re) + f * cbins : nullptr;
     T* o_im = valid && want_cplx ? static_cast<T*>(p.out_im) + f * cbins : nullptr;
     T* o_amp = valid && want_amp ? static_cast<T*>(p.amp) + f * bins : nullptr;
-    T* o_ph = valid && PHASE && p.phase != nullptr ? static_cast<T*>(p.phase) + f * bins : nullptr;
+    T* o_ph = valid && PHASE && want_phase ? static_cast<T*>(p.phase) + f * bins : nullptr;
     PeakCand<T> best{(T)0, 0, (T)0, (T)0};
     T dc_re = (T)0, dc_amp = (T)0;
 
     // emit one bin k in [0, M] with value X
     auto emit = [&](int k, cx<T> X) {
-      if (o_re != nullptr) {
+      if (want_cplx && o_re != nullptr) {
         o_re[k] = X.x;
         o_im[k] = X.y;
-        if (p.cfull && k != 0 && k != M) {
+        if (cfull && k != 0 && k != M) {
           o_re[N - k] = X.x;
           o_im[N - k] = -X.y;
         }
       }
       if (need_mag) {
         const T a = t_mag(X.x, X.y) * ((k == 0 || k == M) ? s_edge : s_mid);
-        if (o_amp != nullptr) {
+        if (want_amp && o_amp != nullptr) {
           o_amp[k] = a;
-          if (p.two_sided && k != 0 && k != M) o_amp[N - k] = a;
+          if (two_sided && k != 0 && k != M) o_amp[N - k] = a;
         }
-        if (k == 0) {
-          dc_re = X.x;
-          dc_amp = a;
-        } else if (peak_better(a, k, best.v, best.k)) {
-          best.v = a;
-          best.k = k;
-          best.re = X.x;
-          best.im = X.y;
+        if (want_peak) {
+          if (k == 0) {
+            dc_re = X.x;
+            dc_amp = a;
+          } else if (peak_better(a, k, best.v, best.k)) {
+            best.v = a;
+            best.k = k;
+            best.re = X.x;
+            best.im = X.y;
+          }
         }
       }
       if constexpr (PHASE) {
-        if (o_ph != nullptr) {
+        if (want_phase && o_ph != nullptr) {
           const T ph = t_atan2(X.y, X.x);
           o_ph[k] = ph;
-          if (p.two_sided && k != 0 && k != M) o_ph[N - k] = -ph;
+          if (two_sided && k != 0 && k != M) o_ph[N - k] = -ph;
         }
       }
     };
@@ -247,12 +291,12 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
           zp = (t == 0) ? v[(P - q) % P] : got;
         }
         const cx<T> a = v[q];
-        const cx<T> sum{a.x + zp.x, a.y - zp.y};   // A + conj(Zp)
-        const cx<T> dif{a.x - zp.x, a.y + zp.y};   // A - conj(Zp)
-        const cx<T> w = ldg_cx(post + k);        // (wi/2, -wr/2): W_N^k * (-i/2)
+        const cx<T> sum{a.x + zp.x, a.y - zp.y};  // A + conj(Zp)
+        const cx<T> dif{a.x - zp.x, a.y + zp.y};  // A - conj(Zp)
+        const cx<T> w = ldg_cx(post + k);          // (wi/2, -wr/2): W_N^k * (-i/2)
         const cx<T> tt = cmul(dif, w);
-        cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};           // X[k]
-        cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};        // X[M-k] = conj(E - W*O)
+        cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};     // X[k]
+        cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};  // X[M-k] = conj(E - W*O)
         if constexpr (q == 0) {
           // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
           // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
@@ -265,7 +309,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
         emit(M - k, xb);
       });
       if (t == 0) emit(M / 2, cx<T>{v[P / 2].x, -v[P / 2].y});  // self-paired bin: conj(Z[M/2])
-      if constexpr (POST_SMEM) frame_sync<TF>(slot, SLOTS);  // partner reads done before smem is reused
+      if constexpr (POST_SMEM) frame_sync<TF>(slot, SLOTS);      // partner reads done before smem is reused
     }
 
     // ---- findPeak: (value desc, index asc) reduction over the frame's threads
@@ -324,8 +368,8 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) r2c_kernel(const R2CParams p) {
   }
 }
 
-template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, 1) c2c_kernel(const C2CParams p) {
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MINB>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) c2c_kernel(const C2CParams p) {
   using E = FftEngine<T, LOG2M, LOG2P, MAXRB>;
   constexpr int M = E::M, P = E::P, TF = E::TF;
   constexpr int SLOTS = THREADS / TF;

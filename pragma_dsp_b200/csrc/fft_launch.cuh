@@ -35,15 +35,15 @@ inline cudaError_t persistent_grid(KernelT kern, int threads, size_t smem, const
   return cudaSuccess;
 }
 
-template <typename T, int LOG2M, bool PHASE>
+template <typename T, int LOG2M, int MODE, int VAR = 0>
 cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
-  using C = KCfg<T, LOG2M>;
+  using C = KCfg<T, LOG2M, VAR>;
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS;
   constexpr int SLOTS = THREADS / E::TF;
   constexpr bool POST_SMEM = E::TF > 32;
   constexpr size_t SMEM = (E::NEEDS_SMEM || POST_SMEM) ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
-  auto kern = r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, PHASE, THREADS>;
+  auto kern = r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>;
   static int bps[kMaxDevices] = {0};
   if (p.batch <= 0) return cudaSuccess;
   int grid = 0;
@@ -60,7 +60,7 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
   constexpr int THREADS = C::THREADS;
   constexpr int SLOTS = THREADS / E::TF;
   constexpr size_t SMEM = E::NEEDS_SMEM ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
-  auto kern = c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS>;
+  auto kern = c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB>;
   static int bps[kMaxDevices] = {0};
   if (p.batch <= 0) return cudaSuccess;
   int grid = 0;
@@ -70,13 +70,44 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
   return cudaGetLastError();
 }
 
+// The output combinations that get a compile-time specialised kernel (everything else, and every
+// ragged/unaligned call, runs the generic kernel).
+#define PDSP_SPEC_MODES(X)                                                                          \
+  X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)
+
+inline bool mode_is_specialised(int mode) {
+  switch (mode) {
+#define X(m) \
+  case (m):  \
+    return true;
+    PDSP_SPEC_MODES(X)
+#undef X
+    default:
+      return false;
+  }
+}
+
 // One translation unit instantiates a contiguous range [LO, HI] of sizes (see inst.cu).
+// `mode` = 0 (generic) or one of PDSP_SPEC_MODES; the caller guarantees the specialised
+// kernels' preconditions (whole vector-aligned frames, one-sided rows).
 template <typename T, int L, int LO, int HI>
-cudaError_t r2c_case(bool phase, const R2CParams& p, const LaunchCtx& lc) {
-  if constexpr (L >= LO && L <= HI)
-    return phase ? launch_r2c_t<T, L, true>(p, lc) : launch_r2c_t<T, L, false>(p, lc);
-  else
+cudaError_t r2c_case(int mode, const R2CParams& p, const LaunchCtx& lc) {
+  if constexpr (L >= LO && L <= HI) {
+    if constexpr (L >= kMinSpecLog2M) {
+      switch (mode) {
+#define X(m) \
+  case (m):  \
+    return launch_r2c_t<T, L, (m)>(p, lc);
+        PDSP_SPEC_MODES(X)
+#undef X
+        default:
+          break;
+      }
+    }
+    return launch_r2c_t<T, L, MD_GENERIC>(p, lc);
+  } else {
     return cudaErrorInvalidValue;
+  }
 }
 template <typename T, int L, int LO, int HI>
 cudaError_t c2c_case(const C2CParams& p, const LaunchCtx& lc) {
@@ -86,7 +117,7 @@ cudaError_t c2c_case(const C2CParams& p, const LaunchCtx& lc) {
     return cudaErrorInvalidValue;
 }
 
-typedef cudaError_t (*r2c_group_fn)(int log2m, bool phase, const R2CParams& p, const LaunchCtx& lc);
+typedef cudaError_t (*r2c_group_fn)(int log2m, int mode, const R2CParams& p, const LaunchCtx& lc);
 typedef cudaError_t (*c2c_group_fn)(int log2m, const C2CParams& p, const LaunchCtx& lc);
 
 }  // namespace pdsp

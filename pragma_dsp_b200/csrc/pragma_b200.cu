@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -27,16 +28,45 @@ namespace pdsp {
 // launchers defined in the inst.cu translation units
 #define X(kind, tag, ctype, lo, hi) PDSP_DECL_##kind(tag, lo, hi)
 #define PDSP_DECL_0(tag, lo, hi) \
-  cudaError_t launch_r2c_##tag##_##lo##_##hi(int, bool, const R2CParams&, const LaunchCtx&);
+  cudaError_t launch_r2c_##tag##_##lo##_##hi(int, int, const R2CParams&, const LaunchCtx&);
 #define PDSP_DECL_1(tag, lo, hi) cudaError_t launch_c2c_##tag##_##lo##_##hi(int, const C2CParams&, const LaunchCtx&);
 PDSP_GROUPS(X)
 #undef X
 
-static cudaError_t dispatch_r2c(bool f64, int log2m, bool phase, const R2CParams& p, const LaunchCtx& lc) {
+// tuning variants (inst_var.cu), one symbol per (type, variant)
+#define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#define X(v)                                                                           \
+  cudaError_t launch_r2c_var_f64_##v(int, const R2CParams&, const LaunchCtx&);         \
+  cudaError_t launch_r2c_var_f32_##v(int, const R2CParams&, const LaunchCtx&);
+PDSP_VARS(X)
+#undef X
+
+static int env_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PDSP_VARIANT");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v >= kNumVariants) v = 0;
+  }
+  return v;
+}
+
+static cudaError_t dispatch_r2c(bool f64, int log2m, int mode, const R2CParams& p, const LaunchCtx& lc) {
+  if (log2m == kVariantLog2M && (mode == MD_AMP || mode == (MD_AMP | MD_PEAK) || mode == MD_PEAK)) {
+    switch (env_variant()) {
+#define X(v) \
+  case v:    \
+    return f64 ? launch_r2c_var_f64_##v(mode, p, lc) : launch_r2c_var_f32_##v(mode, p, lc);
+      PDSP_VARS(X)
+#undef X
+      default:
+        break;
+    }
+  }
 #define X(kind, tag, ctype, lo, hi) PDSP_TRY_R_##kind(tag, ctype, lo, hi)
 #define PDSP_TRY_R_0(tag, ctype, lo, hi)                                   \
   if (f64 == (sizeof(ctype) == 8) && log2m >= lo && log2m <= hi)           \
-    return launch_r2c_##tag##_##lo##_##hi(log2m, phase, p, lc);
+    return launch_r2c_##tag##_##lo##_##hi(log2m, mode, p, lc);
 #define PDSP_TRY_R_1(tag, ctype, lo, hi)
   PDSP_GROUPS(X)
 #undef X
@@ -363,7 +393,11 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
       k_r2c_n1<float><<<(int)blocks, threads, 0, st>>>(p);
     e = cudaGetLastError();
   } else {
-    e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, d_phase != nullptr, p, lc);
+    // compile-time specialised kernel when the call is the regular batched shape, generic otherwise
+    int mode = (d_amp ? MD_AMP : 0) | (d_phase ? MD_PHASE : 0) | (d_peaks ? MD_PEAK : 0) | (d_cre ? MD_CPLX : 0);
+    const bool regular = p.vec_ok && d->frame_len >= n && !p.two_sided && (d_cre == nullptr || cfull) &&
+                         mode_is_specialised(mode);
+    e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, regular ? mode : MD_GENERIC, p, lc);
   }
   if (e != cudaSuccess) return fail("r2c launch (n=%d): %s", n, cudaGetErrorString(e));
   c->launches++;

@@ -77,7 +77,8 @@ def _p(a):
 
 
 def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, window=None, sides="one",
-        sample_rate=1.0, raw=False, want=("complex", "amp", "phase", "peak"), cfull=True, nblocks=1):
+        sample_rate=1.0, raw=False, want=("complex", "amp", "phase", "peak"), cfull=True, nblocks=1,
+        specialised=False, variant=0):
     """Run r2c_kernel under the emulator. samples: 1-D float32/float64 array."""
     samples = np.ascontiguousarray(samples)
     assert samples.dtype in (np.float32, np.float64)
@@ -116,8 +117,17 @@ def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, w
     else:
         p.scale_edge, p.scale_mid = 1.0 / n, 2.0 / n
     p.bin_hz = sample_rate / n
-    rc = lib().emu_r2c(int(dtype == np.float64), log2m, C.byref(p), nblocks)
-    assert rc == 0, f"size {n} not instantiated in the emulator"
+    mode = 0
+    if specialised:  # compile-time specialised kernel (MD_* bits); preconditions are the caller's job
+        assert p.vec_ok and frame_len >= n and sides == "one" and cfull
+        mode = (1 if "amp" in want else 0) | (2 if "phase" in want else 0) | (4 if "peak" in want else 0) | \
+               (8 if "complex" in want else 0)
+    if variant:
+        assert mode in (1, 5, 4) and n == 1024
+        rc = lib().emu_r2c_var(int(dtype == np.float64), variant, C.byref(p), nblocks, mode)
+    else:
+        rc = lib().emu_r2c(int(dtype == np.float64), log2m, C.byref(p), nblocks, mode)
+    assert rc == 0, f"size {n} / mode {mode} not instantiated in the emulator (rc={rc})"
     return out
 
 

@@ -108,14 +108,30 @@ static void run_grid(int nblocks, int nthreads, size_t smem_bytes, F kernel) {
 
 using namespace pdsp;
 
-template <typename T, int LOG2M>
-static int run_r2c(const R2CParams& p, int nblocks) {
-  using C = KCfg<T, LOG2M>;
+template <typename T, int LOG2M, int MODE, int VAR = 0>
+static int run_r2c_m(const R2CParams& p, int nblocks) {
+  using C = KCfg<T, LOG2M, VAR>;
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS, SLOTS = THREADS / E::TF;
   constexpr size_t SMEM = sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS;
-  simt::run_grid(nblocks, THREADS, SMEM, [&] { r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, true, THREADS>(p); });
+  simt::run_grid(nblocks, THREADS, SMEM, [&] { r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>(p); });
   return 0;
+}
+// mode: 0 generic, else a specialised mode (only instantiated for the sizes the tests use)
+template <typename T, int LOG2M>
+static int run_r2c(const R2CParams& p, int nblocks, int mode) {
+  if constexpr (LOG2M == 5 || LOG2M == 7 || LOG2M == 9 || LOG2M == 11) {
+    switch (mode) {
+      case MD_AMP: return run_r2c_m<T, LOG2M, MD_AMP>(p, nblocks);
+      case MD_AMP | MD_PEAK: return run_r2c_m<T, LOG2M, MD_AMP | MD_PEAK>(p, nblocks);
+      case MD_PEAK: return run_r2c_m<T, LOG2M, MD_PEAK>(p, nblocks);
+      case MD_CPLX: return run_r2c_m<T, LOG2M, MD_CPLX>(p, nblocks);
+      case MD_AMP | MD_PHASE | MD_PEAK: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK>(p, nblocks);
+      default: break;
+    }
+  }
+  if (mode != 0) return -2;
+  return run_r2c_m<T, LOG2M, MD_GENERIC>(p, nblocks);
 }
 template <typename T, int LOG2M>
 static int run_c2c(const C2CParams& p, int nblocks) {
@@ -123,17 +139,17 @@ static int run_c2c(const C2CParams& p, int nblocks) {
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS, SLOTS = THREADS / E::TF;
   constexpr size_t SMEM = sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS;
-  simt::run_grid(nblocks, THREADS, SMEM, [&] { c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS>(p); });
+  simt::run_grid(nblocks, THREADS, SMEM, [&] { c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB>(p); });
   return 0;
 }
 
 #define EMU_SIZES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11)
 
-extern "C" int emu_r2c(int f64, int log2m, const R2CParams* p, int nblocks) {
+extern "C" int emu_r2c(int f64, int log2m, const R2CParams* p, int nblocks, int mode) {
   switch (log2m) {
 #define X(L) \
   case L:    \
-    return f64 ? run_r2c<double, L>(*p, nblocks) : run_r2c<float, L>(*p, nblocks);
+    return f64 ? run_r2c<double, L>(*p, nblocks, mode) : run_r2c<float, L>(*p, nblocks, mode);
     EMU_SIZES(X)
 #undef X
   }
@@ -145,6 +161,25 @@ extern "C" int emu_c2c(int f64, int log2m, const C2CParams* p, int nblocks) {
   case L:    \
     return f64 ? run_c2c<double, L>(*p, nblocks) : run_c2c<float, L>(*p, nblocks);
     EMU_SIZES(X)
+#undef X
+  }
+  return -1;
+}
+template <typename T, int VAR>
+static int run_var(const R2CParams& p, int nblocks, int mode) {
+  switch (mode) {
+    case MD_AMP: return run_r2c_m<T, kVariantLog2M, MD_AMP, VAR>(p, nblocks);
+    case MD_AMP | MD_PEAK: return run_r2c_m<T, kVariantLog2M, MD_AMP | MD_PEAK, VAR>(p, nblocks);
+    case MD_PEAK: return run_r2c_m<T, kVariantLog2M, MD_PEAK, VAR>(p, nblocks);
+  }
+  return -2;
+}
+extern "C" int emu_r2c_var(int f64, int var, const R2CParams* p, int nblocks, int mode) {
+  switch (var) {
+#define X(V) \
+  case V:    \
+    return f64 ? run_var<double, V>(*p, nblocks, mode) : run_var<float, V>(*p, nblocks, mode);
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
   }
   return -1;

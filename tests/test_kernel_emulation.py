@@ -170,3 +170,48 @@ def test_golden_reallife_through_emulated_kernel():
         assert np.abs(o["im"][i] - c.fftIm).max() <= 1e-10 * scale, c.name
         ref = oracle.spectrum(c.signal, sampleRate=c.sampleRate, fftSize=c.n)
         assert o["peaks"][i]["index"] == ref["peak"]["index"], c.name
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024, 4096])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("want", [("amp",), ("amp", "peak"), ("peak",), ("complex",), ("amp", "phase", "peak")])
+def test_specialised_kernels_equal_generic(n, dtype, want):
+    """The compile-time specialised kernels (MD_* modes) must produce the generic kernel's bits."""
+    rng = np.random.default_rng(n + len(want))
+    batch = 7  # not a multiple of the CTA's frame slots: exercises the tail slot
+    x = multitone(rng, batch, n).astype(dtype)
+    w = oracle.createWindow("hann", n)
+    kw = dict(dtype=dtype, batch=batch, window=w, sample_rate=48000.0, want=want, nblocks=2)
+    a = E.r2c(x.reshape(-1), n, **kw)
+    b = E.r2c(x.reshape(-1), n, specialised=True, **kw)
+    for key in a:
+        if key == "peaks":
+            assert (a[key] == b[key]).all()
+        else:
+            assert np.array_equal(a[key], b[key]), key
+    # rect window path of the specialised load
+    kw["window"] = None
+    a = E.r2c(x.reshape(-1), n, **kw)
+    b = E.r2c(x.reshape(-1), n, specialised=True, **kw)
+    for key in a:
+        assert (a[key] == b[key]).all()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tuning_variants_match_oracle(variant, dtype):
+    """Alternative thread/radix mappings of N=1024 (fft_config.h PDSP_VARIANT): radix-16 and radix-32
+    passes, 16-thread frames, two-warp frames with named barriers - same answers."""
+    n, batch = 1024, 11
+    rng = np.random.default_rng(variant)
+    x = multitone(rng, batch, n).astype(dtype)
+    w = oracle.createWindow("hann", n)
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann")
+    o = E.r2c(x.reshape(-1), n, dtype=dtype, batch=batch, window=w, sample_rate=48000.0, want=("amp", "peak"),
+              nblocks=2, specialised=True, variant=variant)
+    atol = 1e-13 if dtype == np.float64 else 3e-6
+    assert np.abs(o["amp"] - ref["amplitude"]).max() <= atol
+    assert (o["peaks"]["index"] == ref["peaks"]["index"]).all()
+    o2 = E.r2c(x.reshape(-1), n, dtype=dtype, batch=batch, window=w, sample_rate=48000.0, want=("peak",),
+               nblocks=1, specialised=True, variant=variant)
+    assert (o2["peaks"] == o["peaks"]).all()
