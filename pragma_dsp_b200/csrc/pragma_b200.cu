@@ -42,13 +42,10 @@ PDSP_VARS(X)
 #undef X
 
 static int env_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PDSP_VARIANT");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v >= kNumVariants) v = 0;
-  }
-  return v;
+  // read on every launch (a getenv is nanoseconds) so one process can sweep the variants
+  const char* e = getenv("PDSP_VARIANT");
+  const int v = e ? atoi(e) : 0;
+  return (v < 0 || v >= kNumVariants) ? 0 : v;
 }
 
 static cudaError_t dispatch_r2c(bool f64, int log2m, int mode, const R2CParams& p, const LaunchCtx& lc) {
