@@ -1,6 +1,10 @@
 // fft_launch.cuh - per-size kernel configuration and persistent-grid launchers.
 #pragma once
+#ifdef PDSP_EMU
+#include "cuda_stub.h"  // tests/simt_emu: host stand-in for the runtime API (test builds only)
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include "fft_config.h"
 #include "fft_kernels.cuh"
@@ -49,7 +53,7 @@ cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
   int grid = 0;
   cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
   if (e != cudaSuccess) return e;
-  kern<<<grid, THREADS, SMEM, lc.stream>>>(p);
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
   return cudaGetLastError();
 }
 
@@ -66,7 +70,7 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
   int grid = 0;
   cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
   if (e != cudaSuccess) return e;
-  kern<<<grid, THREADS, SMEM, lc.stream>>>(p);
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
   return cudaGetLastError();
 }
 

@@ -5,7 +5,11 @@
 // constants, computed in extended precision on the host and uploaded), move bytes between
 // caller memory and HBM through pinned staging on two streams, and launch the kernels in
 // fft_kernels.cuh.  There is no CPU implementation of the transform in this library.
+#ifdef PDSP_EMU
+#include "cuda_stub.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -33,8 +37,12 @@ namespace pdsp {
 PDSP_GROUPS(X)
 #undef X
 
-// tuning variants (inst_var.cu), one symbol per (type, variant)
+// tuning variants (inst_var.cu), one symbol per (type, variant); not built into the emulated test library
+#ifdef PDSP_EMU
+#define PDSP_VARS(X)
+#else
 #define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#endif
 #define X(v)                                                                           \
   cudaError_t launch_r2c_var_f64_##v(int, const R2CParams&, const LaunchCtx&);         \
   cudaError_t launch_r2c_var_f32_##v(int, const R2CParams&, const LaunchCtx&);
@@ -81,21 +89,23 @@ static cudaError_t dispatch_c2c(bool f64, int log2m, const C2CParams& p, const L
 }
 
 // ---- small elementwise kernels: magnitude()/phase() on caller arrays, N = 1 frames ----------
-__global__ void k_magnitude(const double* __restrict__ re, const double* __restrict__ im, long long n,
-                            double* __restrict__ out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+PDSP_GLOBAL void k_magnitude(const double* PDSP_RESTRICT re, const double* PDSP_RESTRICT im, long long n,
+                             double* PDSP_RESTRICT out) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride)
     out[i] = hypot(re[i], im[i]);
 }
-__global__ void k_phase(const double* __restrict__ re, const double* __restrict__ im, long long n,
-                        double* __restrict__ out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+PDSP_GLOBAL void k_phase(const double* PDSP_RESTRICT re, const double* PDSP_RESTRICT im, long long n,
+                         double* PDSP_RESTRICT out) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride)
     out[i] = atan2(im[i], re[i]);
 }
 // N = 1: X[0] = x[0] * w[0] (createWindow(size 1) = [1]); one thread per frame
 template <typename T>
-__global__ void k_r2c_n1(const R2CParams p) {
-  for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < p.batch;
-       f += (long long)gridDim.x * blockDim.x) {
+PDSP_GLOBAL void k_r2c_n1(const R2CParams p) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  for (long long f = simt::bid() * (long long)simt::nthreads() + simt::tid(); f < p.batch; f += stride) {
     T x = (T)0;
     if (p.frame_len >= 1)
       x = p.sample_dtype == DT_F32 ? (T) static_cast<const float*>(p.samples)[f * p.hop]
@@ -104,8 +114,8 @@ __global__ void k_r2c_n1(const R2CParams p) {
       static_cast<T*>(p.out_re)[f] = x;
       static_cast<T*>(p.out_im)[f] = (T)0;
     }
-    const T a = fabs(x) * (T)p.scale_edge;
-    const T ph = atan2((T)0, x);
+    const T a = (T)fabs((double)x) * (T)p.scale_edge;
+    const T ph = (T)atan2(0.0, (double)x);
     if (p.amp) static_cast<T*>(p.amp)[f] = a;
     if (p.phase) static_cast<T*>(p.phase)[f] = ph;
     if (p.peaks) {
@@ -169,7 +179,8 @@ struct pdsp_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   Slot slots[kSlots];
-  std::mutex mu;
+  std::mutex mu;       // serialises the host-entry staging pipeline (slots)
+  std::mutex plan_mu;  // guards the plan cache and lazily built window tables (taken inside `mu`)
   std::map<std::pair<int, int>, pdsp_plan*> plans;
   std::atomic<long long> launches{0};
 };
@@ -315,7 +326,7 @@ static int plan_window(pdsp_plan* pl, int window, const void** d_win) {
     *d_win = nullptr;
     return 0;
   }
-  std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  std::lock_guard<std::mutex> lk(pl->ctx->plan_mu);
   if (!pl->d_win[window]) {
     std::vector<double> w((size_t)pl->n);
     if (window_host(window, pl->n, w.data())) return 1;
@@ -385,9 +396,9 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     long long blocks = (batch + threads - 1) / threads;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     if (pl->precision == PDSP_F64)
-      k_r2c_n1<double><<<(int)blocks, threads, 0, st>>>(p);
+      PDSP_LAUNCH(k_r2c_n1<double>, (int)blocks, threads, 0, st, p);
     else
-      k_r2c_n1<float><<<(int)blocks, threads, 0, st>>>(p);
+      PDSP_LAUNCH(k_r2c_n1<float>, (int)blocks, threads, 0, st, p);
     e = cudaGetLastError();
   } else {
     // compile-time specialised kernel when the call is the regular batched shape, generic otherwise
@@ -606,7 +617,7 @@ PDSP_EXPORT int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_pla
   if (log2n - 1 > kMaxLog2M)
     return fail("FFT size %d exceeds the in-CTA limit %d (four-step path not built yet)", size, 2 << kMaxLog2M);
   if (set_device(c)) return 1;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::mutex> lk(c->plan_mu);
   auto key = std::make_pair((int)size, precision);
   auto it = c->plans.find(key);
   if (it != c->plans.end()) {
@@ -823,10 +834,13 @@ static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int
   CU(cudaMemcpyAsync(din + al, im, bytes, cudaMemcpyHostToDevice, s.stream));
   long long blocks = (n + 255) / 256;
   if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
+  const double* d_re = reinterpret_cast<const double*>(din);
+  const double* d_im = reinterpret_cast<const double*>(din + al);
+  double* d_o = static_cast<double*>(s.d_out);
   if (mag)
-    k_magnitude<<<(int)blocks, 256, 0, s.stream>>>((const double*)din, (const double*)(din + al), n, (double*)s.d_out);
+    PDSP_LAUNCH(k_magnitude, (int)blocks, 256, 0, s.stream, d_re, d_im, (long long)n, d_o);
   else
-    k_phase<<<(int)blocks, 256, 0, s.stream>>>((const double*)din, (const double*)(din + al), n, (double*)s.d_out);
+    PDSP_LAUNCH(k_phase, (int)blocks, 256, 0, s.stream, d_re, d_im, (long long)n, d_o);
   CU(cudaGetLastError());
   c->launches++;
   CU(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));

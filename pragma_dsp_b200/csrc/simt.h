@@ -17,6 +17,7 @@
 #define PDSP_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL _Pragma("unroll")
+#define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) kernel<<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__)
 
 namespace simt {
 PDSP_DEVICE int tid() { return (int)threadIdx.x; }
@@ -52,14 +53,20 @@ PDSP_DEVICE T ldg(const T* p) {
 #include <math.h>
 #include <string.h>
 
+#include <functional>
+
 #define PDSP_DEVICE inline
 #define PDSP_DEVICE_NOINLINE static inline
 #define PDSP_GLOBAL
 #define PDSP_LAUNCH_BOUNDS(t, b)
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL
+#define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) \
+  simt::emu_launch((grid), (threads), (smem), [=] { kernel(__VA_ARGS__); })
 
 namespace simt {
+// runs `body` once per emulated CUDA thread, CTA after CTA (tests/simt_emu/emu_runtime.cc)
+void emu_launch(int grid, int threads, size_t smem_bytes, const std::function<void()>& body);
 struct EmuThread {
   int tid, bid, nblocks, nthreads;
   unsigned char* smem;

@@ -34,21 +34,68 @@ PEAK64 = np.dtype([("index", "<i4"), ("_pad", "<i4"), ("frequency", "<f8"), ("am
 PEAK32 = np.dtype([("index", "<i4"), ("frequency", "<f4"), ("amplitude", "<f4"), ("phase", "<f4")])
 
 _lib = None
+_CXX = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-DPDSP_EMU=1", "-I", _HERE]
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+
+
+def _stale(target, srcs):
+    return not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(s) for s in srcs)
+
+
+def _headers():
+    return [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".h", ".cuh"))] + \
+           [os.path.join(_HERE, "cuda_stub.h"), os.path.join(_HERE, "emu_runtime.cc")]
 
 
 def lib():
+    """Kernel-level harness: emu.cpp + emu_runtime.cc -> libpdsp_emu.so."""
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_HERE, "emu.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)
-                                                   if f.endswith((".h", ".cuh"))]
-        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
-            subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
-                            "-o", _SO, os.path.join(_HERE, "emu.cpp")], check=True)
+        srcs = [os.path.join(_HERE, "emu.cpp")] + _headers()
+        if _stale(_SO, srcs):
+            subprocess.run(_CXX + ["-shared", "-o", _SO, os.path.join(_HERE, "emu.cpp"),
+                                   os.path.join(_HERE, "emu_runtime.cc")], check=True)
         L = C.CDLL(_SO)
         assert L.emu_params_size(0) == C.sizeof(R2CParams), (L.emu_params_size(0), C.sizeof(R2CParams))
         assert L.emu_params_size(1) == C.sizeof(C2CParams)
         _lib = L
     return _lib
+
+
+CABI_EMU_SO = os.path.join(_HERE, "libpragma_b200_emu.so")
+
+
+def build_cabi_emulated():
+    """The whole C-ABI library (pragma_b200.cu + a reduced set of inst.cu units) compiled for the host
+    against cuda_stub.h, kernels running under the emulator: exercises the host pipeline without a GPU.
+    TEST ONLY - loaded by tests/test_host_pipeline_emulated.py through a monkeypatched LIB_PATH."""
+    import concurrent.futures as cf
+    import re
+    srcs = _headers() + [os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(_CSRC, "inst.cu"),
+                         os.path.join(_ROOT, "include", "pragma_b200.h")]
+    if not _stale(CABI_EMU_SO, srcs):
+        return CABI_EMU_SO
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    txt = open(os.path.join(_CSRC, "inst_groups.h")).read()
+    txt = txt[:txt.index("#else")]
+    units = [(os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(objdir, "pragma_b200.o"), []),
+             (os.path.join(_HERE, "emu_runtime.cc"), os.path.join(objdir, "emu_runtime.o"), [])]
+    for kind, tag, ctype, lo, hi in re.findall(r"X\((\d), (\w+), (\w+), (\d+), (\d+)\)", txt):
+        name = f"launch_{'r2c' if kind == '0' else 'c2c'}_{tag}_{lo}_{hi}"
+        units.append((os.path.join(_CSRC, "inst.cu"), os.path.join(objdir, name + ".o"),
+                      [f"-DPDSP_INST_KIND={kind}", f"-DPDSP_INST_T={ctype}", f"-DPDSP_INST_LO={lo}",
+                       f"-DPDSP_INST_HI={hi}", f"-DPDSP_INST_NAME={name}"]))
+
+    def cc(u):
+        src, obj, defs = u
+        subprocess.run(_CXX + ["-fvisibility=hidden", "-x", "c++", "-c", src, "-o", obj] + defs, check=True)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(cc, units))
+    subprocess.run(["/usr/bin/g++", "-shared", "-pthread", "-o", CABI_EMU_SO] + objs, check=True)
+    return CABI_EMU_SO
 
 
 def tables(n, dtype):

@@ -6,105 +6,10 @@
 // synchronisation and the epilogue logic of the real kernels can be checked against the oracle
 // in the build container (no GPU).  Arithmetic differs from the device only by FMA contraction.
 // Never linked into libpragma_b200.so; the product has no CPU path.
-#include <condition_variable>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <thread>
-#include <vector>
 
 #define PDSP_EMU 1
 #include "../../pragma_dsp_b200/csrc/fft_config.h"
 #include "../../pragma_dsp_b200/csrc/fft_kernels.cuh"
-
-namespace simt {
-class Barrier {
- public:
-  explicit Barrier(int n) : n_(n) {}
-  void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    const long gen = gen_;
-    if (++count_ == n_) {
-      count_ = 0;
-      ++gen_;
-      cv_.notify_all();
-    } else {
-      cv_.wait(lk, [&] { return gen_ != gen; });
-    }
-  }
-
- private:
-  std::mutex m_;
-  std::condition_variable cv_;
-  int n_, count_ = 0;
-  long gen_ = 0;
-};
-
-struct EmuBlock {
-  int nthreads;
-  std::vector<unsigned char> smem;
-  std::unique_ptr<Barrier> block_bar;
-  std::vector<std::unique_ptr<Barrier>> warp_bar;
-  std::vector<unsigned char> mailbox;  // 16 B per thread
-  std::mutex named_mu;
-  std::map<int, std::unique_ptr<Barrier>> named;
-};
-
-thread_local EmuThread emu_self;
-static EmuBlock* blk() { return static_cast<EmuBlock*>(emu_self.block); }
-
-void emu_sync_warp() { blk()->warp_bar[emu_self.tid / 32]->wait(); }
-void emu_sync_block() { blk()->block_bar->wait(); }
-void emu_sync_named(int id, int nthreads) {
-  Barrier* b;
-  {
-    std::lock_guard<std::mutex> lk(blk()->named_mu);
-    auto& slot = blk()->named[id];
-    if (!slot) slot.reset(new Barrier(nthreads));
-    b = slot.get();
-  }
-  b->wait();
-}
-void emu_shfl(const void* in, void* out, int bytes, int src_lane, int width, bool is_xor) {
-  EmuBlock* b = blk();
-  const int tid = emu_self.tid, lane = tid & 31, warp_base = tid & ~31;
-  memcpy(&b->mailbox[(size_t)tid * 16], in, (size_t)bytes);
-  emu_sync_warp();
-  int src;
-  if (is_xor)
-    src = lane ^ src_lane;
-  else
-    src = (lane & ~(width - 1)) | (src_lane & (width - 1));
-  memcpy(out, &b->mailbox[(size_t)(warp_base + src) * 16], (size_t)bytes);
-  emu_sync_warp();
-}
-
-template <typename F>
-static void run_grid(int nblocks, int nthreads, size_t smem_bytes, F kernel) {
-  for (int bid = 0; bid < nblocks; ++bid) {
-    EmuBlock b;
-    b.nthreads = nthreads;
-    b.smem.assign(smem_bytes + 64, 0xCD);  // poison: uninitialised reads show up as garbage
-    b.block_bar.reset(new Barrier(nthreads));
-    for (int w = 0; w * 32 < nthreads; ++w) {
-      int n = nthreads - w * 32;
-      b.warp_bar.emplace_back(new Barrier(n < 32 ? n : 32));
-    }
-    b.mailbox.assign((size_t)nthreads * 16, 0);
-    unsigned char* sm = b.smem.data();
-    sm += (16 - (reinterpret_cast<uintptr_t>(sm) & 15)) & 15;
-    std::vector<std::thread> th;
-    th.reserve((size_t)nthreads);
-    for (int t = 0; t < nthreads; ++t) {
-      th.emplace_back([&, t] {
-        emu_self = EmuThread{t, bid, nblocks, nthreads, sm, &b};
-        kernel();
-      });
-    }
-    for (auto& x : th) x.join();
-  }
-}
-}  // namespace simt
 
 using namespace pdsp;
 
@@ -114,7 +19,7 @@ static int run_r2c_m(const R2CParams& p, int nblocks) {
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS, SLOTS = THREADS / E::TF;
   constexpr size_t SMEM = sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS;
-  simt::run_grid(nblocks, THREADS, SMEM, [&] { r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>(p); });
+  simt::emu_launch(nblocks, THREADS, SMEM, [&] { r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>(p); });
   return 0;
 }
 // mode: 0 generic, else a specialised mode (only instantiated for the sizes the tests use)
@@ -139,7 +44,7 @@ static int run_c2c(const C2CParams& p, int nblocks) {
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS, SLOTS = THREADS / E::TF;
   constexpr size_t SMEM = sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS;
-  simt::run_grid(nblocks, THREADS, SMEM, [&] { c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB>(p); });
+  simt::emu_launch(nblocks, THREADS, SMEM, [&] { c2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB>(p); });
   return 0;
 }
 

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 def impl():
     from pragma_dsp_b200 import spectrum
     from pragma_dsp_b200.core import ComplexArray
-    from pragma_dsp_b200.xform import FFT, binFrequencies, createWindow, magnitude, phase
+    from pragma_dsp_b200 import xform
+    from pragma_dsp_b200.xform import FFT, magnitude, phase
 
     class B200Impl:
         @staticmethod
@@ -33,8 +34,8 @@ def impl():
         def phase(re, im):
             return phase(ComplexArray(np.asarray(re), np.asarray(im)))
 
-        createWindow = staticmethod(createWindow)
-        binFrequencies = staticmethod(binFrequencies)
+        createWindow = staticmethod(xform.createWindow)
+        binFrequencies = staticmethod(xform.binFrequencies)
 
         @staticmethod
         def spectrum(x, sampleRate=1.0, fftSize=None, window="rect", sides="one"):
