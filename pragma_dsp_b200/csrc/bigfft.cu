@@ -1,0 +1,39 @@
+// bigfft.cu - instantiations and launcher of the multi-pass large-N FFT kernel (bigfft_kernels.cuh).
+#include "bigfft_kernels.cuh"
+#include "fft_launch.cuh"
+
+namespace pdsp {
+
+template <typename T, int LOG2L>
+static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
+  using B = BigCfg<T, LOG2L>;
+  using E = FftEngine<T, LOG2L, B::LOG2P, B::MAXRB>;
+  constexpr int THREADS = B::TF * B::C;
+  constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * B::C;
+  auto kern = bigfft_pass_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C>;
+  static int bps[kMaxDevices] = {0};
+  if (p.n_groups <= 0) return cudaSuccess;
+  int grid = 0;
+  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, p.n_groups, &grid);
+  if (e != cudaSuccess) return e;
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
+  return cudaGetLastError();
+}
+
+int big_pass_c(int log2l) {
+  return log2l == 10 ? BigCfg<double, 10>::C : BigCfg<double, 9>::C;
+}
+
+cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const LaunchCtx& lc) {
+  switch (log2l) {
+#define X(L) \
+  case L:    \
+    return f64 ? launch_big_t<double, L>(p, lc) : launch_big_t<float, L>(p, lc);
+    X(6) X(7) X(8) X(9) X(10)
+#undef X
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace pdsp

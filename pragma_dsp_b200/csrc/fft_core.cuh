@@ -158,8 +158,17 @@ struct FftEngine {
 
   // v[q] holds element t + TF*q (natural order) on entry and the transform on exit.
   // tw: table exp(-2*pi*i*k/NT), NT = M * tw_stride.
+  // BLOCKSYNC: the frame's threads are spread over the CTA's warps (column-tiled passes of the
+  // large-N path), so every exchange is a __syncthreads.
+  template <bool BLOCKSYNC = false>
   PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int tw_stride,
                               int slot, int slots_per_cta) {
+    auto sync = [&]() {
+      if constexpr (BLOCKSYNC)
+        simt::sync_block();
+      else
+        frame_sync<TF>(slot, slots_per_cta);
+    };
     static_for<0, NPASS>([&](auto pi) {
       constexpr int pass = decltype(pi)::value;
       constexpr int b = pass_bits(pass);
@@ -192,9 +201,9 @@ struct FftEngine {
         }
       });
       if constexpr (!last) {
-        frame_sync<TF>(slot, slots_per_cta);
+        sync();
         static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
-        frame_sync<TF>(slot, slots_per_cta);
+        sync();
       }
     });
   }

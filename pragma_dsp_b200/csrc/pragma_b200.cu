@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/pragma_b200.h"
+#include "bigfft_kernels.cuh"
 #include "fft_launch.cuh"
 #include "inst_groups.h"
 
@@ -36,6 +37,10 @@ namespace pdsp {
 #define PDSP_DECL_1(tag, lo, hi) cudaError_t launch_c2c_##tag##_##lo##_##hi(int, const C2CParams&, const LaunchCtx&);
 PDSP_GROUPS(X)
 #undef X
+
+// multi-pass large-N path (bigfft.cu)
+int big_pass_c(int log2l);
+cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const LaunchCtx& lc);
 
 // tuning variants (inst_var.cu), one symbol per (type, variant); not built into the emulated test library
 #ifdef PDSP_EMU
@@ -151,6 +156,7 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------------ objects
+static const int kMaxBigLog2N = 28;  // largest multi-pass transform (2^28 complex points)
 static const int kSlots = 3;  // staging pipeline depth (chunks in flight)
 
 struct Slot {
@@ -180,9 +186,21 @@ struct pdsp_ctx {
   cudaStream_t stream = nullptr;
   Slot slots[kSlots];
   std::mutex mu;       // serialises the host-entry staging pipeline (slots)
-  std::mutex plan_mu;  // guards the plan cache and lazily built window tables (taken inside `mu`)
+  std::recursive_mutex plan_mu;  // guards the plan cache and lazily built tables (taken inside `mu`)
   std::map<std::pair<int, int>, pdsp_plan*> plans;
   std::atomic<long long> launches{0};
+};
+
+// multi-pass plan of a transform too long for one CTA: N = 2^lg[0] * 2^lg[1] (* 2^lg[2])
+struct BigPlan {
+  int npass = 0;
+  int lg[3] = {0, 0, 0};
+  pdsp_plan* sub[3] = {nullptr, nullptr, nullptr};  // plans of the pass lengths (their twiddle tables)
+  void* tw_hi[2] = {nullptr, nullptr};               // two-level inter-pass twiddles of passes 0 and 1
+  void* tw_lo[2] = {nullptr, nullptr};
+  int log_b[2] = {0, 0};
+  void* work_re = nullptr;  // intermediate planes, N elements each
+  void* work_im = nullptr;
 };
 
 struct pdsp_plan {
@@ -190,9 +208,10 @@ struct pdsp_plan {
   int n;
   int log2n;
   int precision;
-  void* d_tw = nullptr;    // cx<T>[n]
+  void* d_tw = nullptr;    // cx<T>[n]   (in-CTA sizes only)
   void* d_post = nullptr;  // cx<T>[n/4 + 1]
   void* d_win[4] = {nullptr, nullptr, nullptr, nullptr};
+  BigPlan* big = nullptr;  // built lazily for n > 8192
 };
 
 static int set_device(const pdsp_ctx* c) {
@@ -326,7 +345,7 @@ static int plan_window(pdsp_plan* pl, int window, const void** d_win) {
     *d_win = nullptr;
     return 0;
   }
-  std::lock_guard<std::mutex> lk(pl->ctx->plan_mu);
+  std::lock_guard<std::recursive_mutex> lk(pl->ctx->plan_mu);
   if (!pl->d_win[window]) {
     std::vector<double> w((size_t)pl->n);
     if (window_host(window, pl->n, w.data())) return 1;
@@ -412,11 +431,167 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
   return 0;
 }
 
+// ------------------------------------------------------------------------------ large-N (multi-pass) path
+template <typename T>
+static int upload_big_twiddles(int log_nt, int log_b, void** d_hi, void** d_lo) {
+  const long long nt = 1LL << log_nt, nb = 1LL << log_b, nh = nt >> log_b;
+  std::vector<cx<T>> hi((size_t)nh), lo((size_t)nb);
+  for (long long a = 0; a < nh; ++a) {
+    long double re, im;
+    twiddle((int)(a << log_b), (int)nt, &re, &im);
+    hi[(size_t)a] = cx<T>{(T)re, (T)im};
+  }
+  for (long long b = 0; b < nb; ++b) {
+    long double re, im;
+    twiddle((int)b, (int)nt, &re, &im);
+    lo[(size_t)b] = cx<T>{(T)re, (T)im};
+  }
+  CU(cudaMalloc(d_hi, sizeof(cx<T>) * hi.size()));
+  CU(cudaMalloc(d_lo, sizeof(cx<T>) * lo.size()));
+  CU(cudaMemcpy(*d_hi, hi.data(), sizeof(cx<T>) * hi.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(*d_lo, lo.data(), sizeof(cx<T>) * lo.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_plan** out);
+
+// Builds (once) the pass structure of a large transform.  *out stays null when PDSP_BIG_FACTORS is
+// set but does not describe this size (the in-CTA kernel is used instead).
+static int big_plan(pdsp_plan* pl, BigPlan** out) {
+  *out = nullptr;
+  std::lock_guard<std::recursive_mutex> lk(pl->ctx->plan_mu);
+  if (pl->big) {
+    *out = pl->big;
+    return 0;
+  }
+  const int n = pl->log2n;
+  int lg[3] = {0, 0, 0}, np = 0;
+  if (const char* e = getenv("PDSP_BIG_FACTORS")) {  // test hook: "a,b[,c]" = log2 of the pass lengths
+    int a = 0, b = 0, c3 = 0;
+    const int got = sscanf(e, "%d,%d,%d", &a, &b, &c3);
+    if (got >= 2 && a + b + (got == 3 ? c3 : 0) == n) {
+      lg[0] = a, lg[1] = b, lg[2] = got == 3 ? c3 : 0;
+      np = got;
+    } else if (n <= kMaxLog2M) {
+      return 0;
+    }
+  }
+  if (np == 0) {
+    np = n <= 2 * kBigMaxLog2L ? 2 : 3;
+    for (int j = 0; j < np; ++j) lg[j] = n / np + (j < n % np ? 1 : 0);
+  }
+  for (int j = 0; j < np; ++j)
+    if (lg[j] < kBigMinLog2L || lg[j] > kBigMaxLog2L)
+      return fail("FFT size 2^%d cannot be split into %d passes of 2^%d..2^%d points", n, np, kBigMinLog2L, kBigMaxLog2L);
+  BigPlan* bp = new BigPlan();
+  bp->npass = np;
+  const size_t es = esize(pl->precision);
+  for (int j = 0; j < np; ++j) {
+    bp->lg[j] = lg[j];
+    if (pdsp_plan_get(pl->ctx, 1 << lg[j], pl->precision, &bp->sub[j])) {
+      delete bp;
+      return 1;
+    }
+  }
+  int rest = n;  // log2(L_j * I_j) of pass j
+  for (int j = 0; j + 1 < np; ++j) {
+    bp->log_b[j] = (rest + 1) / 2;
+    const int rc = pl->precision == PDSP_F64 ? upload_big_twiddles<double>(rest, bp->log_b[j], &bp->tw_hi[j], &bp->tw_lo[j])
+                                             : upload_big_twiddles<float>(rest, bp->log_b[j], &bp->tw_hi[j], &bp->tw_lo[j]);
+    if (rc) return 1;
+    rest -= lg[j];
+  }
+  CU(cudaMalloc(&bp->work_re, es << n));
+  CU(cudaMalloc(&bp->work_im, es << n));
+  pl->big = bp;
+  *out = bp;
+  return 0;
+}
+
+static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
+                      void* d_oim, int inverse, cudaStream_t st) {
+  pdsp_ctx* c = pl->ctx;
+  const size_t es = esize(pl->precision);
+  const long long N = 1LL << pl->log2n;
+  LaunchCtx lc{c->device, c->sm_count, st};
+  const int np = bp->npass;
+  long long Ls[3] = {1, 1, 1};
+  for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
+  for (long long f = 0; f < batch; ++f) {
+    const char* fre = static_cast<const char*>(d_re) + (size_t)f * N * es;
+    const char* fim = d_im ? static_cast<const char*>(d_im) + (size_t)f * N * es : nullptr;
+    char* gre = static_cast<char*>(d_ore) + (size_t)f * N * es;
+    char* gim = static_cast<char*>(d_oim) + (size_t)f * N * es;
+    long long O = 1, I = N;
+    for (int j = 0; j < np; ++j) {
+      const long long L = Ls[j];
+      I /= L;
+      const int C = big_pass_c(bp->lg[j]);
+      const bool last = j == np - 1;
+      BigPassParams p;
+      memset(&p, 0, sizeof p);
+      p.in_re = j == 0 ? (const void*)fre : bp->work_re;
+      p.in_im = j == 0 ? (const void*)fim : bp->work_im;
+      p.out_re = last ? (void*)gre : bp->work_re;
+      p.out_im = last ? (void*)gim : bp->work_im;
+      p.tw = bp->sub[j]->d_tw;
+      p.swap_in = (j == 0 && inverse) ? 1 : 0;
+      p.swap_out = (last && inverse) ? 1 : 0;
+      p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
+      if (!last) {
+        // view [O][L][I]: C adjacent inner indices per CTA, transform along the stride-I axis in place
+        p.n_lo = I / C;
+        p.n_groups = O * p.n_lo;
+        p.in_hi = p.out_hi = L * I;
+        p.in_lo = p.out_lo = C;
+        p.in_c = p.out_c = 1;
+        p.in_e = p.out_e = I;
+        p.tw_hi = bp->tw_hi[j];
+        p.tw_lo = bp->tw_lo[j];
+        p.log_b = bp->log_b[j];
+        p.stage_in = 0;
+      } else if (np == 2) {
+        // rows k1 (contiguous, L2 long); C adjacent k1 per CTA; X[k1 + L1*k2]
+        p.n_lo = 1;
+        p.n_groups = Ls[0] / C;
+        p.in_hi = C * L;
+        p.in_c = L;
+        p.in_e = 1;
+        p.out_hi = C;
+        p.out_c = 1;
+        p.out_e = Ls[0];
+        p.stage_in = 1;
+      } else {
+        // rows (k1, k2); groups (k1 tile, k2); X[k1 + L1*k2 + L1*L2*k3]
+        p.n_lo = Ls[1];
+        p.n_groups = (Ls[0] / C) * Ls[1];
+        p.in_hi = C * Ls[1] * L;
+        p.in_lo = L;
+        p.in_c = Ls[1] * L;
+        p.in_e = 1;
+        p.out_hi = C;
+        p.out_lo = Ls[0];
+        p.out_c = 1;
+        p.out_e = Ls[0] * Ls[1];
+        p.stage_in = 1;
+      }
+      cudaError_t e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
+      if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d): %s", j, pl->log2n, cudaGetErrorString(e));
+      c->launches++;
+      O *= L;
+    }
+  }
+  return 0;
+}
+
 static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
                       int inverse, cudaStream_t st) {
   pdsp_ctx* c = pl->ctx;
-  if (pl->log2n > kMaxLog2M)
-    return fail("complex transforms above %d points are not supported by the in-CTA path", 1 << kMaxLog2M);
+  if (pl->log2n > kMaxLog2M || getenv("PDSP_BIG_FACTORS")) {
+    BigPlan* bp = nullptr;
+    if (big_plan(pl, &bp)) return 1;
+    if (bp) return launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st);
+  }
   C2CParams p;
   memset(&p, 0, sizeof p);
   p.in_re = d_re;
@@ -557,6 +732,15 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
     cudaFree(pl->d_tw);
     cudaFree(pl->d_post);
     for (int i = 0; i < 4; ++i) cudaFree(pl->d_win[i]);
+    if (pl->big) {
+      for (int i = 0; i < 2; ++i) {
+        cudaFree(pl->big->tw_hi[i]);
+        cudaFree(pl->big->tw_lo[i]);
+      }
+      cudaFree(pl->big->work_re);
+      cudaFree(pl->big->work_im);
+      delete pl->big;
+    }
     delete pl;
   }
   for (int i = 0; i < kSlots; ++i) {
@@ -614,10 +798,9 @@ PDSP_EXPORT int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_pla
   if (precision != PDSP_F32 && precision != PDSP_F64) return fail("unknown precision %d", precision);
   int log2n = 0;
   while ((1 << log2n) < size) ++log2n;
-  if (log2n - 1 > kMaxLog2M)
-    return fail("FFT size %d exceeds the in-CTA limit %d (four-step path not built yet)", size, 2 << kMaxLog2M);
+  if (log2n > kMaxBigLog2N) return fail("FFT size %d exceeds the supported maximum 2^%d", size, kMaxBigLog2N);
   if (set_device(c)) return 1;
-  std::lock_guard<std::mutex> lk(c->plan_mu);
+  std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
   auto key = std::make_pair((int)size, precision);
   auto it = c->plans.find(key);
   if (it != c->plans.end()) {
@@ -629,7 +812,9 @@ PDSP_EXPORT int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_pla
   pl->n = size;
   pl->log2n = log2n;
   pl->precision = precision;
-  int rc = precision == PDSP_F64 ? upload_tables<double>(pl) : upload_tables<float>(pl);
+  // single-CTA tables exist for every size the r2c (N <= 16384) or c2c (N <= 8192) kernels can take
+  int rc = 0;
+  if (log2n - 1 <= kMaxLog2M) rc = precision == PDSP_F64 ? upload_tables<double>(pl) : upload_tables<float>(pl);
   if (rc) {
     delete pl;
     return 1;

@@ -48,7 +48,7 @@ def main():
         plan = ctx.plan(n, prec)
         d = SpectrumDesc(sample_dtype=F64 if w["sdtype"] == "f64" else F32, frame_len=n, hop=n, batch=frames,
                          window=WINDOWS[w["window"]], sides=SIDES["one"], sample_rate=48000.0, raw_magnitude=0)
-        st = torch.cuda.current_stream()
+        st = torch.cuda.Stream(device=dev)  # explicit: handle 0 would mean 'the context's own stream' to the C-ABI
         bpf = bench.algorithmic_bytes_per_frame(w)
         ref_amp = ref_pk = None
         for v in [int(s) for s in a.variants.split(",")]:
@@ -61,6 +61,7 @@ def main():
             for _ in range(5):
                 go()
             torch.cuda.synchronize()
+            assert st.cuda_stream != 0
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
             for _ in range(a.reps):
