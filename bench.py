@@ -39,6 +39,11 @@ WORKLOADS = {
                desc="spectrum() batched: 65536 frames x N=1024 fp32, Hann, one-sided amplitude + peak @48kHz"),
     "north_star": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude",), frames=65536, n=1024,
                        desc="fp64 Hann-windowed FFT + one-sided magnitude, 65536 frames x N=1024"),
+    # BASELINE config C4: large single complex fp64 transforms (multi-pass path); a "frame" is one transform
+    "c4_2e20": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=8, n=1 << 20, kind="c2c",
+                    desc="complex fp64 FFT, N=2^20, 8 transforms per step (multi-pass 1024x1024)"),
+    "c4_2e24": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=1, n=1 << 24, kind="c2c",
+                    desc="complex fp64 FFT, N=2^24 (multi-pass 256x256x256)"),
     "c5": dict(prec="f64", sdtype="f64", window="hann", outputs=("peak",), frames=131072, n=1024,
                desc="fp64 window + FFT + peak argmax only, frame-sharded"),
 }
@@ -48,6 +53,8 @@ def algorithmic_bytes_per_frame(w) -> int:
     """compulsory HBM traffic per frame; cached tables excluded."""
     es = 8 if w["sdtype"] == "f64" else 4
     os_ = 8 if w["prec"] == "f64" else 4
+    if w.get("kind") == "c2c":
+        return 2 * 2 * es * w["n"]  # both planes in, both planes out
     bins = w["n"] // 2 + 1
     b = w["n"] * es
     if "amplitude" in w["outputs"]:
@@ -79,6 +86,25 @@ def run_reference(args, w):
 
     threads = oracle.max_threads()
     n = w["n"]
+    if w.get("kind") == "c2c":
+        rng = np.random.default_rng(SEED)
+        re, im = rng.uniform(-1, 1, (1, n)), rng.uniform(-1, 1, (1, n))
+        plan = oracle.FFT(n)
+        for _ in range(min(args.warmup, 1)):
+            plan.forwardComplex(re, im)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            plan.forwardComplex(re, im)
+        dt = time.perf_counter() - t0
+        fps = args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                           "sample": "one transform per step (a single radix-2 transform does not thread)"},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
     # bounded sample: about 0.5 s of all-core work per step
     sample = int(min(w["frames"], max(2048, 12000 * threads)))
     x = synth_frames_numpy(sample, n, np.float64 if w["sdtype"] == "f64" else np.float32)
@@ -420,6 +446,126 @@ def run_b200(args, w):
     return 0
 
 
+# ----------------------------------------------------------------------------- b200 arm, large transforms (C4)
+def run_b200_c2c(args, w):
+    """BASELINE config C4: single large complex fp64 transforms on the multi-pass path.  Replicas only
+    (SURVEY 8e): with N ranks every rank transforms its own arrays; no collective."""
+    import torch
+    import torch.distributed as dist
+
+    from pragma_dsp_b200 import _lib
+    from pragma_dsp_b200._lib import F64, check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = _lib.Context(local)
+    L = lib()
+    n, frames = w["n"], w["frames"]
+    plan = ctx.plan(n, F64)
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    re = torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    im = torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    ore, oim = torch.empty_like(re), torch.empty_like(re)
+    st = torch.cuda.Stream(device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def step():
+        check(L.pdsp_fft_complex_dev(plan, vp(re), vp(im), frames, vp(ore), vp(oim), 0, C.c_void_p(st.cuda_stream)))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        step()
+    e1.record(st)
+    barrier()
+    launches = ctx.launch_count - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    if sampler and not args.quick:
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.6:
+            step()
+            st.synchronize()
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt[0])
+    # e2e: host planes (pinned) through pdsp_fft_forward_complex
+    e2e_steps = 1 if args.quick else max(2, min(args.steps, 5))
+    hre, him = re.cpu().pin_memory(), im.cpu().pin_memory()
+    hor, hoi = torch.empty_like(hre).pin_memory(), torch.empty_like(hre).pin_memory()
+
+    def e2e_step():
+        check(L.pdsp_fft_forward_complex(plan, vp(hre), vp(him), frames, vp(hor), vp(hoi)))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    parity = cpu_baseline = None
+    if rank == 0:
+        ref = np.fft.fft(hre[0].numpy() + 1j * him[0].numpy())
+        got = hor[0].numpy() + 1j * hoi[0].numpy()
+        parity = {"frames": 1, "rel_l2_vs_numpy": float(np.linalg.norm(got - ref) / np.linalg.norm(ref)),
+                  "bound": 1e-12 * np.log2(n)}
+        if world == 1 and not args.quick:
+            import oracle
+            plan_o = oracle.FFT(n)
+            t0 = time.perf_counter()
+            plan_o.forwardComplex(hre[0].numpy(), him[0].numpy())
+            cpu_baseline = {"value": 1.0 / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                            "sample": "one transform of the same size through oracle/pragma_oracle.c (radix-2, single thread)"}
+        bpf = algorithmic_bytes_per_frame(w)
+        peak, peak_src = measured_hbm_peak()
+        fps = frames * world * args.steps / (elapsed_ms * 1e-3)
+        step_ms = elapsed_ms / args.steps
+        achieved = bpf * frames / (step_ms * 1e-3) / 1e9
+        line = {
+            "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "fft_size": n, "frames_per_gpu": frames,
+                       "l2": "2^24: 1 GiB per step >> L2; 2^20: 8 x 32 MiB in + out per step > 126 MB L2",
+                       "parallelism": f"replicas x{world}"},
+            "hbm_gbs": fps * bpf / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "bigfft_pass_kernel (all passes of a transform)",
+                         "algorithmic_bytes_per_frame": bpf, "kernel_ms": step_ms},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": frames * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 16 * n * frames,
+                    "d2h_bytes_per_step": 16 * n * frames, "steps": e2e_steps, "api": "pdsp_fft_forward_complex (host pinned)"},
+            "gpu_launches": launches * world, "clocks": sampler.summary() if sampler else None, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,6 +581,8 @@ def main():
         w["frames"] = args.frames
     if args.impl == "reference":
         return run_reference(args, w)
+    if w.get("kind") == "c2c":
+        return run_b200_c2c(args, w)
     return run_b200(args, w)
 
 

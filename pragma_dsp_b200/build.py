@@ -61,7 +61,8 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
     headers.append(os.path.join(os.path.dirname(HERE), "include", "pragma_b200.h"))
     tasks = []
     objs = []
-    units = [(os.path.join(CSRC, "pragma_b200.cu"), os.path.join(OBJ, "pragma_b200.o"), [])]
+    units = [(os.path.join(CSRC, "pragma_b200.cu"), os.path.join(OBJ, "pragma_b200.o"), []),
+             (os.path.join(CSRC, "bigfft.cu"), os.path.join(OBJ, "bigfft.o"), [])]
     for kind, ctype, lo, hi, name in groups():
         defs = [f"-DPDSP_INST_KIND={kind}", f"-DPDSP_INST_T={ctype}", f"-DPDSP_INST_LO={lo}", f"-DPDSP_INST_HI={hi}",
                 f"-DPDSP_INST_NAME={name}"]

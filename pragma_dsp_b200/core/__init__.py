@@ -66,6 +66,8 @@ class Radix2Fft:
         x = _as_samples(input)
         if x.shape[0] != self.size:
             raise ValueError(f"FFT input length {x.shape[0]} != size {self.size}")
+        if self.size > 16384 and x.dtype != np.float64:
+            x = x.astype(np.float64)  # the multi-pass path reads planes in the plan's precision
         result = self._out(out)
         check(lib().pdsp_fft_forward_real(self._plan, ptr(x), F64 if x.dtype == np.float64 else F32, 1,
                                           ptr(result.real), ptr(result.imag)))

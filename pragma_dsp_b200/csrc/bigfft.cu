@@ -16,7 +16,10 @@ static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
   int grid = 0;
   cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, p.n_groups, &grid);
   if (e != cudaSuccess) return e;
-  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
+  BigPassParams q = p;
+  q.tw = lc.pass_twiddles(lc.owner, sizeof(T) == 8, LOG2L, E::RB);
+  if (!q.tw) return cudaErrorInvalidValue;
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, q);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ struct BigPassParams {
   long long n_lo;
   long long in_hi, in_lo, in_c, in_e;      // element strides of (g_hi, g_lo, sequence c, element e)
   long long out_hi, out_lo, out_c, out_e;  // same for the output index k
-  const void* tw;                          // cx<T>[L]  exp(-2*pi*i*k/L)
+  const void* tw;                          // per-pass twiddles of the L-point schedule (set by the launcher)
   const void* tw_hi;                       // two-level inter-pass twiddle W_NT^m = hi[m >> log_b] * lo[m & (B-1)];
   const void* tw_lo;                       // null on the last pass
   int log_b;
@@ -88,7 +88,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
       });
     }
 
-    E::template fft<true>(v, t, sm, tw, 1, 0, 1);
+    E::template fft<true>(v, t, sm, tw, 0, 1);
 
     if (p.tw_hi != nullptr) {
       // W_NT^{k*i}, k = t + TF*q: start at W^{t*i}, step by W^{TF*i}

@@ -154,15 +154,25 @@ struct FftEngine {
   static constexpr int PAD_SHIFT = ilog2(PAD_UNIT);
   static constexpr int SMEM_ELEMS = M + (M >> PAD_SHIFT) + 1;  // per frame slot
   static constexpr bool NEEDS_SMEM = NPASS > 1;
+  // Per-schedule twiddle table: pass i >= 1 owns a block of (R_i - 1) * Ns_i entries laid out
+  // [(s - 1) * Ns_i + r] = W_{Ns_i*R_i}^{s*r}, so that for a fixed leg s the lanes of a warp
+  // (consecutive r) read consecutive entries - 4 wavefronts per warp load instead of up to 32 with
+  // a natural-order exp(-2*pi*i*k/M) table (profiles/r1: that cost more L1 cycles than both exchanges).
+  static constexpr int tw_offset(int pass) {
+    int off = 0;
+    for (int i = 1; i < pass; ++i) off += ((1 << pass_bits(i)) - 1) << (RB * i);
+    return off;
+  }
+  static constexpr int TW_ELEMS = tw_offset(NPASS);
   PDSP_DEVICE static int pad(int i) { return i + (i >> PAD_SHIFT); }
 
   // v[q] holds element t + TF*q (natural order) on entry and the transform on exit.
-  // tw: table exp(-2*pi*i*k/NT), NT = M * tw_stride.
+  // tw: the per-schedule table described at tw_offset() (TW_ELEMS entries).
   // BLOCKSYNC: the frame's threads are spread over the CTA's warps (column-tiled passes of the
   // large-N path), so every exchange is a __syncthreads.
   template <bool BLOCKSYNC = false>
-  PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int tw_stride,
-                              int slot, int slots_per_cta) {
+  PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int slot,
+                              int slots_per_cta) {
     auto sync = [&]() {
       if constexpr (BLOCKSYNC)
         simt::sync_block();
@@ -183,11 +193,9 @@ struct FftEngine {
         static_for<0, R>([&](auto s) { a[decltype(s)::value] = v[u + decltype(s)::value * BPT]; });
         [[maybe_unused]] const int j = t + TF * u;
         if constexpr (NSL > 0) {
-          const int r = j & (NS - 1);
-          // W_{Ns*R}^{s*r} = tw[s*r*(M/(Ns*R))*tw_stride]
-          const int step = r * ((M >> (NSL + b)) * tw_stride);
+          const cx<T>* PDSP_RESTRICT twp = tw + tw_offset(pass) + (j & (NS - 1));
           static_for<1, R>([&](auto s) {
-            const cx<T> w = ldg_cx(tw + decltype(s)::value * step);
+            const cx<T> w = ldg_cx(twp + (decltype(s)::value - 1) * NS);  // W_{Ns*R}^{s*r}
             a[decltype(s)::value] = cmul(a[decltype(s)::value], w);
           });
         }

@@ -39,7 +39,7 @@ struct R2CParams {
   long long hop;
   long long batch;
   const void* window;  // T[N] or nullptr (rect)
-  const void* tw;      // cx<T>[N]: exp(-2*pi*i*k/N)
+  const void* tw;      // cx<T>[E::TW_ELEMS]: per-pass twiddles of the M-point schedule (set by the launcher)
   const void* post;    // cx<T>[M/2+1]: (wi/2, -wr/2) of W_N^k
   // outputs, any may be null.  All in T.
   void* out_re;  // complex spectrum, planar; pitch = cbins
@@ -60,7 +60,7 @@ struct C2CParams {
   void* out_re;
   void* out_im;
   long long batch;
-  const void* tw;  // cx<T>[N]
+  const void* tw;  // cx<T>[E::TW_ELEMS]: per-pass twiddles (set by the launcher)
   int inverse;     // conjugate transform and multiply by 1/N
 };
 
@@ -219,7 +219,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) r2c_kernel(const R2CParams p)
     }
 
     // ---- M-point complex FFT of the packed frame
-    E::fft(v, t, sm, tw, 2, slot, SLOTS);
+    E::fft(v, t, sm, tw, slot, SLOTS);
 
     // ---- Hermitian split + fused epilogue
     T* o_re = valid && want_cplx ? static_cast<T*>(p.out_re) + f * cbins : nullptr;
@@ -396,7 +396,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) c2c_kernel(const C2CParams p)
       // inverse = swap(FFT(swap(x))) / N
       v[q] = p.inverse ? cx<T>{im, re} : cx<T>{re, im};
     });
-    E::fft(v, t, sm, tw, 1, slot, SLOTS);
+    E::fft(v, t, sm, tw, slot, SLOTS);
     if (valid) {
       T* ore = static_cast<T*>(p.out_re) + f * M;
       T* oim = static_cast<T*>(p.out_im) + f * M;

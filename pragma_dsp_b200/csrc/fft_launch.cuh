@@ -15,6 +15,10 @@ struct LaunchCtx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  // returns the device table of per-pass twiddles for an M = 2^log2m point schedule with full-pass
+  // radix 2^rb (FftEngine::tw_offset layout), building and caching it on first use; null on failure
+  const void* (*pass_twiddles)(void* owner, bool f64, int log2m, int rb);
+  void* owner;
 };
 
 constexpr int kMaxDevices = 16;
@@ -53,7 +57,10 @@ cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
   int grid = 0;
   cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
   if (e != cudaSuccess) return e;
-  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
+  R2CParams q = p;
+  q.tw = E::TW_ELEMS ? lc.pass_twiddles(lc.owner, sizeof(T) == 8, LOG2M, E::RB) : nullptr;
+  if (E::TW_ELEMS && !q.tw) return cudaErrorInvalidValue;
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, q);
   return cudaGetLastError();
 }
 
@@ -70,7 +77,10 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
   int grid = 0;
   cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, (p.batch + SLOTS - 1) / SLOTS, &grid);
   if (e != cudaSuccess) return e;
-  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, p);
+  C2CParams q = p;
+  q.tw = E::TW_ELEMS ? lc.pass_twiddles(lc.owner, sizeof(T) == 8, LOG2M, E::RB) : nullptr;
+  if (E::TW_ELEMS && !q.tw) return cudaErrorInvalidValue;
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, q);
   return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/pragma_b200.h"
@@ -188,6 +189,7 @@ struct pdsp_ctx {
   std::mutex mu;       // serialises the host-entry staging pipeline (slots)
   std::recursive_mutex plan_mu;  // guards the plan cache and lazily built tables (taken inside `mu`)
   std::map<std::pair<int, int>, pdsp_plan*> plans;
+  std::map<std::tuple<int, int, int>, void*> pass_tw;  // (f64, log2m, rb) -> per-pass twiddle table
   std::atomic<long long> launches{0};
 };
 
@@ -195,7 +197,6 @@ struct pdsp_ctx {
 struct BigPlan {
   int npass = 0;
   int lg[3] = {0, 0, 0};
-  pdsp_plan* sub[3] = {nullptr, nullptr, nullptr};  // plans of the pass lengths (their twiddle tables)
   void* tw_hi[2] = {nullptr, nullptr};               // two-level inter-pass twiddles of passes 0 and 1
   void* tw_lo[2] = {nullptr, nullptr};
   int log_b[2] = {0, 0};
@@ -208,7 +209,6 @@ struct pdsp_plan {
   int n;
   int log2n;
   int precision;
-  void* d_tw = nullptr;    // cx<T>[n]   (in-CTA sizes only)
   void* d_post = nullptr;  // cx<T>[n/4 + 1]
   void* d_win[4] = {nullptr, nullptr, nullptr, nullptr};
   BigPlan* big = nullptr;  // built lazily for n > 8192
@@ -281,22 +281,53 @@ static void twiddle(int k, int n, long double* re, long double* im) {
   *im = -s;
 }
 
+// Per-pass twiddles of an M = 2^log2m point Stockham schedule whose full passes have radix 2^rb
+// (same schedule arithmetic as FftEngine: all passes rb bits, the last one the remainder).  Block of
+// pass i >= 1: [(s - 1) * Ns + r] = exp(-2*pi*i * s*r / (Ns * R)), s = 1..R-1, r = 0..Ns-1.
+template <typename T>
+static int upload_pass_twiddles(int log2m, int rb, void** d_out) {
+  std::vector<cx<T>> tab;
+  const int npass = log2m == 0 ? 0 : (log2m + rb - 1) / rb;
+  for (int i = 1; i < npass; ++i) {
+    const int bits = i < npass - 1 ? rb : log2m - rb * (npass - 1);
+    const int R = 1 << bits, Ns = 1 << (rb * i), n = Ns * R;
+    for (int sidx = 1; sidx < R; ++sidx)
+      for (int r = 0; r < Ns; ++r) {
+        long double re, im;
+        const int k = (int)(((long long)sidx * r) % n);
+        if (n >= 8) {
+          twiddle(k, n, &re, &im);
+        } else {  // n = 4
+          static const long double c4[4] = {1, 0, -1, 0}, s4[4] = {0, -1, 0, 1};
+          re = c4[k * (4 / n)];
+          im = s4[k * (4 / n)];
+        }
+        tab.push_back(cx<T>{(T)re, (T)im});
+      }
+  }
+  if (tab.empty()) tab.push_back(cx<T>{(T)1, (T)0});
+  CU(cudaMalloc(d_out, sizeof(cx<T>) * tab.size()));
+  CU(cudaMemcpy(*d_out, tab.data(), sizeof(cx<T>) * tab.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static const void* pass_twiddles_cb(void* owner, bool f64, int log2m, int rb) {
+  pdsp_ctx* c = static_cast<pdsp_ctx*>(owner);
+  std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
+  auto key = std::make_tuple((int)f64, log2m, rb);
+  auto it = c->pass_tw.find(key);
+  if (it != c->pass_tw.end()) return it->second;
+  void* d = nullptr;
+  const int rc = f64 ? upload_pass_twiddles<double>(log2m, rb, &d) : upload_pass_twiddles<float>(log2m, rb, &d);
+  if (rc) return nullptr;
+  c->pass_tw[key] = d;
+  return d;
+}
+
+// Hermitian post-pass table of a real plan: post[k] = W_N^k * (-i/2) = (wi/2, -wr/2), k = 0..N/4
 template <typename T>
 static int upload_tables(pdsp_plan* pl) {
   const int n = pl->n;
-  std::vector<cx<T>> tw((size_t)n);
-  for (int k = 0; k < n; ++k) {
-    long double re, im;
-    if (n >= 8) {
-      twiddle(k, n, &re, &im);
-    } else {  // n = 1, 2, 4: axis points only
-      static const long double c4[4] = {1, 0, -1, 0}, s4[4] = {0, -1, 0, 1};
-      int idx = k * (4 / n);
-      re = c4[idx];
-      im = s4[idx];
-    }
-    tw[k] = cx<T>{(T)re, (T)im};
-  }
   const int m = n / 2;
   const int np = m / 2 + 1;
   std::vector<cx<T>> post((size_t)np);
@@ -311,9 +342,7 @@ static int upload_tables(pdsp_plan* pl) {
     }
     post[k] = cx<T>{(T)(im / 2), (T)(-re / 2)};
   }
-  CU(cudaMalloc(&pl->d_tw, sizeof(cx<T>) * (size_t)n));
   CU(cudaMalloc(&pl->d_post, sizeof(cx<T>) * (size_t)np));
-  CU(cudaMemcpy(pl->d_tw, tw.data(), sizeof(cx<T>) * (size_t)n, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(pl->d_post, post.data(), sizeof(cx<T>) * (size_t)np, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -390,7 +419,6 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
   const void* win = nullptr;
   if (plan_window(pl, d->window, &win)) return 1;
   p.window = win;
-  p.tw = pl->d_tw;
   p.post = pl->d_post;
   p.out_re = d_cre;
   p.out_im = d_cim;
@@ -408,7 +436,7 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     p.scale_mid = 2.0 / (double)n;   // (2 * mag) / size, identical bits for power-of-two size
   }
   p.bin_hz = d->sample_rate / (double)n;  // binFrequencies: quotient first (fourier.ts:160)
-  LaunchCtx lc{c->device, c->sm_count, st};
+  LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   cudaError_t e;
   if (n == 1) {
     const int threads = 128;
@@ -453,8 +481,6 @@ static int upload_big_twiddles(int log_nt, int log_b, void** d_hi, void** d_lo) 
   return 0;
 }
 
-extern "C" int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_plan** out);
-
 // Builds (once) the pass structure of a large transform.  *out stays null when PDSP_BIG_FACTORS is
 // set but does not describe this size (the in-CTA kernel is used instead).
 static int big_plan(pdsp_plan* pl, BigPlan** out) {
@@ -486,13 +512,7 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
   BigPlan* bp = new BigPlan();
   bp->npass = np;
   const size_t es = esize(pl->precision);
-  for (int j = 0; j < np; ++j) {
-    bp->lg[j] = lg[j];
-    if (pdsp_plan_get(pl->ctx, 1 << lg[j], pl->precision, &bp->sub[j])) {
-      delete bp;
-      return 1;
-    }
-  }
+  for (int j = 0; j < np; ++j) bp->lg[j] = lg[j];
   int rest = n;  // log2(L_j * I_j) of pass j
   for (int j = 0; j + 1 < np; ++j) {
     bp->log_b[j] = (rest + 1) / 2;
@@ -513,7 +533,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   pdsp_ctx* c = pl->ctx;
   const size_t es = esize(pl->precision);
   const long long N = 1LL << pl->log2n;
-  LaunchCtx lc{c->device, c->sm_count, st};
+  LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   const int np = bp->npass;
   long long Ls[3] = {1, 1, 1};
   for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
@@ -534,7 +554,6 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       p.in_im = j == 0 ? (const void*)fim : bp->work_im;
       p.out_re = last ? (void*)gre : bp->work_re;
       p.out_im = last ? (void*)gim : bp->work_im;
-      p.tw = bp->sub[j]->d_tw;
       p.swap_in = (j == 0 && inverse) ? 1 : 0;
       p.swap_out = (last && inverse) ? 1 : 0;
       p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
@@ -599,9 +618,8 @@ static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long lo
   p.out_re = d_ore;
   p.out_im = d_oim;
   p.batch = batch;
-  p.tw = pl->d_tw;
   p.inverse = inverse;
-  LaunchCtx lc{c->device, c->sm_count, st};
+  LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   cudaError_t e = dispatch_c2c(pl->precision == PDSP_F64, pl->log2n, p, lc);
   if (e != cudaSuccess) return fail("c2c launch (n=%d): %s", pl->n, cudaGetErrorString(e));
   c->launches++;
@@ -729,7 +747,6 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& kv : c->plans) {
     pdsp_plan* pl = kv.second;
-    cudaFree(pl->d_tw);
     cudaFree(pl->d_post);
     for (int i = 0; i < 4; ++i) cudaFree(pl->d_win[i]);
     if (pl->big) {
@@ -743,6 +760,7 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
     }
     delete pl;
   }
+  for (auto& kv : c->pass_tw) cudaFree(kv.second);
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = c->slots[i];
     cudaFree(s.d_in);
@@ -828,6 +846,8 @@ PDSP_EXPORT int pdsp_plan_precision(const pdsp_plan* p) { return p ? p->precisio
 
 static int check_desc(const pdsp_plan* pl, const pdsp_spectrum_desc* d) {
   if (!pl || !d) return fail("null argument");
+  if (pl->log2n - 1 > kMaxLog2M)
+    return fail("spectrum() is fused for FFT sizes up to %d; use the transform entry points for larger sizes", 2 << kMaxLog2M);
   if (d->batch < 0) return fail("negative batch");
   if (d->frame_len < 0) return fail("negative frame length");
   if (d->hop < 0) return fail("negative hop");
@@ -853,6 +873,12 @@ PDSP_EXPORT int pdsp_fft_forward_real_dev(pdsp_plan* pl, const void* d_in, int i
   if (!pl || !d_in || !d_ore || !d_oim) return fail("null argument");
   if (set_device(pl->ctx)) return 1;
   if (batch <= 0) return batch == 0 ? 0 : fail("negative batch");
+  if (pl->log2n - 1 > kMaxLog2M) {
+    if (in_dtype != pl->precision) return fail("large real transforms need input in the plan's precision");
+    if (!full) return fail("large real transforms write all N bins");
+    cudaStream_t st2 = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
+    return launch_c2c(pl, d_in, nullptr, batch, d_ore, d_oim, 0, st2);
+  }
   pdsp_spectrum_desc d;
   memset(&d, 0, sizeof d);
   d.sample_dtype = in_dtype;
@@ -931,6 +957,8 @@ static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, i
   if (!pl || !in_re || !out_re || !out_im) return fail("null argument");
   if (mode != 0 && !in_im) return fail("null argument");
   if (pl->precision != PDSP_F64) return fail("host transform entry points need a PDSP_F64 plan (Float64Array planes)");
+  if (mode == 0 && pl->log2n - 1 > kMaxLog2M && in_dtype != PDSP_F64)
+    return fail("real transforms above %d points take Float64Array input", 2 << kMaxLog2M);
   if (batch < 0) return fail("negative batch");
   pdsp_ctx* c = pl->ctx;
   if (set_device(c)) return 1;
@@ -967,7 +995,10 @@ static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, i
     const size_t oplane = (size_t)nb * n * 8, oplane_al = align256(oplane);
     if ((rc = ensure(&s.d_out, &s.d_out_cap, 2 * oplane_al, false))) break;
     char* dout = static_cast<char*>(s.d_out);
-    if (mode == 0) {
+    if (mode == 0 && pl->log2n - 1 > kMaxLog2M) {
+      // real frame longer than the in-CTA limit: multi-pass complex transform of (x, 0)
+      rc = launch_c2c(pl, s.d_in, nullptr, nb, dout, dout + oplane_al, 0, s.stream);
+    } else if (mode == 0) {
       pdsp_spectrum_desc dd;
       memset(&dd, 0, sizeof dd);
       dd.sample_dtype = in_dtype;

@@ -71,7 +71,7 @@ def build_cabi_emulated():
     TEST ONLY - loaded by tests/test_host_pipeline_emulated.py through a monkeypatched LIB_PATH."""
     import concurrent.futures as cf
     import re
-    srcs = _headers() + [os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(_CSRC, "inst.cu"),
+    srcs = _headers() + [os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(_CSRC, "inst.cu"), os.path.join(_CSRC, "bigfft.cu"),
                          os.path.join(_ROOT, "include", "pragma_b200.h")]
     if not _stale(CABI_EMU_SO, srcs):
         return CABI_EMU_SO
@@ -80,6 +80,7 @@ def build_cabi_emulated():
     txt = open(os.path.join(_CSRC, "inst_groups.h")).read()
     txt = txt[:txt.index("#else")]
     units = [(os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(objdir, "pragma_b200.o"), []),
+             (os.path.join(_CSRC, "bigfft.cu"), os.path.join(objdir, "bigfft.o"), []),
              (os.path.join(_HERE, "emu_runtime.cc"), os.path.join(objdir, "emu_runtime.o"), [])]
     for kind, tag, ctype, lo, hi in re.findall(r"X\((\d), (\w+), (\w+), (\d+), (\d+)\)", txt):
         name = f"launch_{'r2c' if kind == '0' else 'c2c'}_{tag}_{lo}_{hi}"
@@ -98,25 +99,47 @@ def build_cabi_emulated():
     return CABI_EMU_SO
 
 
-def tables(n, dtype):
-    """Twiddle and post-pass tables as pragma_b200.cu::upload_tables builds them."""
-    k = np.arange(n, dtype=np.longdouble)
-    ang = -2 * np.longdouble(np.pi) * k / np.longdouble(n)
-    re, im = np.cos(ang), np.sin(ang)
-    for kk in range(n):  # exact axis / diagonal points
-        if (8 * kk) % n == 0:
-            o = (8 * kk) // n
-            s = np.sqrt(np.longdouble(0.5))
-            re[kk] = [1, s, 0, -s, -1, -s, 0, s][o]
-            im[kk] = [0, -s, -1, -s, 0, s, 1, s][o]
-    tw = np.empty((n, 2), dtype=dtype)
-    tw[:, 0], tw[:, 1] = re.astype(dtype), im.astype(dtype)
-    m = n // 2
+def _w(k, n):
+    """exp(-2*pi*i*k/n) in long double with exact axis/diagonal values (as pragma_b200.cu::twiddle)."""
+    k %= n
+    if (8 * k) % n == 0:
+        o = (8 * k) // n
+        s = np.sqrt(np.longdouble(0.5))
+        return ([1, s, 0, -s, -1, -s, 0, s][o], [0, -s, -1, -s, 0, s, 1, s][o])
+    ang = -2 * np.longdouble(np.pi) * np.longdouble(k) / np.longdouble(n)
+    return (np.cos(ang), np.sin(ang))
+
+
+def pass_table(log2m, rb, dtype):
+    """Per-pass twiddles in FftEngine::tw_offset layout (as pragma_b200.cu::upload_pass_twiddles)."""
+    rows = []
+    npass = 0 if log2m == 0 else -(-log2m // rb)
+    for i in range(1, npass):
+        bits = rb if i < npass - 1 else log2m - rb * (npass - 1)
+        R, Ns = 1 << bits, 1 << (rb * i)
+        for s in range(1, R):
+            for r in range(Ns):
+                rows.append(_w(s * r, Ns * R))
+    if not rows:
+        rows.append((1, 0))
+    return np.ascontiguousarray(np.array(rows, dtype=np.longdouble).astype(dtype))
+
+
+def tables(n, dtype, variant=0, complex_plan=False):
+    """Twiddle and post-pass tables as the product builds them for size n (real plan: M = n/2 points)."""
+    m = n if complex_plan else n // 2
+    log2m = max(m, 1).bit_length() - 1
+    cfg = (C.c_int * 3)()
+    rc = lib().emu_cfg(int(dtype == np.float64), log2m, variant, cfg)
+    assert rc == 0, f"size {n} not instantiated in the emulator"
+    tw = pass_table(log2m, cfg[1], dtype)
+    assert cfg[2] == 0 or len(tw) == cfg[2], (len(tw), cfg[2])
     post = np.empty((m // 2 + 1, 2), dtype=dtype)
-    for kk in range(m // 2 + 1):
-        r, i = (re[kk], im[kk]) if n >= 4 else (np.longdouble(1), np.longdouble(0))
-        post[kk] = (i / 2, -r / 2)
-    return np.ascontiguousarray(tw), np.ascontiguousarray(post)
+    if not complex_plan:
+        for kk in range(m // 2 + 1):
+            r, i = _w(kk, n) if n >= 4 else (np.longdouble(1), np.longdouble(0))
+            post[kk] = (i / 2, -r / 2)
+    return tw, np.ascontiguousarray(post)
 
 
 def _p(a):
@@ -134,7 +157,7 @@ def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, w
     batch = 1 if batch is None else batch
     m = n // 2
     log2m = m.bit_length() - 1
-    tw, post = tables(n, dtype)
+    tw, post = tables(n, dtype, variant)
     win = None if window is None else np.ascontiguousarray(window, dtype=dtype)
     bins = n if sides == "two" else m + 1
     cb = n if cfull else m + 1
@@ -182,7 +205,7 @@ def c2c(re, im, n, *, dtype=np.float64, inverse=False, nblocks=1):
     re = np.ascontiguousarray(re, dtype=dtype)
     im = None if im is None else np.ascontiguousarray(im, dtype=dtype)
     batch = re.size // n
-    tw, _ = tables(n, dtype)
+    tw, _ = tables(n, dtype, complex_plan=True)
     ore = np.full_like(re, np.nan)
     oim = np.full_like(re, np.nan)
     p = C2CParams()

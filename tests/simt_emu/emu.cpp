@@ -89,4 +89,36 @@ extern "C" int emu_r2c_var(int f64, int var, const R2CParams* p, int nblocks, in
   }
   return -1;
 }
+// kernel configuration of (type, size, variant): lets the harness build the per-pass twiddle table
+template <typename T, int LOG2M, int VAR>
+static void cfg_of(int* out) {
+  using C = KCfg<T, LOG2M, VAR>;
+  using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
+  out[0] = C::LOG2P;
+  out[1] = E::RB;
+  out[2] = E::TW_ELEMS;
+}
+extern "C" int emu_cfg(int f64, int log2m, int var, int* out) {
+  if (var) {
+    if (log2m != kVariantLog2M) return -1;
+    switch (var) {
+#define X(V) \
+  case V:    \
+    f64 ? cfg_of<double, kVariantLog2M, V>(out) : cfg_of<float, kVariantLog2M, V>(out); \
+    return 0;
+      X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#undef X
+    }
+    return -1;
+  }
+  switch (log2m) {
+#define X(L) \
+  case L:    \
+    f64 ? cfg_of<double, L, 0>(out) : cfg_of<float, L, 0>(out); \
+    return 0;
+    EMU_SIZES(X)
+#undef X
+  }
+  return -1;
+}
 extern "C" int emu_params_size(int which) { return which == 0 ? (int)sizeof(R2CParams) : (int)sizeof(C2CParams); }

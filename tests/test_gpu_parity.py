@@ -219,3 +219,50 @@ def test_full_size_properties(ctx, prec, frames):
     got = (xr[idx].cpu().numpy().astype(np.float64) + 1j * xi[idx].cpu().numpy().astype(np.float64))
     for f in range(len(idx)):
         assert rel_l2(got[f], rre[f] + 1j * rim[f]) <= tol(n, prec)
+
+
+@pytest.mark.parametrize("log2n", [14, 15, 17, 20, 21, 24])
+def test_large_multipass_fft(ctx, log2n):
+    """BASELINE config C4 (N = 2^20, 2^24 complex fp64) and neighbours: the multi-pass path against
+    numpy's pocketfft (the reference's own golden generator, scripts/gen_fixtures.py:11-13) and, at 2^20,
+    against the oracle.  Tolerance: relative L2 1e-12*log2(N) (north_star)."""
+    from pragma_dsp_b200.core import ComplexArray, Radix2Fft
+    n = 1 << log2n
+    rng = np.random.default_rng(1337)
+    re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    fft = Radix2Fft(n)
+    out = fft.forwardComplex(ComplexArray(re, im))
+    ref = np.fft.fft(re + 1j * im)
+    tol_ = 1e-12 * log2n
+    assert rel_l2(out.real + 1j * out.imag, ref) <= tol_
+    if log2n == 20:
+        rre, rim = oracle.FFT(n).forwardComplex(re, im)
+        assert rel_l2(out.real + 1j * out.imag, rre[0] + 1j * rim[0] if rre.ndim > 1 else rre + 1j * rim) <= tol_
+    back = fft.inverse(out)
+    assert np.abs(back.real - re).max() <= 1e-12 and np.abs(back.imag - im).max() <= 1e-12
+    if log2n in (15, 20):
+        x = rng.standard_normal(n)
+        r = fft.forward(x)  # real input through the same path
+        assert rel_l2(r.real + 1j * r.imag, np.fft.fft(x)) <= tol_
+    # exact-zero rule survives the multi-pass path
+    z = fft.forwardComplex(ComplexArray(np.zeros(n), np.zeros(n)))
+    assert (z.real == 0).all() and (z.imag == 0).all()
+
+
+def test_large_multipass_fft_fp32_device(ctx):
+    import torch
+    from pragma_dsp_b200._lib import F32, check, lib
+    L = lib()
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(7)
+    re = torch.rand(n, generator=g, device="cuda") * 2 - 1
+    im = torch.rand(n, generator=g, device="cuda") * 2 - 1
+    ore, oim = torch.empty_like(re), torch.empty_like(re)
+    plan = ctx.plan(n, F32)
+    st = torch.cuda.Stream()
+    check(L.pdsp_fft_complex_dev(plan, C.c_void_p(re.data_ptr()), C.c_void_p(im.data_ptr()), 1, C.c_void_p(ore.data_ptr()),
+                                 C.c_void_p(oim.data_ptr()), 0, C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    ref = np.fft.fft(re.cpu().numpy().astype(np.float64) + 1j * im.cpu().numpy().astype(np.float64))
+    got = ore.cpu().numpy().astype(np.float64) + 1j * oim.cpu().numpy().astype(np.float64)
+    assert rel_l2(got, ref) <= 1e-5

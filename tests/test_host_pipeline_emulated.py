@@ -155,3 +155,34 @@ def test_launch_and_plan_accounting(emu_api):
     assert ctx.launch_count == before + 1
     h = C.c_void_p()
     assert L.pdsp_plan_get(ctx.h, 12, 1, C.byref(h)) != 0 and b"power of two" in L.pdsp_last_error()
+
+
+@pytest.mark.parametrize("factors,n", [("6,6", 4096), ("7,6", 8192), ("6,6,6", 1 << 18), ("7,7", 1 << 14)])
+def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n):
+    """K2: the multi-pass (four-step / six-step) path, forced onto small sizes with PDSP_BIG_FACTORS so the
+    emulator can run it: forward, inverse, real-input forward, batch of 2."""
+    from pragma_dsp_b200.core import Radix2Fft
+    if n > 8192:
+        monkeypatch.delenv("PDSP_BIG_FACTORS", raising=False) if factors == "7,7" else monkeypatch.setenv("PDSP_BIG_FACTORS", factors)
+    else:
+        monkeypatch.setenv("PDSP_BIG_FACTORS", factors)
+    rng = np.random.default_rng(n)
+    batch = 2 if n <= 8192 else 1
+    re, im = rng.standard_normal((batch, n)), rng.standard_normal((batch, n))
+    fft = Radix2Fft(n)
+    ore, oim = fft.complex_batch(re, im)
+    ref = np.fft.fft(re + 1j * im, axis=1)
+    tol = 1e-12 * np.log2(n)
+    for f in range(batch):
+        assert np.linalg.norm((ore[f] + 1j * oim[f]) - ref[f]) / np.linalg.norm(ref[f]) <= tol
+    bre, bim = fft.complex_batch(ore, oim, inverse=True)
+    assert np.abs(bre - re).max() <= 1e-12 and np.abs(bim - im).max() <= 1e-12
+    if n <= 8192:
+        rre, rim = oracle.FFT(n).forwardComplex(re, im)
+        assert np.linalg.norm((ore + 1j * oim) - (rre + 1j * rim)) / np.linalg.norm(rre + 1j * rim) <= tol
+    if n > 16384 or factors == "6,6":
+        xr = rng.standard_normal(n)
+        out = fft.forward(xr) if n > 16384 else None
+        if out is not None:
+            refr = np.fft.fft(xr)
+            assert np.linalg.norm((out.real + 1j * out.imag) - refr) / np.linalg.norm(refr) <= tol
