@@ -5,7 +5,7 @@ namespace pdsp {
 
 constexpr int kMaxLog2M = 13;      // largest in-CTA complex length 8192 (real frames up to 16384)
 constexpr int kMinSpecLog2M = 5;   // sizes below this only get the generic (runtime-flag) kernel
-constexpr int kNumVariants = 8;    // tuning variants compiled for kVariantLog2M (see inst_var.cu)
+constexpr int kNumVariants = 14;   // tuning variants compiled for kVariantLog2M (see inst_var.cu)
 constexpr int kVariantLog2M = 9;   // N = 1024, the headline size
 
 // Points per thread / radix / CTA size / occupancy target for a complex length 2^LOG2M.
@@ -17,11 +17,13 @@ struct KCfg {
   static constexpr int MAXRB = 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
   static constexpr int THREADS = TF > 128 ? TF : 128;
-  // register cap via __launch_bounds__: 128 regs/thread for 128-thread CTAs of doubles, 96 for floats
+  // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread for 128-thread CTAs of
+  // doubles, 96 for floats.  MAXREG > 0 selects a hard __maxnreg__ cap instead (tuning variants).
   static constexpr int MINB = THREADS <= 128 ? (sizeof(T) == 8 ? 4 : 5) : (THREADS <= 256 ? 2 : 1);
+  static constexpr int MAXREG = 0;
 };
 
-#define PDSP_VARIANT(VAR, LP, RB, THR, MB64, MB32)                          \
+#define PDSP_VARIANT(VAR, LP, RB, THR, MB64, MB32, REG64, REG32)             \
   template <typename T>                                                     \
   struct KCfg<T, kVariantLog2M, VAR> {                                      \
     static constexpr int LOG2P = LP;                                        \
@@ -29,15 +31,22 @@ struct KCfg {
     static constexpr int TF = (1 << kVariantLog2M) >> LOG2P;                \
     static constexpr int THREADS = THR;                                     \
     static constexpr int MINB = sizeof(T) == 8 ? MB64 : MB32;               \
+    static constexpr int MAXREG = sizeof(T) == 8 ? REG64 : REG32;           \
   };
-//           var  log2P radix-bits threads minB(f64) minB(f32)
-PDSP_VARIANT(1, 4, 4, 128, 4, 5)   // 16 x 16 x 2, one warp per frame
-PDSP_VARIANT(2, 5, 5, 64, 4, 8)    // 32 x 16, 16 threads per frame, one exchange
-PDSP_VARIANT(3, 3, 3, 128, 6, 8)   // 8 x 8 x 8, two warps per frame (named barriers)
-PDSP_VARIANT(4, 4, 3, 128, 3, 4)   // baseline mapping with a looser register cap
-PDSP_VARIANT(5, 5, 5, 128, 2, 4)   // 32 x 16, 8 frames per CTA
-PDSP_VARIANT(6, 4, 3, 256, 2, 2)   // baseline mapping, 8 frames per CTA
-PDSP_VARIANT(7, 5, 5, 32, 8, 16)   // 32 x 16, one warp (2 frames) per CTA
+//           var log2P radix-bits threads minB(f64,f32) maxnreg(f64,f32; 0 = use minB)
+PDSP_VARIANT(1, 4, 4, 128, 4, 5, 0, 0)      // 16 x 16 x 2, one warp per frame
+PDSP_VARIANT(2, 5, 5, 64, 4, 8, 0, 0)       // 32 x 16, 16 threads per frame, one exchange
+PDSP_VARIANT(3, 3, 3, 128, 6, 8, 0, 0)      // 8 x 8 x 8, two warps per frame (named barriers)
+PDSP_VARIANT(4, 4, 3, 128, 3, 4, 0, 0)      // baseline mapping with a looser register cap
+PDSP_VARIANT(5, 5, 5, 128, 2, 4, 0, 0)      // 32 x 16, 8 frames per CTA
+PDSP_VARIANT(6, 4, 3, 256, 2, 2, 0, 0)      // baseline mapping, 8 frames per CTA
+PDSP_VARIANT(7, 5, 5, 32, 8, 16, 0, 0)      // 32 x 16, one warp (2 frames) per CTA
+PDSP_VARIANT(8, 4, 4, 32, 18, 24, 0, 0)     // 16 x 16 x 2, single-warp CTAs: 18 (f64) / 24 (f32) per SM
+PDSP_VARIANT(9, 4, 4, 32, 20, 28, 0, 0)     // same, 20 / 28 per SM
+PDSP_VARIANT(10, 4, 4, 32, 1, 1, 112, 80)   // same, hard caps 112 / 80 registers
+PDSP_VARIANT(11, 4, 3, 32, 18, 24, 0, 0)    // 8 x 8 x 8, single-warp CTAs
+PDSP_VARIANT(12, 4, 4, 32, 1, 1, 120, 88)   // 16 x 16 x 2, hard caps 120 / 88 registers
+PDSP_VARIANT(13, 4, 4, 32, 16, 21, 0, 0)    // 16 x 16 x 2, single-warp CTAs at the baseline occupancy
 #undef PDSP_VARIANT
 
 }  // namespace pdsp

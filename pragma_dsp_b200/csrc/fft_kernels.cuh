@@ -127,8 +127,8 @@ PDSP_DEVICE cx<T> load_pair(const S* PDSP_RESTRICT s, int i0) {
   return cx<T>{(T)pr.x, (T)pr.y};
 }
 
-template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MINB, int MODE>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) r2c_kernel(const R2CParams p) {
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MODE>
+PDSP_DEVICE void r2c_body(const R2CParams& p) {
   using E = FftEngine<T, LOG2M, LOG2P, MAXRB>;
   constexpr int M = E::M, P = E::P, TF = E::TF, N = 2 * M;
   constexpr int SLOTS = THREADS / TF;
@@ -366,6 +366,17 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) r2c_kernel(const R2CParams p)
       }
     }
   }
+}
+
+// Kernel entry points: the occupancy target is either __launch_bounds__(THREADS, MINB) or, for the
+// tuning variants that want an exact register budget, __launch_bounds__(THREADS) __maxnreg__(MAXREG).
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MINB, int MODE>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) r2c_kernel(const R2CParams p) {
+  r2c_body<T, LOG2M, LOG2P, MAXRB, THREADS, MODE>(p);
+}
+template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MAXREG, int MODE>
+PDSP_GLOBAL void PDSP_KERNEL_LIMITS(THREADS, MAXREG) r2c_kernel_mr(const R2CParams p) {
+  r2c_body<T, LOG2M, LOG2P, MAXRB, THREADS, MODE>(p);
 }
 
 template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MINB>

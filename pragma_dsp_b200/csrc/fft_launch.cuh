@@ -51,7 +51,12 @@ cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
   constexpr int SLOTS = THREADS / E::TF;
   constexpr bool POST_SMEM = E::TF > 32;
   constexpr size_t SMEM = (E::NEEDS_SMEM || POST_SMEM) ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
-  auto kern = r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>;
+  auto kern = [] {
+    if constexpr (C::MAXREG > 0)
+      return r2c_kernel_mr<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MAXREG, MODE>;
+    else
+      return r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>;
+  }();
   static int bps[kMaxDevices] = {0};
   if (p.batch <= 0) return cudaSuccess;
   int grid = 0;

@@ -47,7 +47,7 @@ cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const L
 #ifdef PDSP_EMU
 #define PDSP_VARS(X)
 #else
-#define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 #endif
 #define X(v)                                                                           \
   cudaError_t launch_r2c_var_f64_##v(int, const R2CParams&, const LaunchCtx&);         \

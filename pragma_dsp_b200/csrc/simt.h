@@ -15,6 +15,7 @@
 #define PDSP_DEVICE_NOINLINE static __device__ __noinline__
 #define PDSP_GLOBAL __global__
 #define PDSP_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define PDSP_KERNEL_LIMITS(threads, regs) __launch_bounds__(threads) __maxnreg__(regs)
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL _Pragma("unroll")
 #define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) kernel<<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__)
@@ -59,6 +60,7 @@ PDSP_DEVICE T ldg(const T* p) {
 #define PDSP_DEVICE_NOINLINE static inline
 #define PDSP_GLOBAL
 #define PDSP_LAUNCH_BOUNDS(t, b)
+#define PDSP_KERNEL_LIMITS(threads, regs)
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL
 #define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) \

@@ -27,7 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=30)
-    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7")
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10,11,12,13")
     ap.add_argument("--workloads", default="c2,north_star,c5")
     a = ap.parse_args()
     ctx = _lib.Context(0)

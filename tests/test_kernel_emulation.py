@@ -197,7 +197,7 @@ def test_specialised_kernels_equal_generic(n, dtype, want):
         assert (a[key] == b[key]).all()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 11])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_tuning_variants_match_oracle(variant, dtype):
     """Alternative thread/radix mappings of N=1024 (fft_config.h PDSP_VARIANT): radix-16 and radix-32
