@@ -1,15 +1,9 @@
 #!/bin/bash
-# Variant sweep + ncu launch list + full capture of the dominant kernel for the given workloads.
+# ncu launch list + full capture of the dominant kernel for the given workloads.
 # Usage: bash scripts/gpu_profile.sh "c2 north_star" ; ncu only runs after the plain command exited 0.
 set -u
 WLS=${1:-"c2 north_star"}
 mkdir -p gpurun_out
-echo "== variant sweep"; timeout 300 python -u scripts/sweep_variants.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep rc=$?"; python - <<'PY'
-import json
-for l in open('gpurun_out/sweep.jsonl'):
-    r = json.loads(l); print(r['workload'], 'v%d' % r['variant'], '%.3f ms' % r['ms'], '%.3e f/s' % r['frames_per_s'], '%.0f GB/s' % r['gbs'], '%.3f' % r['frac_of_measured_hbm'], r['agree_with_v0'])
-PY
-tail -3 gpurun_out/sweep.err
 for WL in $WLS; do
   CMD="python bench.py --workload $WL --steps 3 --warmup 3 --quick"
   $CMD > gpurun_out/plain_$WL.log 2>&1 &&

@@ -48,7 +48,7 @@ static int run_c2c(const C2CParams& p, int nblocks) {
   return 0;
 }
 
-#define EMU_SIZES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(8) X(9) X(10) X(11)
+#define EMU_SIZES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11)
 
 extern "C" int emu_r2c(int f64, int log2m, const R2CParams* p, int nblocks, int mode) {
   switch (log2m) {
