@@ -14,7 +14,8 @@ constexpr int kVariantLog2M = 9;   // N = 1024, the headline size
 template <typename T, int LOG2M, int VAR = 0>
 struct KCfg {
   static constexpr int LOG2P = LOG2M < 3 ? LOG2M : (LOG2M >= 9 ? 4 : 3);
-  static constexpr int MAXRB = 3;
+  // radix 16 passes where a thread holds 16 points (fewest exchanges: 512 = 16 x 16 x 2), else radix 8
+  static constexpr int MAXRB = LOG2P == 4 ? 4 : 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
   static constexpr int THREADS = TF > 128 ? TF : 128;
   // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread for 128-thread CTAs of
@@ -34,7 +35,7 @@ struct KCfg {
     static constexpr int MAXREG = sizeof(T) == 8 ? REG64 : REG32;           \
   };
 //           var log2P radix-bits threads minB(f64,f32) maxnreg(f64,f32; 0 = use minB)
-PDSP_VARIANT(1, 4, 4, 128, 4, 5, 0, 0)      // 16 x 16 x 2, one warp per frame
+PDSP_VARIANT(1, 4, 3, 128, 4, 5, 0, 0)      // 8 x 8 x 8, one warp per frame (the default is 16 x 16 x 2)
 PDSP_VARIANT(2, 5, 5, 64, 4, 8, 0, 0)       // 32 x 16, 16 threads per frame, one exchange
 PDSP_VARIANT(3, 3, 3, 128, 6, 8, 0, 0)      // 8 x 8 x 8, two warps per frame (named barriers)
 PDSP_VARIANT(4, 4, 3, 128, 3, 4, 0, 0)      // baseline mapping with a looser register cap

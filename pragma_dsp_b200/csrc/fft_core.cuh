@@ -106,6 +106,17 @@ PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
   }
 }
 
+// d * W32^K for any K in [0, 32)
+template <int K, typename T>
+PDSP_DEVICE cx<T> mul_w32_full(cx<T> d) {
+  if constexpr (K < 16) {
+    return mul_w32<K>(d);
+  } else {
+    const cx<T> r = mul_w32<K - 16>(d);
+    return cx<T>{-r.x, -r.y};
+  }
+}
+
 // In-register radix-R DFT, decimation in frequency: natural order in, X[k] left in
 // a[bitrev(k, log2 R)].  R in {1, 2, 4, 8, 16, 32}.
 template <typename T, int R>
@@ -187,17 +198,31 @@ struct FftEngine {
       constexpr int NSL = RB * pass;  // log2 Ns
       constexpr int NS = 1 << NSL;
       constexpr bool last = pass == NPASS - 1;
+      // Last pass with several butterflies per thread: Ns = TF*BPT, so r = t + TF*u and
+      // W_M^{s*(t + TF*u)} = W_M^{s*t} * exp(-2*pi*i*s*u/P): one table entry per leg (u = 0) and a
+      // compile-time 32nd root of unity for the others - P/R - 1 fewer L1 loads per leg.
+      constexpr bool DERIVE = last && NSL > 0 && BPT > 1 && (32 % P) == 0;
+      [[maybe_unused]] cx<T> w0[R];
       static_for<0, BPT>([&](auto ui) {
         constexpr int u = decltype(ui)::value;
         cx<T> a[R];
         static_for<0, R>([&](auto s) { a[decltype(s)::value] = v[u + decltype(s)::value * BPT]; });
         [[maybe_unused]] const int j = t + TF * u;
         if constexpr (NSL > 0) {
-          const cx<T>* PDSP_RESTRICT twp = tw + tw_offset(pass) + (j & (NS - 1));
-          static_for<1, R>([&](auto s) {
-            const cx<T> w = ldg_cx(twp + (decltype(s)::value - 1) * NS);  // W_{Ns*R}^{s*r}
-            a[decltype(s)::value] = cmul(a[decltype(s)::value], w);
-          });
+          if constexpr (DERIVE) {
+            static_for<1, R>([&](auto si) {
+              constexpr int s = decltype(si)::value;
+              if constexpr (u == 0) w0[s] = ldg_cx(tw + tw_offset(pass) + (s - 1) * NS + t);
+              const cx<T> w = mul_w32_full<(s * u * (32 / P)) % 32>(w0[s]);
+              a[s] = cmul(a[s], w);
+            });
+          } else {
+            const cx<T>* PDSP_RESTRICT twp = tw + tw_offset(pass) + (j & (NS - 1));
+            static_for<1, R>([&](auto s) {
+              const cx<T> w = ldg_cx(twp + (decltype(s)::value - 1) * NS);  // W_{Ns*R}^{s*r}
+              a[decltype(s)::value] = cmul(a[decltype(s)::value], w);
+            });
+          }
         }
         dif_butterfly<T, R>(a);
         if constexpr (last) {

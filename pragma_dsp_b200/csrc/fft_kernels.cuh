@@ -79,20 +79,31 @@ PDSP_DEVICE_NOINLINE double t_atan2(double y, double x) { return atan2(y, x); }
 PDSP_DEVICE_NOINLINE float t_hypot_slow(float x, float y) { return hypotf(x, y); }
 PDSP_DEVICE_NOINLINE double t_hypot_slow(double x, double y) { return hypot(x, y); }
 
-// |re + i*im|: sqrt(re^2+im^2), falling back to hypot() when the sum of squares leaves the
-// comfortably-normal range (0, subnormal, huge, inf/nan) so extreme inputs behave like Math.hypot.
-PDSP_DEVICE double t_mag(double re, double im) {
-  const double s = re * re + im * im;
-  const unsigned hi = (unsigned)__double2hiint(s);
-  if ((hi - 0x00400000u) >= (0x7fd00000u - 0x00400000u)) return t_hypot_slow(re, im);
-  return t_sqrt<double>(s);
+// sqrt without the IEEE slow path.  fp32: MUFU.SQRT (sqrt.approx, <= 1 ulp-ish, 2^-23 relative).
+// fp64: MUFU.RSQ64H seed + two Newton steps, branch-free; exact 0 for +0; inf/NaN and sums outside
+// the normal range are caught by the caller's exponent tracker and redone with hypot().
+#if defined(__CUDACC__) && !defined(PDSP_EMU)
+PDSP_DEVICE float fast_sqrt(float s) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(s));
+  return r;
 }
-PDSP_DEVICE float t_mag(float re, float im) {
-  const float s = re * re + im * im;
-  const unsigned b = (unsigned)__float_as_int(s);
-  if ((b - 0x01000000u) >= (0x7e800000u - 0x01000000u)) return t_hypot_slow(re, im);
-  return t_sqrt<float>(s);
+PDSP_DEVICE double fast_sqrt(double s) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  double g = s * y;          // ~ sqrt(s), 22 bits
+  double h = 0.5 * y;        // ~ 1 / (2 sqrt(s))
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);          // 44 bits
+  h = fma(h, r, h);
+  r = fma(-g, g, s);         // residual s - g^2
+  g = fma(r, h, g);          // full precision
+  return __double2hiint(s) == 0 ? 0.0 : g;  // +0 (and sub-2^-1042 dust): rsqrt gave inf
 }
+#else
+PDSP_DEVICE float fast_sqrt(float s) { return sqrtf(s); }
+PDSP_DEVICE double fast_sqrt(double s) { return sqrt(s); }
+#endif
 
 template <typename T>
 struct PeakCand {
@@ -229,88 +240,158 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     PeakCand<T> best{(T)0, 0, (T)0, (T)0};
     T dc_re = (T)0, dc_amp = (T)0;
 
-    // emit one bin k in [0, M] with value X
-    auto emit = [&](int k, cx<T> X) {
-      if (want_cplx && o_re != nullptr) {
-        o_re[k] = X.x;
-        o_im[k] = X.y;
-        if (cfull && k != 0 && k != M) {
-          o_re[N - k] = X.x;
-          o_im[N - k] = -X.y;
-        }
-      }
-      if (need_mag) {
-        const T a = t_mag(X.x, X.y) * ((k == 0 || k == M) ? s_edge : s_mid);
-        if (want_amp && o_amp != nullptr) {
-          o_amp[k] = a;
-          if (two_sided && k != 0 && k != M) o_amp[N - k] = a;
-        }
-        if (want_peak) {
-          if (k == 0) {
-            dc_re = X.x;
-            dc_amp = a;
-          } else if (peak_better(a, k, best.v, best.k)) {
-            best.v = a;
-            best.k = k;
-            best.re = X.x;
-            best.im = X.y;
+    // The bins of one thread form two streams: stream 0 walks k = t + TF*q upward, stream 1 walks
+    // M - k downward.  Every address is a per-thread base plus a compile-time offset.
+    auto post_pass = [&](auto careful_c) {
+      constexpr bool CAREFUL = decltype(careful_c)::value;  // second run with hypot() for out-of-range sums
+      // findPeak keeps the first of equal values (strict '>' scanning upward): stream 0 is visited in
+      // ascending k so '>' suffices; stream 1 is visited in descending k so '>=' lets the lower bin
+      // win a tie (its threshold starts at the smallest positive number: a candidate needs v > 0).
+      PeakCand<T> c0{(T)0, 0, (T)0, (T)0};
+      PeakCand<T> c1{sizeof(T) == 8 ? (T)4.9406564584124654e-324 : (T)1.401298464324817e-45, 0, (T)0, (T)0};
+      unsigned hi_max = 0u, lo_min = 0xffffffffu;  // exponent range of re^2+im^2 seen by this thread (fp64)
+
+      auto emit = [&](auto stream_c, auto off_c, auto edge_c, int k, cx<T> X) {
+        constexpr int STREAM = decltype(stream_c)::value;
+        constexpr int OFF = decltype(off_c)::value;    // element offset from the stream's base pointer
+        constexpr bool EDGE = decltype(edge_c)::value;  // k may be 0 or M (DC / Nyquist)
+        const int b0 = STREAM == 0 ? t : M - t;          // base bin of the stream
+        const int m0 = STREAM == 0 ? N - t : M + t;      // base of the mirrored bin N - k
+        if (want_cplx && o_re != nullptr) {
+          (o_re + b0)[OFF] = X.x;
+          (o_im + b0)[OFF] = X.y;
+          if (cfull && (!EDGE || (k != 0 && k != M))) {
+            (o_re + m0)[-OFF] = X.x;
+            (o_im + m0)[-OFF] = -X.y;
           }
         }
-      }
-      if constexpr (PHASE) {
-        if (want_phase && o_ph != nullptr) {
-          const T ph = t_atan2(X.y, X.x);
-          o_ph[k] = ph;
-          if (two_sided && k != 0 && k != M) o_ph[N - k] = -ph;
+        if (need_mag) {
+          T mag;
+          if constexpr (CAREFUL) {
+            mag = t_hypot_slow(X.x, X.y);
+          } else {
+            const T ss = X.x * X.x + X.y * X.y;
+            if constexpr (sizeof(T) == 8) {
+              const unsigned hi = (unsigned)__double2hiint((double)ss);
+              hi_max = hi > hi_max ? hi : hi_max;
+              lo_min = (hi - 1u) < lo_min ? (hi - 1u) : lo_min;
+            }
+            mag = fast_sqrt(ss);
+          }
+          T scale = s_mid;
+          if constexpr (EDGE) scale = (k == 0 || k == M) ? s_edge : s_mid;
+          const T a = mag * scale;
+          if (want_amp && o_amp != nullptr) {
+            (o_amp + b0)[OFF] = a;
+            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_amp + m0)[-OFF] = a;
+          }
+          if (want_peak) {
+            bool is_dc = false;
+            if constexpr (EDGE) is_dc = k == 0;
+            if (is_dc) {
+              dc_re = X.x;
+              dc_amp = a;
+            } else if constexpr (STREAM == 0) {
+              if (a > c0.v) c0 = PeakCand<T>{a, k, X.x, X.y};
+            } else {
+              if (a >= c1.v) c1 = PeakCand<T>{a, k, X.x, X.y};
+            }
+          }
         }
+        if constexpr (PHASE) {
+          if (want_phase && o_ph != nullptr) {
+            const T ph = t_atan2(X.y, X.x);
+            (o_ph + b0)[OFF] = ph;
+            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_ph + m0)[-OFF] = -ph;
+          }
+        }
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+
+      if constexpr (M == 1) {
+        // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
+        emit(I0{}, I0{}, std::true_type{}, 0, cx<T>{v[0].x + v[0].y, (T)0});
+        emit(I1{}, I0{}, std::true_type{}, 1, cx<T>{v[0].x - v[0].y, (T)0});
+      } else {
+        // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
+        // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
+        constexpr bool DERIVE = (16 % P) == 0 && P >= 2;
+        cx<T> post0{(T)0, (T)0};
+        if constexpr (DERIVE) post0 = ldg_cx(post + t);
+        static_for<0, P / 2>([&](auto qi) {
+          constexpr int q = decltype(qi)::value;
+          const int k = t + TF * q;  // 0 <= k < M/2
+          cx<T> zp;                  // Z[(M - k) % M]
+          if constexpr (POST_SMEM) {
+            zp = sm[E::pad((M - k) & (M - 1))];
+          } else if constexpr (TF == 1) {
+            zp = v[(P - q) % P];
+          } else {
+            const cx<T> mine = v[P - 1 - q];
+            cx<T> got;
+            got.x = simt::shfl(mine.x, (TF - t) & (TF - 1), TF);
+            got.y = simt::shfl(mine.y, (TF - t) & (TF - 1), TF);
+            zp = (t == 0) ? v[(P - q) % P] : got;
+          }
+          const cx<T> a = v[q];
+          const cx<T> sum{a.x + zp.x, a.y - zp.y};  // A + conj(Zp)
+          const cx<T> dif{a.x - zp.x, a.y + zp.y};  // A - conj(Zp)
+          cx<T> w;                                   // (wi/2, -wr/2): W_N^k * (-i/2)
+          if constexpr (DERIVE)
+            w = mul_w32<(q * 16 / P) % 16>(post0);
+          else
+            w = ldg_cx(post + k);
+          const cx<T> tt = cmul(dif, w);
+          cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};     // X[k]
+          cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};  // X[M-k] = conj(E - W*O)
+          if constexpr (q == 0) {
+            // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
+            // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
+            if (t == 0) {
+              xa.y = (T)0;
+              xb.y = (T)0;
+            }
+          }
+          emit(I0{}, std::integral_constant<int, TF * q>{}, std::bool_constant<q == 0>{}, k, xa);
+          emit(I1{}, std::integral_constant<int, -TF * q>{}, std::bool_constant<q == 0>{}, M - k, xb);
+        });
+        // self-paired bin M/2 = conj(Z[M/2]) (thread 0; above every stream-0 bin of that thread)
+        if (t == 0) emit(I0{}, std::integral_constant<int, M / 2>{}, std::false_type{}, M / 2, cx<T>{v[P / 2].x, -v[P / 2].y});
       }
+      int verdict = 0;  // bit 0: a sum of squares left the safe range; bit 1: every sum of this thread was 0
+      if constexpr (sizeof(T) == 8 && !CAREFUL) {
+        // sums of squares outside [2^-1019, 2^+1022) rerun with hypot(); an exact 0 is fine (sqrt(0) = 0)
+        // unless it is the underflow of a non-zero bin, which the caller settles for all-zero threads
+        if (need_mag) verdict = ((hi_max >= 0x7fd00000u || lo_min < 0x003fffffu) ? 1 : 0) | (hi_max == 0u ? 2 : 0);
+      }
+      // merge the two streams: higher value wins, equal values go to the lower bin
+      best = c0;
+      if (c1.k != 0 && (best.k == 0 || peak_better(c1.v, c1.k, best.v, best.k))) best = c1;
+      return verdict;
     };
 
-    if constexpr (M == 1) {
-      // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
-      emit(0, cx<T>{v[0].x + v[0].y, (T)0});
-      emit(1, cx<T>{v[0].x - v[0].y, (T)0});
-    } else {
-      if constexpr (POST_SMEM) {
-        static_for<0, P>([&](auto q) { sm[E::pad(t + TF * decltype(q)::value)] = v[decltype(q)::value]; });
-        frame_sync<TF>(slot, SLOTS);
-      }
-      static_for<0, P / 2>([&](auto qi) {
-        constexpr int q = decltype(qi)::value;
-        const int k = t + TF * q;  // 0 <= k < M/2
-        cx<T> zp;                  // Z[(M - k) % M]
-        if constexpr (POST_SMEM) {
-          zp = sm[E::pad((M - k) & (M - 1))];
-        } else if constexpr (TF == 1) {
-          zp = v[(P - q) % P];
-        } else {
-          const cx<T> mine = v[P - 1 - q];
-          cx<T> got;
-          got.x = simt::shfl(mine.x, (TF - t) & (TF - 1), TF);
-          got.y = simt::shfl(mine.y, (TF - t) & (TF - 1), TF);
-          zp = (t == 0) ? v[(P - q) % P] : got;
-        }
-        const cx<T> a = v[q];
-        const cx<T> sum{a.x + zp.x, a.y - zp.y};  // A + conj(Zp)
-        const cx<T> dif{a.x - zp.x, a.y + zp.y};  // A - conj(Zp)
-        const cx<T> w = ldg_cx(post + k);          // (wi/2, -wr/2): W_N^k * (-i/2)
-        const cx<T> tt = cmul(dif, w);
-        cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};     // X[k]
-        cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};  // X[M-k] = conj(E - W*O)
-        if constexpr (q == 0) {
-          // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
-          // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
-          if (t == 0) {
-            xa.y = (T)0;
-            xb.y = (T)0;
-          }
-        }
-        emit(k, xa);
-        emit(M - k, xb);
-      });
-      if (t == 0) emit(M / 2, cx<T>{v[P / 2].x, -v[P / 2].y});  // self-paired bin: conj(Z[M/2])
-      if constexpr (POST_SMEM) frame_sync<TF>(slot, SLOTS);      // partner reads done before smem is reused
+    if constexpr (M > 1 && POST_SMEM) {
+      static_for<0, P>([&](auto q) { sm[E::pad(t + TF * decltype(q)::value)] = v[decltype(q)::value]; });
+      frame_sync<TF>(slot, SLOTS);
     }
+    {
+      int verdict = post_pass(std::false_type{});
+      if (!valid) verdict = 0;  // tail slots hold no frame
+      if constexpr (sizeof(T) == 8) {
+        // rare: some |X|^2 over/underflowed - redo the epilogue with hypot(), like Math.hypot.  Votes span
+        // the warp (the shuffles inside post_pass need converged lanes).
+        bool redo = simt::any((verdict & 1) != 0);
+        if (!redo && simt::any((verdict & 2) != 0)) {
+          // some thread saw only zeros: genuine silence, or bins below 2^-521 whose squares underflowed?
+          bool nonzero = false;
+          static_for<0, P>([&](auto q) { nonzero = nonzero || v[decltype(q)::value].x != (T)0 || v[decltype(q)::value].y != (T)0; });
+          redo = simt::any(nonzero);
+        }
+        if (redo) post_pass(std::true_type{});
+      }
+    }
+    if constexpr (M > 1 && POST_SMEM) frame_sync<TF>(slot, SLOTS);  // partner reads done before smem is reused
 
     // ---- findPeak: (value desc, index asc) reduction over the frame's threads
     if (want_peak) {

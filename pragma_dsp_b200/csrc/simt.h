@@ -39,6 +39,7 @@ template <typename T>
 PDSP_DEVICE T shfl_xor(T v, int mask, int width) {
   return __shfl_xor_sync(0xffffffffu, v, mask, width);
 }
+PDSP_DEVICE bool any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
 PDSP_DEVICE unsigned char* smem() {
   extern __shared__ __align__(16) unsigned char pdsp_smem_[];
   return pdsp_smem_;
@@ -98,6 +99,11 @@ inline T shfl_xor(T v, int mask, int width) {
   T r;
   emu_shfl(&v, &r, (int)sizeof(T), mask, width, true);
   return r;
+}
+inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over the warp's lanes
+  int acc = pred ? 1 : 0;
+  for (int m = 16; m >= 1; m >>= 1) acc |= shfl_xor(acc, m, 32);
+  return acc != 0;
 }
 inline unsigned char* smem() { return emu_self.smem; }
 template <typename T>
