@@ -13,14 +13,16 @@ constexpr int kVariantLog2M = 9;   // N = 1024, the headline size
 // selectable at run time with PDSP_VARIANT=<n> so one GPU session can rank them.
 template <typename T, int LOG2M, int VAR = 0>
 struct KCfg {
-  static constexpr int LOG2P = LOG2M < 3 ? LOG2M : (LOG2M >= 9 ? 4 : 3);
-  // radix 16 passes where a thread holds 16 points (fewest exchanges: 512 = 16 x 16 x 2), else radix 8
-  static constexpr int MAXRB = LOG2P == 4 ? 4 : 3;
+  // doubles: 16 points per thread from M = 512 up (radix 16 passes: 512 = 16 x 16 x 2, one warp per frame);
+  // floats: 32 points per thread (radix 32: 512 = 32 x 16, a single exchange) - registers allow it and the
+  // fp32 kernels are issue-bound, so fewer exchange instructions win (profiles/r1 sweep).  Below 512: 8.
+  static constexpr int LOG2P = LOG2M < 3 ? LOG2M : (LOG2M >= 9 ? (sizeof(T) == 4 ? 5 : 4) : 3);
+  static constexpr int MAXRB = LOG2P >= 4 ? LOG2P : 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
-  static constexpr int THREADS = TF > 128 ? TF : 128;
-  // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread for 128-thread CTAs of
-  // doubles, 96 for floats.  MAXREG > 0 selects a hard __maxnreg__ cap instead (tuning variants).
-  static constexpr int MINB = THREADS <= 128 ? (sizeof(T) == 8 ? 4 : 5) : (THREADS <= 256 ? 2 : 1);
+  static constexpr int THREADS = (sizeof(T) == 4 && LOG2P == 5) ? (TF > 32 ? TF : 32) : (TF > 128 ? TF : 128);
+  // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread, except 96 for floats holding
+  // 8 or 16 points.  MAXREG > 0 selects a hard __maxnreg__ cap instead (tuning variants).
+  static constexpr int MINB = (sizeof(T) == 4 && LOG2P < 5 && THREADS <= 128) ? 5 : (512 / THREADS > 0 ? 512 / THREADS : 1);
   static constexpr int MAXREG = 0;
 };
 
@@ -41,7 +43,8 @@ PDSP_VARIANT(3, 3, 3, 128, 6, 8, 0, 0)      // 8 x 8 x 8, two warps per frame (n
 PDSP_VARIANT(4, 4, 3, 128, 3, 4, 0, 0)      // baseline mapping with a looser register cap
 PDSP_VARIANT(5, 5, 5, 128, 2, 4, 0, 0)      // 32 x 16, 8 frames per CTA
 PDSP_VARIANT(6, 4, 3, 256, 2, 2, 0, 0)      // baseline mapping, 8 frames per CTA
-PDSP_VARIANT(7, 5, 5, 32, 8, 16, 0, 0)      // 32 x 16, one warp (2 frames) per CTA
+PDSP_VARIANT(7, 5, 5, 32, 8, 16, 0, 0)      // 32 x 16, one warp (2 frames) per CTA (= the fp32 default)
+
 PDSP_VARIANT(8, 4, 4, 32, 18, 24, 0, 0)     // 16 x 16 x 2, single-warp CTAs: 18 (f64) / 24 (f32) per SM
 PDSP_VARIANT(9, 4, 4, 32, 20, 28, 0, 0)     // same, 20 / 28 per SM
 PDSP_VARIANT(10, 4, 4, 32, 1, 1, 112, 80)   // same, hard caps 112 / 80 registers

@@ -105,6 +105,15 @@ PDSP_DEVICE float fast_sqrt(float s) { return sqrtf(s); }
 PDSP_DEVICE double fast_sqrt(double s) { return sqrt(s); }
 #endif
 
+// |re + i*im| for one value: fast_sqrt inside the safe exponent range, hypot() outside it
+PDSP_DEVICE double t_mag_checked(double re, double im) {
+  const double ss = re * re + im * im;
+  const unsigned hi = (unsigned)__double2hiint(ss);
+  if (hi >= 0x7fd00000u || hi < 0x00400000u) return t_hypot_slow(re, im);
+  return fast_sqrt(ss);
+}
+PDSP_DEVICE float t_mag_checked(float re, float im) { return fast_sqrt(re * re + im * im); }
+
 template <typename T>
 struct PeakCand {
   T v;     // scaled amplitude of the best non-DC bin so far (0 = none)
@@ -148,6 +157,9 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   constexpr bool PHASE = GEN || (MODE & MD_PHASE) != 0;
   constexpr bool POST_SMEM = TF > 32;  // partner bin via shared memory instead of shuffle
   constexpr int SLOT_ELEMS = (E::NEEDS_SMEM || POST_SMEM) ? E::SMEM_ELEMS : 0;
+  // peak-only kernels rank bins by |X|^2 (no square root per bin); the winner's amplitude is computed
+  // once, in the finishing loop.  Frames spanning several warps keep the linear key.
+  constexpr bool KEYSQ = MODE == MD_PEAK && TF <= 32;
 
   const int tid = simt::tid();
   const int slot = tid / TF;
@@ -162,6 +174,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const int bins = two_sided ? N : M + 1;
   const int cbins = cfull ? N : M + 1;
   const T s_edge = (T)p.scale_edge, s_mid = (T)p.scale_mid;
+  [[maybe_unused]] const T edge_key = (T)((p.scale_edge / p.scale_mid) * (p.scale_edge / p.scale_mid));
   const bool want_cplx = GEN ? p.out_re != nullptr : (MODE & MD_CPLX) != 0;
   const bool want_amp = GEN ? p.amp != nullptr : (MODE & MD_AMP) != 0;
   const bool want_phase = GEN ? p.phase != nullptr : (MODE & MD_PHASE) != 0;
@@ -266,21 +279,34 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           }
         }
         if (need_mag) {
-          T mag;
-          if constexpr (CAREFUL) {
-            mag = t_hypot_slow(X.x, X.y);
-          } else {
+          T a;
+          if constexpr (KEYSQ && !CAREFUL) {
+            // ranking key |X|^2 relative to the interior scale: Nyquist (and DC) carry (s_edge/s_mid)^2
             const T ss = X.x * X.x + X.y * X.y;
             if constexpr (sizeof(T) == 8) {
               const unsigned hi = (unsigned)__double2hiint((double)ss);
               hi_max = hi > hi_max ? hi : hi_max;
               lo_min = (hi - 1u) < lo_min ? (hi - 1u) : lo_min;
             }
-            mag = fast_sqrt(ss);
+            a = ss;
+            if constexpr (EDGE) a = (k == 0 || k == M) ? ss * edge_key : ss;
+          } else {
+            T mag;
+            if constexpr (CAREFUL) {
+              mag = t_hypot_slow(X.x, X.y);
+            } else {
+              const T ss = X.x * X.x + X.y * X.y;
+              if constexpr (sizeof(T) == 8) {
+                const unsigned hi = (unsigned)__double2hiint((double)ss);
+                hi_max = hi > hi_max ? hi : hi_max;
+                lo_min = (hi - 1u) < lo_min ? (hi - 1u) : lo_min;
+              }
+              mag = fast_sqrt(ss);
+            }
+            T scale = s_mid;
+            if constexpr (EDGE) scale = (k == 0 || k == M) ? s_edge : s_mid;
+            a = mag * scale;
           }
-          T scale = s_mid;
-          if constexpr (EDGE) scale = (k == 0 || k == M) ? s_edge : s_mid;
-          const T a = mag * scale;
           if (want_amp && o_amp != nullptr) {
             (o_amp + b0)[OFF] = a;
             if (two_sided && (!EDGE || (k != 0 && k != M))) (o_amp + m0)[-OFF] = a;
@@ -429,22 +455,38 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         }
         frame_sync<TF>(slot, SLOTS);
       }
-      // the thread that owns the winning bin writes the record; no non-DC bin > 0 -> bin 0
+      // The thread that owns the winning bin parks (index, re, im[, amplitude]) in the record; no non-DC
+      // bin > 0 -> bin 0.  frequency / phase (and the amplitude in peak-only mode) are filled in by the
+      // CTA-wide finishing loop below, where every lane has a record - an atan2 issued here would occupy
+      // the whole warp for one lane.
       const bool owner = bk != 0 ? (best.k == bk) : (t == 0);
       if (valid && owner) {
         PeakRec<T> rec;
         rec.index = bk;
-        rec.frequency = (T)((double)bk * p.bin_hz);
-        if (bk != 0) {
-          rec.amplitude = best.v;
-          rec.phase = t_atan2(best.im, best.re);
-        } else {
-          rec.amplitude = dc_amp;
-          rec.phase = t_atan2((T)0, dc_re);
-        }
+        rec.frequency = bk != 0 ? best.re : dc_re;
+        rec.phase = bk != 0 ? best.im : (T)0;
+        rec.amplitude = bk != 0 ? best.v : dc_amp;  // a squared key in peak-only mode; recomputed below
         if constexpr (sizeof(T) == 8) rec.pad = 0;
         static_cast<PeakRec<T>*>(p.peaks)[f] = rec;
       }
+    }
+  }
+
+  if (want_peak) {
+    // finish the records of the frames this CTA processed: amplitude (peak-only mode), frequency, phase
+    simt::sync_block();
+    PeakRec<T>* recs = static_cast<PeakRec<T>*>(p.peaks);
+    const long long groups = (p.batch + SLOTS - 1) / SLOTS;
+    const long long my_groups = groups > simt::bid() ? (groups - simt::bid() + simt::nblocks() - 1) / simt::nblocks() : 0;
+    for (long long idx = tid; idx < my_groups * SLOTS; idx += THREADS) {
+      const long long f = (simt::bid() + (idx / SLOTS) * simt::nblocks()) * SLOTS + (idx % SLOTS);
+      if (f >= p.batch) continue;
+      PeakRec<T> rec = recs[f];
+      const T re = rec.frequency, im = rec.phase;
+      if (KEYSQ) rec.amplitude = t_mag_checked(re, im) * ((rec.index == 0 || rec.index == M) ? s_edge : s_mid);
+      rec.frequency = (T)((double)rec.index * p.bin_hz);
+      rec.phase = t_atan2(im, re);
+      recs[f] = rec;
     }
   }
 }
