@@ -39,6 +39,10 @@ WORKLOADS = {
                desc="spectrum() batched: 65536 frames x N=1024 fp32, Hann, one-sided amplitude + peak @48kHz"),
     "north_star": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude",), frames=65536, n=1024,
                        desc="fp64 Hann-windowed FFT + one-sided magnitude, 65536 frames x N=1024"),
+    # BASELINE config C3: STFT via spectrumStream - 10 min @ 48 kHz, N=4096, hop 1024, Hann, magnitude + phase,
+    # Float32Array frames (spectrumStream's element type) computed in fp64 like the reference
+    "c3": dict(prec="f64", sdtype="f32", window="hann", outputs=("amplitude", "phase"), frames=28122, n=4096, hop=1024,
+               desc="STFT: 28,800,000 fp32 samples (10 min @48kHz), N=4096 hop 1024 Hann, fp64 amplitude + phase, 28122 frames"),
     # BASELINE config C4: large single complex fp64 transforms (multi-pass path); a "frame" is one transform
     "c4_2e20": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=8, n=1 << 20, kind="c2c",
                     desc="complex fp64 FFT, N=2^20, 8 transforms per step (multi-pass 1024x1024)"),
@@ -56,7 +60,7 @@ def algorithmic_bytes_per_frame(w) -> int:
     if w.get("kind") == "c2c":
         return 2 * 2 * es * w["n"]  # both planes in, both planes out
     bins = w["n"] // 2 + 1
-    b = w["n"] * es
+    b = w.get("hop", w["n"]) * es  # unique input bytes per frame (overlap re-reads are expected to hit L2)
     if "amplitude" in w["outputs"]:
         b += bins * os_
     if "phase" in w["outputs"]:
@@ -136,7 +140,8 @@ def run_reference(args, w):
 
 
 def workload_config(args, w):
-    return {"workload": args.workload, "description": w["desc"], "fft_size": w["n"], "frames_per_gpu": w["frames"],
+    return {"workload": args.workload, "description": w["desc"], "fft_size": w["n"], "hop": w.get("hop", w["n"]),
+            "frames_per_gpu": w["frames"],
             "window": w["window"], "sides": "one", "sample_rate": 48000, "outputs": list(w["outputs"]),
             "sample_dtype": w["sdtype"], "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
             "parallelism": f"frames sharded x{args.gpus}"}
@@ -158,6 +163,23 @@ def synth_frames_numpy(frames, n, dtype, seed=SEED):
         for j in range(3):
             acc += a[:, j, None] * np.sin(2 * np.pi * k[:, j, None] * t[None, :] / n + ph[:, j, None])
         out[lo:hi] = acc.astype(dtype)
+    return out
+
+
+def synth_stream_torch(torch, samples, dtype, device, seed):
+    """One long multi-tone stream (3 tones, slowly chirped) for the STFT workload."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(samples, dtype=dtype, device=device)
+    f0 = torch.tensor([440.0, 1500.0, 5200.0], dtype=torch.float64, device=device)
+    a = torch.tensor([1.0, 0.4, 0.2], dtype=torch.float64, device=device)
+    for lo in range(0, samples, 1 << 22):
+        hi = min(samples, lo + (1 << 22))
+        t = torch.arange(lo, hi, dtype=torch.float64, device=device) / 48000.0
+        acc = torch.zeros(hi - lo, dtype=torch.float64, device=device)
+        for j in range(3):
+            acc += a[j] * torch.sin(2 * np.pi * (f0[j] * t + 0.5 * (20.0 * (j + 1)) * t * t / 60.0))
+        out[lo:hi] = acc.to(dtype)
     return out
 
 
@@ -263,14 +285,18 @@ def run_b200(args, w):
     bins = n // 2 + 1
     pk_bytes = 32 if prec == F64 else 16
 
-    x = synth_frames_torch(torch, frames, n, sdt, dev, SEED + rank)
+    hop = w.get("hop", n)
+    if hop == n:
+        x = synth_frames_torch(torch, frames, n, sdt, dev, SEED + rank)
+    else:  # one long stream, frames are overlapping views
+        x = synth_stream_torch(torch, (frames - 1) * hop + n, sdt, dev, SEED + rank)
     amp = torch.empty((frames, bins), dtype=tdt, device=dev) if "amplitude" in w["outputs"] else None
     ph = torch.empty((frames, bins), dtype=tdt, device=dev) if "phase" in w["outputs"] else None
     want_peak = "peak" in w["outputs"]
     peaks = [torch.zeros((frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] if want_peak else None
     gathered = [torch.zeros((world * frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] \
         if (want_peak and world > 1) else None
-    desc = SpectrumDesc(sample_dtype=F64 if w["sdtype"] == "f64" else F32, frame_len=n, hop=n, batch=frames,
+    desc = SpectrumDesc(sample_dtype=F64 if w["sdtype"] == "f64" else F32, frame_len=n, hop=hop, batch=frames,
                         window=WINDOWS[w["window"]], sides=SIDES["one"], sample_rate=48000.0, raw_magnitude=0)
     compute = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev) if gathered else None
@@ -353,11 +379,11 @@ def run_b200(args, w):
 
     # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
     e2e_steps = max(2, min(args.steps, 10)) if not args.quick else 1
-    hx = torch.empty((frames, n), dtype=sdt).pin_memory()
+    hx = torch.empty(tuple(x.shape), dtype=sdt).pin_memory()
     hx.copy_(x.cpu())
     hx_np = hx.numpy()
     outs = tuple(w["outputs"])
-    h2d = frames * n * hx.element_size()
+    h2d = hx.numel() * hx.element_size()
     d2h = frames * ((bins * (8 if prec == F64 else 4) if "amplitude" in outs else 0) +
                     (bins * (8 if prec == F64 else 4) if "phase" in outs else 0) + (pk_bytes if want_peak else 0))
     # pinned output buffers handed to the C-ABI directly (what createComplexArray-style pinned arrays give JS)
@@ -390,19 +416,26 @@ def run_b200(args, w):
     cpu_baseline = None
     if rank == 0:
         import oracle
-        sub = hx_np[:256]
-        got = spectrum_batch(sub, sampleRate=48000.0, fftSize=n, window=w["window"], precision=w["prec"], context=ctx)
-        ref = oracle.spectrum_batch(sub, fftSize=n, sampleRate=48000.0, window=w["window"])
+        if hop == n:
+            sub, kw = hx_np[:256], {}
+        else:
+            sub, kw = hx_np[:255 * hop + n], dict(frameLen=n, hop=hop, batch=256)
+        got = spectrum_batch(sub, sampleRate=48000.0, fftSize=n, window=w["window"], precision=w["prec"], context=ctx, **kw)
+        ref = oracle.spectrum_batch(sub, fftSize=n, sampleRate=48000.0, window=w["window"], **kw)
         parity = {"frames": 256, "peak_index_equal": bool((got["peaks"]["index"] == ref["peaks"]["index"]).all()),
                   "amp_max_abs_err": float(np.abs(got["amplitude"] - ref["amplitude"]).max())}
         if world == 1 and not args.quick:
-            sample = min(frames, 65536)
+            sample = min(frames, 65536 if n <= 1024 else 16384)
+            if hop == n:
+                sx, skw = hx_np[:sample], {}
+            else:
+                sx, skw = hx_np[:(sample - 1) * hop + n], dict(frameLen=n, hop=hop, batch=sample)
             t0 = time.perf_counter()
-            oracle.spectrum_batch(hx_np[:sample], fftSize=n, sampleRate=48000.0, window=w["window"], threads=1)
+            oracle.spectrum_batch(sx, fftSize=n, sampleRate=48000.0, window=w["window"], threads=1, **skw)
             one = sample / (time.perf_counter() - t0)
             thr = oracle.max_threads()
             t0 = time.perf_counter()
-            oracle.spectrum_batch(hx_np[:sample], fftSize=n, sampleRate=48000.0, window=w["window"], threads=thr)
+            oracle.spectrum_batch(sx, fftSize=n, sampleRate=48000.0, window=w["window"], threads=thr, **skw)
             allc = sample / (time.perf_counter() - t0)
             cpu_baseline = {"value": one, "unit": "frames/s", "cores": 1, "kind": "port",
                             "sample": f"first {sample} frames of the same batch through oracle/pragma_oracle.c "
