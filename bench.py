@@ -7,8 +7,8 @@ Metric (BASELINE.json): batched N=1024 FFT frames/s (+ achieved HBM GB/s).  A "s
 of the fused kernel (frame build + window + FFT + amplitude + peak) over one batch of synthetic
 multi-tone frames.  Default workload = BASELINE configs[1] ("c2"): 65,536 frames x N=1024 fp32,
 Hann, one-sided amplitude + peak @ 48 kHz per GPU (weak scaling: every rank owns a batch of that
-size; with N>1 the per-frame peaks are all-gathered over NCCL on a side stream, overlapped with
-the next step's kernel).  Other workloads: "north_star" (fp64 Hann FFT + one-sided magnitude),
+size; with N>1 every rank also receives all ranks' per-frame peaks - by default through NVLink peer
+stores fused into the kernel's epilogue (--gather p2p), alternatively a side-stream NCCL all_gather).  Other workloads: "north_star" (fp64 Hann FFT + one-sided magnitude),
 "c5" (fp64 window + FFT + peak only).
 
 One JSON line on stdout (rank 0).  `value` = whole-job frames/s with inputs resident in HBM;
@@ -88,7 +88,7 @@ def run_reference(args, w):
         return 0
     import oracle
 
-    threads = oracle.max_threads()
+    threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1; the oracle takes an explicit count
     n = w["n"]
     if w.get("kind") == "c2c":
         rng = np.random.default_rng(SEED)
@@ -294,8 +294,28 @@ def run_b200(args, w):
     ph = torch.empty((frames, bins), dtype=tdt, device=dev) if "phase" in w["outputs"] else None
     want_peak = "peak" in w["outputs"]
     peaks = [torch.zeros((frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] if want_peak else None
+    gather = args.gather if (want_peak and world > 1) else "none"
     gathered = [torch.zeros((world * frames, pk_bytes), dtype=torch.uint8, device=dev) for _ in range(2)] \
-        if (want_peak and world > 1) else None
+        if gather == "nccl" else None
+    peers = gbuf = None
+    if gather == "p2p":
+        # every rank owns a (world * frames) record buffer; all ranks map all of them (CUDA IPC over NVLink)
+        # and the kernel's epilogue stores each finished record into every one of them
+        gbuf = C.c_void_p()
+        check(lib().pdsp_dev_alloc(ctx.h, world * frames * pk_bytes, C.byref(gbuf)))
+        hbuf = C.create_string_buffer(64)
+        check(lib().pdsp_ipc_export(ctx.h, gbuf, hbuf))
+        handles = [None] * world
+        dist.all_gather_object(handles, hbuf.raw)
+        peers = (C.c_void_p * 8)()
+        for g_ in range(world):
+            if g_ == rank:
+                peers[g_] = gbuf.value
+            else:
+                pp = C.c_void_p()
+                check(lib().pdsp_ipc_open(ctx.h, handles[g_], C.byref(pp)))
+                peers[g_] = pp.value
+        dist.barrier()
     desc = SpectrumDesc(sample_dtype=F64 if w["sdtype"] == "f64" else F32, frame_len=n, hop=hop, batch=frames,
                         window=WINDOWS[w["window"]], sides=SIDES["one"], sample_rate=48000.0, raw_magnitude=0)
     compute = torch.cuda.Stream(device=dev)
@@ -316,7 +336,11 @@ def run_b200(args, w):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(compute)
-            check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), C.c_void_p(compute.cuda_stream)))
+            if peers is not None:
+                check(L.pdsp_spectrum_dev_gather(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), peers, world,
+                                                 rank * frames, C.c_void_p(compute.cuda_stream)))
+            else:
+                check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), C.c_void_p(compute.cuda_stream)))
             if timed:
                 e1.record(compute)
                 kernel_events.append((e0, e1))
@@ -376,6 +400,26 @@ def run_b200(args, w):
     if sampler:
         sampler.stop()
     barrier()
+
+    gather_check = None
+    if peers is not None:
+        # every rank's segment of the local gathered buffer must hold that rank's records
+        host = np.zeros(world * frames * pk_bytes, dtype=np.uint8)
+        check(L.pdsp_memcpy_d2h(ctx.h, C.c_void_p(host.ctypes.data), gbuf, host.nbytes, C.c_void_p(compute.cuda_stream)))
+        compute.synchronize()
+        rec = host.view(PEAK_F64 if prec == F64 else PEAK_F32)
+        mine = peaks[(args.steps - 1) & 1].cpu().numpy().view(PEAK_F64 if prec == F64 else PEAK_F32).reshape(-1)
+        ok_self = bool((rec[rank * frames:(rank + 1) * frames] == mine).all())
+        ok_all = bool(((rec["index"] >= 8) & (rec["index"] < n // 2)).all())
+        gather_check = {"mode": "p2p", "own_segment_equal": ok_self, "all_segments_filled": ok_all}
+        barrier()
+        for g_ in range(world):
+            if g_ != rank:
+                check(L.pdsp_ipc_close(ctx.h, C.c_void_p(peers[g_])))
+        barrier()
+        check(L.pdsp_dev_free(ctx.h, gbuf))
+    elif gathered is not None:
+        gather_check = {"mode": "nccl"}
 
     # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
     e2e_steps = max(2, min(args.steps, 10)) if not args.quick else 1
@@ -470,6 +514,7 @@ def run_b200(args, w):
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
             "parity": parity,
+            "gather": gather_check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -607,6 +652,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how per-frame peaks reach every rank - peer stores fused into the kernel epilogue (p2p) "
+                         "or a side-stream NCCL all_gather")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the clock probe, CPU baseline, shorten e2e")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

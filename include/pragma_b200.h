@@ -110,6 +110,20 @@ int pdsp_spectrum(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* s
  *      (a cudaStream_t passed as void*; NULL = the context's stream) ------------------------- */
 int pdsp_spectrum_dev(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* d_samples, void* d_amplitude,
                       void* d_phase, void* d_peaks, void* stream);
+/* Frame-sharded multi-GPU form (BASELINE config C5; no reference counterpart - the reference is
+ * single-process): as pdsp_spectrum_dev, and in addition every finished peak record of local frame f is
+ * stored by the same kernel into peer_peaks[g] + (record_offset + f) records for g < n_peers - buffers of
+ * the other ranks' GPUs mapped with pdsp_ipc_open (NVLink peer stores fused into the epilogue; no
+ * separate all-gather).  d_peaks is the local workspace (required).  The caller synchronises the ranks
+ * before reading a gathered buffer. */
+int pdsp_spectrum_dev_gather(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* d_samples, void* d_amplitude,
+                             void* d_phase, void* d_peaks, void* const* peer_peaks, int n_peers, int64_t record_offset,
+                             void* stream);
+/* CUDA IPC plumbing for the peer buffers: export a device allocation made by pdsp_dev_alloc as a 64-byte
+ * handle, open / close another process's handle on this context's device. */
+int pdsp_ipc_export(pdsp_ctx* ctx, void* d_ptr, unsigned char handle[64]);
+int pdsp_ipc_open(pdsp_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int pdsp_ipc_close(pdsp_ctx* ctx, void* d_ptr);
 /* real forward: out planes in plan precision; full != 0 writes all N bins, else N/2+1 */
 int pdsp_fft_forward_real_dev(pdsp_plan* plan, const void* d_in, int in_dtype, int64_t batch, void* d_out_re,
                               void* d_out_im, int full, void* stream);

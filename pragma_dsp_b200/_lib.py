@@ -57,6 +57,10 @@ SYMBOLS = {
     "pdsp_phase": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "pdsp_spectrum": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp]),
     "pdsp_spectrum_dev": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp, _vp]),
+    "pdsp_spectrum_dev_gather": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp, C.POINTER(_vp), C.c_int, _i64, _vp]),
+    "pdsp_ipc_export": (C.c_int, [_vp, _vp, C.c_char_p]),
+    "pdsp_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "pdsp_ipc_close": (C.c_int, [_vp, _vp]),
     "pdsp_fft_forward_real_dev": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, C.c_int, _vp]),
     "pdsp_fft_complex_dev": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _vp]),
     "pdsp_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),

@@ -52,6 +52,11 @@ struct R2CParams {
   double scale_edge;  // amplitude scale of DC and Nyquist
   double scale_mid;   // amplitude scale of every other bin
   double bin_hz;      // sampleRate / N
+  // fused gather of the peak records over NVLink peer memory: every finished record of frame f is also
+  // stored to peer[g] + (peer_offset + f) records, g < n_peers (mapped peer buffers, one per rank incl. self)
+  void* peer[8];
+  int n_peers;
+  long long peer_offset;
 };
 
 struct C2CParams {
@@ -487,6 +492,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       rec.frequency = (T)((double)rec.index * p.bin_hz);
       rec.phase = t_atan2(im, re);
       recs[f] = rec;
+      for (int g = 0; g < p.n_peers; ++g) static_cast<PeakRec<T>*>(p.peer[g])[p.peer_offset + f] = rec;
     }
   }
 }

@@ -402,9 +402,15 @@ struct SpecGeom {
   size_t out_esize, peak_size;
 };
 
+struct PeerSpec {
+  void* const* ptrs;
+  int n;
+  long long offset;
+};
+
 static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, long long batch,
                            void* d_amp, void* d_phase, void* d_peaks, void* d_cre, void* d_cim, int cfull,
-                           cudaStream_t st) {
+                           cudaStream_t st, const PeerSpec* peers = nullptr) {
   pdsp_ctx* c = pl->ctx;
   const int n = pl->n;
   R2CParams p;
@@ -426,6 +432,11 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
   p.amp = d_amp;
   p.phase = d_phase;
   p.peaks = d_peaks;
+  if (peers) {
+    for (int g = 0; g < peers->n; ++g) p.peer[g] = peers->ptrs[g];
+    p.n_peers = peers->n;
+    p.peer_offset = peers->offset;
+  }
   p.two_sided = d->sides == PDSP_SIDES_TWO;
   if (d->raw_magnitude) {
     p.scale_edge = p.scale_mid = 1.0;
@@ -866,6 +877,58 @@ PDSP_EXPORT int pdsp_spectrum_dev(pdsp_plan* pl, const pdsp_spectrum_desc* d, co
   if (!d_samples && d->frame_len > 0) return fail("null samples");
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
   return launch_spectrum(pl, d, d_samples, d->batch, d_amp, d_phase, d_peaks, nullptr, nullptr, 0, st);
+}
+
+PDSP_EXPORT int pdsp_spectrum_dev_gather(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, void* d_amp,
+                                         void* d_phase, void* d_peaks, void* const* peer_peaks, int n_peers,
+                                         int64_t record_offset, void* stream) {
+  if (check_desc(pl, d)) return 1;
+  if (!d_peaks) return fail("pdsp_spectrum_dev_gather needs the local peaks workspace");
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_peaks)) return fail("n_peers must be 0..8 with a pointer table");
+  if (record_offset < 0) return fail("negative record offset");
+  if (pl->n == 1) return fail("pdsp_spectrum_dev_gather needs an FFT size of at least 2");
+  if (set_device(pl->ctx)) return 1;
+  if (d->batch == 0) return 0;
+  if (!d_samples && d->frame_len > 0) return fail("null samples");
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream;
+  PeerSpec ps{peer_peaks, n_peers, record_offset};
+  return launch_spectrum(pl, d, d_samples, d->batch, d_amp, d_phase, d_peaks, nullptr, nullptr, 0, st, &ps);
+}
+
+PDSP_EXPORT int pdsp_ipc_export(pdsp_ctx* c, void* d_ptr, unsigned char handle[64]) {
+  if (!c || !d_ptr || !handle) return fail("null argument");
+  if (set_device(c)) return 1;
+#ifdef PDSP_EMU
+  return fail("CUDA IPC is not available in the emulated test build");
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, 64);
+  return 0;
+#endif
+}
+PDSP_EXPORT int pdsp_ipc_open(pdsp_ctx* c, const unsigned char handle[64], void** d_ptr) {
+  if (!c || !d_ptr || !handle) return fail("null argument");
+  if (set_device(c)) return 1;
+#ifdef PDSP_EMU
+  return fail("CUDA IPC is not available in the emulated test build");
+#else
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+#endif
+}
+PDSP_EXPORT int pdsp_ipc_close(pdsp_ctx* c, void* d_ptr) {
+  if (!c || !d_ptr) return fail("null argument");
+  if (set_device(c)) return 1;
+#ifdef PDSP_EMU
+  return fail("CUDA IPC is not available in the emulated test build");
+#else
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+#endif
 }
 
 PDSP_EXPORT int pdsp_fft_forward_real_dev(pdsp_plan* pl, const void* d_in, int in_dtype, int64_t batch, void* d_ore,

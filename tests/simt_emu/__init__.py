@@ -22,7 +22,8 @@ class R2CParams(C.Structure):
                 ("hop", C.c_longlong), ("batch", C.c_longlong), ("window", C.c_void_p), ("tw", C.c_void_p),
                 ("post", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p), ("cfull", C.c_int),
                 ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int),
-                ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double)]
+                ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double),
+                ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong)]
 
 
 class C2CParams(C.Structure):
