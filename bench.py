@@ -33,6 +33,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 SEED = 1337
+_STDOUT_GUARD = None
+
+
+def emit_line(obj):
+    """The ONE JSON line, on the real stdout."""
+    global _STDOUT_GUARD
+    if _STDOUT_GUARD is not None:
+        _STDOUT_GUARD.restore()
+        _STDOUT_GUARD = None
+    print(json.dumps(obj), flush=True)
+
 WORKLOADS = {
     # name: (precision, sample dtype, window, outputs, frames/GPU, N, description)
     "c2": dict(prec="f32", sdtype="f32", window="hann", outputs=("amplitude", "peak"), frames=65536, n=1024,
@@ -101,13 +112,13 @@ def run_reference(args, w):
             plan.forwardComplex(re, im)
         dt = time.perf_counter() - t0
         fps = args.steps / dt
-        print(json.dumps({"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s",
+        emit_line({"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
                                            "sample": "one transform per step (a single radix-2 transform does not thread)"},
-                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
     # bounded sample: about 0.5 s of all-core work per step
     sample = int(min(w["frames"], max(2048, 12000 * threads)))
@@ -135,7 +146,7 @@ def run_reference(args, w):
                                    f"scaling, findPeak), gcc -O2 -ffp-contract=off, OpenMP static split"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -516,7 +527,7 @@ def run_b200(args, w):
             "parity": parity,
             "gather": gather_check,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -636,12 +647,27 @@ def run_b200_c2c(args, w):
                     "d2h_bytes_per_step": 16 * n * frames, "steps": e2e_steps, "api": "pdsp_fft_forward_complex (host pinned)"},
             "gpu_launches": launches * world, "clocks": sampler.summary() if sampler else None, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+class StdoutToStderr:
+    """Keeps stdout clean for the single JSON line: anything libraries print to fd 1 meanwhile (NCCL's
+    version banner, for one) goes to stderr; restore() gives the real stdout back for the result line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -660,11 +686,17 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.frames:
         w["frames"] = args.frames
-    if args.impl == "reference":
-        return run_reference(args, w)
-    if w.get("kind") == "c2c":
-        return run_b200_c2c(args, w)
-    return run_b200(args, w)
+    global _STDOUT_GUARD
+    _STDOUT_GUARD = StdoutToStderr()
+    try:
+        if args.impl == "reference":
+            return run_reference(args, w)
+        if w.get("kind") == "c2c":
+            return run_b200_c2c(args, w)
+        return run_b200(args, w)
+    finally:
+        if _STDOUT_GUARD is not None:
+            _STDOUT_GUARD.restore()
 
 
 if __name__ == "__main__":

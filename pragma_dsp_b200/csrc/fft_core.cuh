@@ -201,7 +201,9 @@ struct FftEngine {
       // Last pass with several butterflies per thread: Ns = TF*BPT, so r = t + TF*u and
       // W_M^{s*(t + TF*u)} = W_M^{s*t} * exp(-2*pi*i*s*u/P): one table entry per leg (u = 0) and a
       // compile-time 32nd root of unity for the others - P/R - 1 fewer L1 loads per leg.
-      constexpr bool DERIVE = last && NSL > 0 && BPT > 1 && (32 % P) == 0;
+      // (doubles only: the fp64 kernels are L1-bound with DP slack, the fp32 kernels are issue-bound with
+      // L1 slack - there a load is cheaper than the four FP instructions of the derivation)
+      constexpr bool DERIVE = sizeof(T) == 8 && last && NSL > 0 && BPT > 1 && (32 % P) == 0;
       [[maybe_unused]] cx<T> w0[R];
       static_for<0, BPT>([&](auto ui) {
         constexpr int u = decltype(ui)::value;

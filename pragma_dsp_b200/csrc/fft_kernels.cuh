@@ -347,7 +347,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       } else {
         // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
         // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
-        constexpr bool DERIVE = (16 % P) == 0 && P >= 2;
+        constexpr bool DERIVE = sizeof(T) == 8 && (16 % P) == 0 && P >= 2;  // see FftEngine::fft
         cx<T> post0{(T)0, (T)0};
         if constexpr (DERIVE) post0 = ldg_cx(post + t);
         static_for<0, P / 2>([&](auto qi) {

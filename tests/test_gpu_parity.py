@@ -266,3 +266,33 @@ def test_large_multipass_fft_fp32_device(ctx):
     ref = np.fft.fft(re.cpu().numpy().astype(np.float64) + 1j * im.cpu().numpy().astype(np.float64))
     got = ore.cpu().numpy().astype(np.float64) + 1j * oim.cpu().numpy().astype(np.float64)
     assert rel_l2(got, ref) <= 1e-5
+
+
+def test_fused_peer_scatter_single_gpu(ctx):
+    """pdsp_spectrum_dev_gather with the rank's own buffer (and a second local buffer standing in for a
+    peer): every finished peak record lands at record_offset + f in each target."""
+    import torch
+    from pragma_dsp_b200._lib import F32, PEAK_F32, SIDES, WINDOWS, SpectrumDesc, check, lib
+    L = lib()
+    rng = np.random.default_rng(11)
+    n, batch, offset = 1024, 777, 100
+    x = multitone(rng, batch, n, np.float32)
+    dx = torch.from_numpy(x).cuda()
+    local = torch.zeros((batch, 16), dtype=torch.uint8, device="cuda")
+    tgt = [torch.zeros((offset + batch + 5, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    peers = (C.c_void_p * 8)()
+    peers[0], peers[1] = tgt[0].data_ptr(), tgt[1].data_ptr()
+    plan = ctx.plan(n, F32)
+    d = SpectrumDesc(sample_dtype=F32, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
+                     sample_rate=48000.0, raw_magnitude=0)
+    st = torch.cuda.Stream()
+    check(L.pdsp_spectrum_dev_gather(plan, C.byref(d), C.c_void_p(dx.data_ptr()), None, None, C.c_void_p(local.data_ptr()),
+                                     peers, 2, offset, C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann")
+    loc = local.cpu().numpy().view(PEAK_F32).reshape(-1)
+    assert (loc["index"] == ref["peaks"]["index"]).all()
+    for t_ in tgt:
+        rec = t_.cpu().numpy().view(PEAK_F32).reshape(-1)
+        assert (rec[offset:offset + batch] == loc).all()
+        assert (rec[:offset]["index"] == 0).all() and (rec[offset + batch:]["index"] == 0).all()

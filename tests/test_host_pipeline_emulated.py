@@ -186,3 +186,27 @@ def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n):
         if out is not None:
             refr = np.fft.fft(xr)
             assert np.linalg.norm((out.real + 1j * out.imag) - refr) / np.linalg.norm(refr) <= tol
+
+
+def test_fused_peer_scatter_emulated(emu_api):
+    """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
+    from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
+    L = emu_api.lib()
+    ctx = emu_api.default_context()
+    rng = np.random.default_rng(6)
+    n, batch, offset = 1024, 9, 3
+    x = multitone(rng, batch, n)
+    local = np.zeros(batch, dtype=PEAK_F64)
+    tgt = [np.zeros(offset + batch + 2, dtype=PEAK_F64) for _ in range(2)]
+    peers = (C.c_void_p * 8)()
+    peers[0], peers[1] = tgt[0].ctypes.data, tgt[1].ctypes.data
+    d = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
+                     sample_rate=48000.0, raw_magnitude=0)
+    emu_api.check(L.pdsp_spectrum_dev_gather(ctx.plan(n, F64), C.byref(d), C.c_void_p(x.ctypes.data), None, None,
+                                             C.c_void_p(local.ctypes.data), peers, 2, offset, None))
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann")
+    assert (local["index"] == ref["peaks"]["index"]).all()
+    assert np.abs(local["amplitude"] - ref["peaks"]["amplitude"]).max() <= 1e-13
+    assert np.abs(local["phase"] - ref["peaks"]["phase"]).max() <= 1e-9
+    for t_ in tgt:
+        assert (t_[offset:offset + batch] == local).all() and (t_[:offset]["index"] == 0).all()
