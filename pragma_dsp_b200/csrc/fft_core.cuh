@@ -67,6 +67,33 @@ constexpr int bitrev(int k, int bits) {
   return r;
 }
 
+// Compile-time sine/cosine (constant evaluation only: Taylor series in long double after reduction to
+// [-pi, pi]); used for per-register rotation constants such as the window recurrence in r2c_body.
+constexpr long double kPiL = 3.141592653589793238462643383279502884L;
+constexpr long double cx_reduce(long double x) {
+  while (x > kPiL) x -= 2 * kPiL;
+  while (x < -kPiL) x += 2 * kPiL;
+  return x;
+}
+constexpr long double cx_sin(long double x) {
+  x = cx_reduce(x);
+  long double term = x, sum = x;
+  for (int k = 1; k < 20; ++k) {
+    term *= -x * x / ((2 * k) * (2 * k + 1));
+    sum += term;
+  }
+  return sum;
+}
+constexpr long double cx_cos(long double x) {
+  x = cx_reduce(x);
+  long double term = 1, sum = 1;
+  for (int k = 1; k < 20; ++k) {
+    term *= -x * x / ((2 * k - 1) * (2 * k));
+    sum += term;
+  }
+  return sum;
+}
+
 // cos(pi*k/16), k = 0..8 (round-to-nearest binary64 literals)
 constexpr double cos16(int k) {
   switch (k) {

@@ -57,6 +57,11 @@ struct R2CParams {
   void* peer[8];
   int n_peers;
   long long peer_offset;
+  // window by rotation (fp64 specialised kernels): w[i] = a0 - a1*cos(th_i) + a2*cos(2*th_i), th_i = 2*pi*i/(N-1).
+  // winphase[i] = (cos th_i, sin th_i) for i < N; each thread loads its two base phases and rotates them by
+  // compile-time constants - two 16-byte loads per frame instead of one per complex point.  Null: use `window`.
+  const void* winphase;
+  double win_a0, win_a1, win_a2;
 };
 
 struct C2CParams {
@@ -202,7 +207,34 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         const double* s = static_cast<const double*>(p.samples) + base;
         static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
       }
-      if (win != nullptr) {
+      if constexpr (sizeof(T) == 8) {
+        if (p.winphase != nullptr) {
+          const cx<T>* PDSP_RESTRICT wph = static_cast<const cx<T>*>(p.winphase);
+          const cx<T> e0 = ldg_cx(wph + 2 * t), e1 = ldg_cx(wph + 2 * t + 1);  // phases of samples 2t, 2t+1
+          const T a0 = (T)p.win_a0, a1 = (T)p.win_a1, a2 = (T)p.win_a2;
+          static_for<0, P>([&](auto qi) {
+            constexpr int q = decltype(qi)::value;
+            // samples 2(t + TF*q) (+1): phase advanced by q * 2*pi*(2*TF)/(N-1)
+            constexpr long double ang = 2 * kPiL * (long double)(2 * TF * q) / (long double)(N - 1);
+            constexpr T CQ = (T)cx_cos(ang), SQ = (T)cx_sin(ang);
+            const T c0 = e0.x * CQ - e0.y * SQ, c1 = e1.x * CQ - e1.y * SQ;
+            T w0 = a0 - a1 * c0, w1 = a0 - a1 * c1;
+            if (a2 != (T)0) {  // Blackman: cos(2 th) = 2 cos^2(th) - 1
+              w0 += a2 * ((T)2 * c0 * c0 - (T)1);
+              w1 += a2 * ((T)2 * c1 * c1 - (T)1);
+            }
+            v[q].x *= w0;
+            v[q].y *= w1;
+          });
+        } else if (win != nullptr) {
+          static_for<0, P>([&](auto qi) {
+            constexpr int q = decltype(qi)::value;
+            const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
+            v[q].x *= w.x;
+            v[q].y *= w.y;
+          });
+        }
+      } else if (win != nullptr) {
         static_for<0, P>([&](auto qi) {
           constexpr int q = decltype(qi)::value;
           const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));

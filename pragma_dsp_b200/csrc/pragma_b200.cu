@@ -211,7 +211,8 @@ struct pdsp_plan {
   int precision;
   void* d_post = nullptr;  // cx<T>[n/4 + 1]
   void* d_win[4] = {nullptr, nullptr, nullptr, nullptr};
-  BigPlan* big = nullptr;  // built lazily for n > 8192
+  void* d_winphase = nullptr;  // cx<double>[n]: (cos, sin)(2*pi*i/(n-1)), fp64 plans (window by rotation)
+  BigPlan* big = nullptr;      // built lazily for n > 8192
 };
 
 static int set_device(const pdsp_ctx* c) {
@@ -393,6 +394,26 @@ static int plan_window(pdsp_plan* pl, int window, const void** d_win) {
   return 0;
 }
 
+// window by rotation (fp64 specialised kernels): phase table + the window's cosine-series coefficients
+static int plan_winphase(pdsp_plan* pl, int window, const void** d_tab, double coef[3]) {
+  static const double kCoef[4][3] = {{1, 0, 0}, {0.5, 0.5, 0}, {0.54, 0.46, 0}, {0.42, 0.5, 0.08}};
+  for (int i = 0; i < 3; ++i) coef[i] = kCoef[window][i];
+  std::lock_guard<std::recursive_mutex> lk(pl->ctx->plan_mu);
+  if (!pl->d_winphase) {
+    const int n = pl->n;
+    std::vector<cx<double>> tab((size_t)n);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int i = 0; i < n; ++i) {
+      const long double th = two_pi * (long double)i / (long double)(n - 1);
+      tab[(size_t)i] = cx<double>{(double)cosl(th), (double)sinl(th)};
+    }
+    CU(cudaMalloc(&pl->d_winphase, sizeof(cx<double>) * tab.size()));
+    CU(cudaMemcpy(pl->d_winphase, tab.data(), sizeof(cx<double>) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  *d_tab = pl->d_winphase;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ kernel launches
 static size_t esize(int dtype) { return dtype == PDSP_F64 ? 8 : 4; }
 
@@ -463,6 +484,14 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     int mode = (d_amp ? MD_AMP : 0) | (d_phase ? MD_PHASE : 0) | (d_peaks ? MD_PEAK : 0) | (d_cre ? MD_CPLX : 0);
     const bool regular = p.vec_ok && d->frame_len >= n && !p.two_sided && (d_cre == nullptr || cfull) &&
                          mode_is_specialised(mode);
+    if (regular && pl->precision == PDSP_F64 && d->window != PDSP_WIN_RECT && n >= 4) {
+      const char* off = getenv("PDSP_WINROT");  // tuning switch: PDSP_WINROT=0 keeps the table loads
+      if (!(off && off[0] == '0')) {
+        double coef[3];
+        if (plan_winphase(pl, d->window, &p.winphase, coef)) return 1;
+        p.win_a0 = coef[0], p.win_a1 = coef[1], p.win_a2 = coef[2];
+      }
+    }
     e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, regular ? mode : MD_GENERIC, p, lc);
   }
   if (e != cudaSuccess) return fail("r2c launch (n=%d): %s", n, cudaGetErrorString(e));
@@ -760,6 +789,7 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
     pdsp_plan* pl = kv.second;
     cudaFree(pl->d_post);
     for (int i = 0; i < 4; ++i) cudaFree(pl->d_win[i]);
+    cudaFree(pl->d_winphase);
     if (pl->big) {
       for (int i = 0; i < 2; ++i) {
         cudaFree(pl->big->tw_hi[i]);

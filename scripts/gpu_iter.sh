@@ -13,6 +13,13 @@ for l in open('gpurun_out/sweep.jsonl'):
     r = json.loads(l); print(r['workload'], 'v%d' % r['variant'], '%.3f ms' % r['ms'], '%.3e f/s' % r['frames_per_s'], '%.0f GB/s' % r['gbs'], '%.3f' % r['frac_of_measured_hbm'], r['agree_with_v0'])
 PY
 tail -3 gpurun_out/sweep.err
+if [ -n "${AB_ENV:-}" ]; then
+  echo "== A/B: $AB_ENV"; env $AB_ENV timeout 300 python -u scripts/sweep_variants.py --variants 0 > gpurun_out/sweep_ab.jsonl 2>> gpurun_out/sweep.err; python - <<'PY'
+import json
+for l in open('gpurun_out/sweep_ab.jsonl'):
+    r = json.loads(l); print('AB', r['workload'], 'v%d' % r['variant'], '%.3f ms' % r['ms'], '%.3e f/s' % r['frames_per_s'], '%.3f' % r['frac_of_measured_hbm'])
+PY
+fi
 for wl in $WLS; do
   echo "== bench $wl"; timeout 300 python -u bench.py --workload $wl --steps 20 --warmup 3 > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; echo "bench rc=$?"; cat gpurun_out/bench_$wl.json; tail -3 gpurun_out/bench_$wl.err
 done
