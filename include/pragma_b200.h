@@ -97,6 +97,11 @@ int pdsp_fft_inverse(pdsp_plan* plan, const double* in_re, const double* in_im, 
 /* magnitude(c, out) / phase(c, out) (src/xform/fourier.ts:98-120): elementwise over n values */
 int pdsp_magnitude(pdsp_ctx* ctx, const double* re, const double* im, int64_t n, double* out);
 int pdsp_phase(pdsp_ctx* ctx, const double* re, const double* im, int64_t n, double* out);
+/* applyWindow(input, window, out) (src/xform/fourier.ts:54-67): out[i] = input[i] * window[i] */
+int pdsp_apply_window(pdsp_ctx* ctx, const double* input, const double* window, int64_t n, double* out);
+/* fftShift(input, out) (src/xform/fourier.ts:122-134): out[i] = input[(i + floor(n/2)) % n];
+ * fftShiftComplex (:136-145) is this applied to each plane */
+int pdsp_fft_shift(pdsp_ctx* ctx, const double* input, int64_t n, double* out);
 
 /* ---- spectrum() / spectrumFx / spectrumStream chunk, host buffers -------------------------
  * (src/public/spectrum.ts:107-142, src/effect/index.ts:143-194).  Outputs are in the plan's

@@ -55,6 +55,8 @@ SYMBOLS = {
     "pdsp_fft_inverse": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "pdsp_magnitude": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "pdsp_phase": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pdsp_apply_window": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pdsp_fft_shift": (C.c_int, [_vp, _vp, _i64, _vp]),
     "pdsp_spectrum": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp]),
     "pdsp_spectrum_dev": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp, _vp]),
     "pdsp_spectrum_dev_gather": (C.c_int, [_vp, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp, C.POINTER(_vp), C.c_int, _i64, _vp]),

@@ -107,6 +107,21 @@ PDSP_GLOBAL void k_phase(const double* PDSP_RESTRICT re, const double* PDSP_REST
   for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride)
     out[i] = atan2(im[i], re[i]);
 }
+// applyWindow (src/xform/fourier.ts:54-67) and fftShift (:122-134) on caller arrays
+PDSP_GLOBAL void k_apply_window(const double* PDSP_RESTRICT in, const double* PDSP_RESTRICT w, long long n,
+                                double* PDSP_RESTRICT out) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride) out[i] = in[i] * w[i];
+}
+PDSP_GLOBAL void k_fft_shift(const double* PDSP_RESTRICT in, long long n, double* PDSP_RESTRICT out) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  const long long mid = n / 2;
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride) {
+    long long j = i + mid;
+    if (j >= n) j -= n;
+    out[i] = in[j];
+  }
+}
 // N = 1: X[0] = x[0] * w[0] (createWindow(size 1) = [1]); one thread per frame
 template <typename T>
 PDSP_GLOBAL void k_r2c_n1(const R2CParams p) {
@@ -485,8 +500,10 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     const bool regular = p.vec_ok && d->frame_len >= n && !p.two_sided && (d_cre == nullptr || cfull) &&
                          mode_is_specialised(mode);
     if (regular && pl->precision == PDSP_F64 && d->window != PDSP_WIN_RECT && n >= 4) {
-      const char* off = getenv("PDSP_WINROT");  // tuning switch: PDSP_WINROT=0 keeps the table loads
-      if (!(off && off[0] == '0')) {
+      // Opt-in (PDSP_WINROT=1): measured on B200 it trades 56 L1 wavefronts per frame for 96 DP instructions
+      // and loses ~5% (profiles/r1/README.md), so the window table stays the default.
+      const char* on = getenv("PDSP_WINROT");
+      if (on && on[0] == '1') {
         double coef[3];
         if (plan_winphase(pl, d->window, &p.winphase, coef)) return 1;
         p.win_a0 = coef[0], p.win_a1 = coef[1], p.win_a2 = coef[2];
@@ -1127,8 +1144,10 @@ PDSP_EXPORT int pdsp_fft_inverse(pdsp_plan* pl, const double* in_re, const doubl
   return host_transform(pl, in_re, in_im, PDSP_F64, batch, out_re, out_im, 2);
 }
 
-static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out, bool mag) {
-  if (!c || !re || !im || !out) return fail("null argument");
+// op: 0 magnitude(re, im), 1 phase(re, im), 2 applyWindow(a = input, b = window), 3 fftShift(a)
+static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out, int op) {
+  const bool mag = op == 0;
+  if (!c || !re || (!im && op != 3) || !out) return fail("null argument");
   if (n < 0) return fail("negative length");
   if (set_device(c)) return 1;
   if (n == 0) return 0;
@@ -1140,7 +1159,7 @@ static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int
   if (ensure(&s.d_out, &s.d_out_cap, al, false)) return 1;
   char* din = static_cast<char*>(s.d_in);
   CU(cudaMemcpyAsync(din, re, bytes, cudaMemcpyHostToDevice, s.stream));
-  CU(cudaMemcpyAsync(din + al, im, bytes, cudaMemcpyHostToDevice, s.stream));
+  if (im) CU(cudaMemcpyAsync(din + al, im, bytes, cudaMemcpyHostToDevice, s.stream));
   long long blocks = (n + 255) / 256;
   if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
   const double* d_re = reinterpret_cast<const double*>(din);
@@ -1148,8 +1167,12 @@ static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int
   double* d_o = static_cast<double*>(s.d_out);
   if (mag)
     PDSP_LAUNCH(k_magnitude, (int)blocks, 256, 0, s.stream, d_re, d_im, (long long)n, d_o);
-  else
+  else if (op == 1)
     PDSP_LAUNCH(k_phase, (int)blocks, 256, 0, s.stream, d_re, d_im, (long long)n, d_o);
+  else if (op == 2)
+    PDSP_LAUNCH(k_apply_window, (int)blocks, 256, 0, s.stream, d_re, d_im, (long long)n, d_o);
+  else
+    PDSP_LAUNCH(k_fft_shift, (int)blocks, 256, 0, s.stream, d_re, (long long)n, d_o);
   CU(cudaGetLastError());
   c->launches++;
   CU(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -1157,10 +1180,16 @@ static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int
   return 0;
 }
 PDSP_EXPORT int pdsp_magnitude(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out) {
-  return host_elementwise(c, re, im, n, out, true);
+  return host_elementwise(c, re, im, n, out, 0);
 }
 PDSP_EXPORT int pdsp_phase(pdsp_ctx* c, const double* re, const double* im, int64_t n, double* out) {
-  return host_elementwise(c, re, im, n, out, false);
+  return host_elementwise(c, re, im, n, out, 1);
+}
+PDSP_EXPORT int pdsp_apply_window(pdsp_ctx* c, const double* input, const double* window, int64_t n, double* out) {
+  return host_elementwise(c, input, window, n, out, 2);
+}
+PDSP_EXPORT int pdsp_fft_shift(pdsp_ctx* c, const double* input, int64_t n, double* out) {
+  return host_elementwise(c, input, nullptr, n, out, 3);
 }
 
 PDSP_EXPORT int pdsp_dev_alloc(pdsp_ctx* c, size_t bytes, void** p) {

@@ -1,1 +1,1 @@
-from .spectrum import spectrum, spectrum_batch  # noqa: F401
+from .spectrum import spectrum, spectrum_batch, stft  # noqa: F401

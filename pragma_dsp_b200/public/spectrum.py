@@ -78,3 +78,23 @@ def spectrum(samples, options: dict | None = None, **kw):
     return {"frequencies": r["frequencies"], "amplitude": r["amplitude"][0], "phase": r["phase"][0],
             "peak": {"index": int(pk["index"]), "frequency": float(pk["frequency"]),
                      "amplitude": float(pk["amplitude"]), "phase": float(pk["phase"])}}
+
+
+def stft(signal, *, fftSize: int, hopSize: int, window: str = "hann", sampleRate: float = 1, sides: str = "one",
+         precision="f64", outputs=("amplitude",), raw_magnitude=False, context=None):
+    """STFT / spectrogram (the reference's v0.2 roadmap item, ROADMAP.md:31-45; BASELINE config C3 does it
+    through spectrumStream): frames are overlapping views signal[f*hopSize : f*hopSize + fftSize]; no frame
+    matrix is materialised - the hop is an address stride inside the fused kernel.
+
+    Returns dict(frequencies, times, amplitude (frames x bins), phase, peaks) in the plan precision."""
+    x = _as_samples(signal)
+    if x.ndim != 1:
+        raise ValueError("stft expects a 1-D signal")
+    if hopSize <= 0:
+        raise ValueError(f"hop size must be positive, got {hopSize}")
+    frames = 0 if x.shape[0] < fftSize else (x.shape[0] - fftSize) // hopSize + 1
+    r = spectrum_batch(x, sampleRate=sampleRate, fftSize=fftSize, window=window, sides=sides, frameLen=fftSize,
+                       hop=hopSize, batch=frames, precision=precision, outputs=outputs, raw_magnitude=raw_magnitude,
+                       context=context)
+    r["times"] = np.arange(frames, dtype=np.float64) * (hopSize / float(sampleRate))
+    return r

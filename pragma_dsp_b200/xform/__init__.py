@@ -1,1 +1,2 @@
-from .fourier import FFT, binFrequencies, createWindow, magnitude, phase  # noqa: F401
+from .fourier import (FFT, applyWindow, binFrequencies, createWindow, fftShift, fftShiftComplex, magnitude,  # noqa: F401
+                      phase)

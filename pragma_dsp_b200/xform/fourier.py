@@ -71,6 +71,34 @@ def phase(input: ComplexArray, out: np.ndarray | None = None) -> np.ndarray:
     return _elementwise(lib().pdsp_phase, input, out)
 
 
+def applyWindow(input, window, out: np.ndarray | None = None) -> np.ndarray:
+    """src/xform/fourier.ts:54-67 - elementwise product (the fused spectrum path never materialises it)."""
+    x = np.ascontiguousarray(input, dtype=np.float64)
+    w = np.ascontiguousarray(window, dtype=np.float64)
+    if x.shape[0] != w.shape[0]:
+        raise ValueError("Window length must match input length.")
+    result = out if out is not None else np.empty(x.shape[0], dtype=np.float64)
+    check(lib().pdsp_apply_window(_lib.default_context().h, ptr(x), ptr(w), x.shape[0], ptr(result)))
+    return result
+
+
+def fftShift(input, out: np.ndarray | None = None) -> np.ndarray:
+    """src/xform/fourier.ts:122-134 - rotate by floor(n/2) so DC sits in the middle."""
+    x = np.ascontiguousarray(input, dtype=np.float64)
+    result = out if out is not None else np.empty(x.shape[0], dtype=np.float64)
+    if x.shape[0]:
+        check(lib().pdsp_fft_shift(_lib.default_context().h, ptr(x), x.shape[0], ptr(result)))
+    return result
+
+
+def fftShiftComplex(input: ComplexArray, out: ComplexArray | None = None) -> ComplexArray:
+    """src/xform/fourier.ts:136-145"""
+    result = out if out is not None else createComplexArray(input.real.shape[0])
+    fftShift(input.real, result.real)
+    fftShift(input.imag, result.imag)
+    return result
+
+
 def binFrequencies(size: int, sampleRate: float, sides: FftSides = "one") -> np.ndarray:
     """src/xform/fourier.ts:147-165"""
     if size <= 0:
@@ -84,4 +112,5 @@ def binFrequencies(size: int, sampleRate: float, sides: FftSides = "one") -> np.
     return out
 
 
-__all__ = ["FFT", "createWindow", "magnitude", "phase", "binFrequencies", "WindowType", "FftSides"]
+__all__ = ["FFT", "createWindow", "applyWindow", "magnitude", "phase", "fftShift", "fftShiftComplex", "binFrequencies",
+           "WindowType", "FftSides"]

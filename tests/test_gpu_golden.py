@@ -102,3 +102,22 @@ def test_effect_layer_parity():
         mixed = [frame, frame[:512], frame, frame[:512]]
         res = list(spectrumStream(mixed, {"sampleRate": 48000.0}, service=svc, chunk=2))
         assert [len(r["amplitude"]) for r in res] == [513, 257, 513, 257]
+
+
+def test_apply_window_fftshift_stft_gpu():
+    import oracle
+    from pragma_dsp_b200 import stft
+    from pragma_dsp_b200.xform import applyWindow, createWindow, fftShift
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(4096)
+    w = createWindow("blackman", 4096)
+    assert (applyWindow(x, w) == x * w).all()
+    for n in (1, 2, 7, 8, 1025):
+        v = rng.standard_normal(n)
+        assert (fftShift(v) == oracle.fftShift(v)).all()
+    sig = rng.standard_normal(48000).astype(np.float32)
+    r = stft(sig, fftSize=4096, hopSize=1024, window="hann", sampleRate=48000.0, outputs=("amplitude", "phase", "peak"))
+    frames = (48000 - 4096) // 1024 + 1
+    ref = oracle.spectrum_batch(sig, fftSize=4096, frameLen=4096, hop=1024, batch=frames, sampleRate=48000.0, window="hann")
+    assert r["amplitude"].shape == (frames, 2049) and np.abs(r["amplitude"] - ref["amplitude"]).max() <= 1e-13
+    assert (r["peaks"]["index"] == ref["peaks"]["index"]).all()

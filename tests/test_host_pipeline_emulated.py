@@ -210,3 +210,26 @@ def test_fused_peer_scatter_emulated(emu_api):
     assert np.abs(local["phase"] - ref["peaks"]["phase"]).max() <= 1e-9
     for t_ in tgt:
         assert (t_[offset:offset + batch] == local).all() and (t_[:offset]["index"] == 0).all()
+
+
+def test_apply_window_fftshift_stft_emulated(emu_api):
+    from pragma_dsp_b200 import stft
+    from pragma_dsp_b200.core import ComplexArray
+    from pragma_dsp_b200.xform import applyWindow, createWindow, fftShift, fftShiftComplex
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(1024)
+    w = createWindow("hann", 1024)
+    assert (applyWindow(x, w) == x * w).all()  # src/xform/fourier.ts:54-67
+    with pytest.raises(ValueError, match="Window length must match input length."):
+        applyWindow(x, w[:10])
+    for n in (1, 2, 7, 8):  # src/xform/fourier.ts:122-134, odd and even
+        v = np.arange(n, dtype=np.float64)
+        assert (fftShift(v) == oracle.fftShift(v)).all()
+    c = fftShiftComplex(ComplexArray(np.arange(8.0), -np.arange(8.0)))
+    assert (c.real == np.roll(np.arange(8.0), -4)).all() and (c.imag == -c.real).all()
+    sig = rng.standard_normal(1024 + 7 * 256).astype(np.float32)
+    r = stft(sig, fftSize=1024, hopSize=256, window="hann", sampleRate=48000.0, outputs=("amplitude", "peak"))
+    ref = oracle.spectrum_batch(sig, fftSize=1024, frameLen=1024, hop=256, batch=8, sampleRate=48000.0, window="hann")
+    assert r["amplitude"].shape == (8, 513) and np.abs(r["amplitude"] - ref["amplitude"]).max() <= 1e-13
+    assert (r["peaks"]["index"] == ref["peaks"]["index"]).all() and r["times"][1] == 256 / 48000.0
+    assert stft(sig[:100], fftSize=1024, hopSize=256)["amplitude"].shape == (0, 513)
