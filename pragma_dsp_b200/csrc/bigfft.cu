@@ -12,9 +12,9 @@ static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
   constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * B::C;
   auto kern = bigfft_pass_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C>;
   static int bps[kMaxDevices] = {0};
-  if (p.n_groups <= 0) return cudaSuccess;
+  if (p.n_groups <= 0 || p.n_frames <= 0) return cudaSuccess;
   int grid = 0;
-  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, p.n_groups, &grid);
+  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, p.n_groups * p.n_frames, &grid);
   if (e != cudaSuccess) return e;
   BigPassParams q = p;
   q.tw = lc.pass_twiddles(lc.owner, sizeof(T) == 8, LOG2L, E::RB);

@@ -22,8 +22,10 @@ struct BigPassParams {
   const void* in_im;
   void* out_re;
   void* out_im;
-  long long n_groups;  // CTA work items; group g = g_hi * n_lo + g_lo
+  long long n_groups;  // CTA work items per transform; group g = g_hi * n_lo + g_lo
   long long n_lo;
+  long long n_frames;                  // transforms in this launch (work item = frame * n_groups + g)
+  long long in_frame, out_frame;       // element strides between consecutive transforms
   long long in_hi, in_lo, in_c, in_e;      // element strides of (g_hi, g_lo, sequence c, element e)
   long long out_hi, out_lo, out_c, out_e;  // same for the output index k
   const void* tw;                          // per-pass twiddles of the L-point schedule (set by the launcher)
@@ -61,10 +63,11 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
   T* PDSP_RESTRICT oim = static_cast<T*>(p.out_im);
   const T scale = (T)p.scale;
 
-  for (long long g = simt::bid(); g < p.n_groups; g += simt::nblocks()) {
+  for (long long w = simt::bid(); w < p.n_groups * p.n_frames; w += simt::nblocks()) {
+    const long long fb = w / p.n_groups, g = w % p.n_groups;
     const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
-    const long long in_base = g_hi * p.in_hi + g_lo * p.in_lo;
-    const long long out_base = g_hi * p.out_hi + g_lo * p.out_lo;
+    const long long in_base = fb * p.in_frame + g_hi * p.in_hi + g_lo * p.in_lo;
+    const long long out_base = fb * p.out_frame + g_hi * p.out_hi + g_lo * p.out_lo;
     cx<T> v[P];
     if (p.stage_in) {
       // rows are contiguous in memory: read them with the element index fastest, park in shared memory

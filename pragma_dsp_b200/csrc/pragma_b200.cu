@@ -215,8 +215,9 @@ struct BigPlan {
   void* tw_hi[2] = {nullptr, nullptr};               // two-level inter-pass twiddles of passes 0 and 1
   void* tw_lo[2] = {nullptr, nullptr};
   int log_b[2] = {0, 0};
-  void* work_re = nullptr;  // intermediate planes, N elements each
+  void* work_re = nullptr;  // intermediate planes, work_frames * N elements each
   void* work_im = nullptr;
+  long long work_frames = 0;
 };
 
 struct pdsp_plan {
@@ -578,8 +579,7 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
     if (rc) return 1;
     rest -= lg[j];
   }
-  CU(cudaMalloc(&bp->work_re, es << n));
-  CU(cudaMalloc(&bp->work_im, es << n));
+  (void)es;
   pl->big = bp;
   *out = bp;
   return 0;
@@ -594,11 +594,28 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   const int np = bp->npass;
   long long Ls[3] = {1, 1, 1};
   for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
-  for (long long f = 0; f < batch; ++f) {
-    const char* fre = static_cast<const char*>(d_re) + (size_t)f * N * es;
-    const char* fim = d_im ? static_cast<const char*>(d_im) + (size_t)f * N * es : nullptr;
-    char* gre = static_cast<char*>(d_ore) + (size_t)f * N * es;
-    char* gim = static_cast<char*>(d_oim) + (size_t)f * N * es;
+  // transforms are processed `chunk` at a time (all passes of a chunk share the work planes)
+  long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  {
+    std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
+    if (bp->work_frames < chunk) {
+      CU(cudaStreamSynchronize(st));
+      CU(cudaFree(bp->work_re));
+      CU(cudaFree(bp->work_im));
+      bp->work_re = bp->work_im = nullptr;
+      CU(cudaMalloc(&bp->work_re, es * (size_t)N * (size_t)chunk));
+      CU(cudaMalloc(&bp->work_im, es * (size_t)N * (size_t)chunk));
+      bp->work_frames = chunk;
+    }
+  }
+  for (long long f0 = 0; f0 < batch; f0 += chunk) {
+    const long long nf = batch - f0 < chunk ? batch - f0 : chunk;
+    const char* fre = static_cast<const char*>(d_re) + (size_t)f0 * N * es;
+    const char* fim = d_im ? static_cast<const char*>(d_im) + (size_t)f0 * N * es : nullptr;
+    char* gre = static_cast<char*>(d_ore) + (size_t)f0 * N * es;
+    char* gim = static_cast<char*>(d_oim) + (size_t)f0 * N * es;
     long long O = 1, I = N;
     for (int j = 0; j < np; ++j) {
       const long long L = Ls[j];
@@ -611,6 +628,8 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       p.in_im = j == 0 ? (const void*)fim : bp->work_im;
       p.out_re = last ? (void*)gre : bp->work_re;
       p.out_im = last ? (void*)gim : bp->work_im;
+      p.n_frames = nf;
+      p.in_frame = p.out_frame = N;
       p.swap_in = (j == 0 && inverse) ? 1 : 0;
       p.swap_out = (last && inverse) ? 1 : 0;
       p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
