@@ -117,6 +117,129 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
   }
 }
 
+// TMA-staged form of a non-last pass.  The C x L tile of each plane (C adjacent columns of the view
+// [O*L rows][I cols], row stride I) is fetched by cp.async.bulk.tensor 2-D box loads ({C, <=256 rows} per
+// box) issued by one thread and tracked by an mbarrier; with STAGES = 2 the next work item's tile is in
+// flight while the current one is transformed, with STAGES = 1 (tile + exchange buffers do not both fit)
+// the tile aliases the exchange buffers.  Results are stored with the same coalesced per-thread stores
+// as the plain kernel.  Requires frames to be contiguous (in_frame = N) and the inner index to be the
+// tensor's contiguous dimension - i.e. any pass but the last.
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int STAGES>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
+    bigfft_pass_tma_kernel(const BigPassParams p, const PDSP_GRID_CONSTANT simt::TensorMap2D tm_re,
+                           const PDSP_GRID_CONSTANT simt::TensorMap2D tm_im) {
+  using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
+  constexpr int L = E::M, P = E::P, TF = E::TF;
+  constexpr int SLOT = E::SMEM_ELEMS | 1;
+  constexpr int BOX_ROWS = L < 256 ? L : 256;
+  constexpr int NBOX = L / BOX_ROWS;
+  constexpr size_t PLANE = sizeof(T) * (size_t)L * C;         // one plane of one tile
+  constexpr size_t TILES = 2 * PLANE * STAGES;                // re + im, per stage
+  constexpr size_t EXCH = sizeof(cx<T>) * (size_t)SLOT * C;
+  constexpr size_t EXCH_OFF = STAGES == 2 ? TILES : 0;        // STAGES == 1: the tile aliases the exchange buffers
+  constexpr size_t BAR_OFF = ((STAGES == 2 ? TILES + EXCH : (TILES > EXCH ? TILES : EXCH)) + 15) & ~(size_t)15;
+  const int tid = simt::tid();
+  const int c = tid % C;
+  const int t = tid / C;
+  // 128-byte aligned carve-up of dynamic shared memory (TMA destinations)
+  unsigned char* base = simt::smem();
+  base += (128 - (reinterpret_cast<uintptr_t>(base) & 127)) & 127;
+  cx<T>* sm = reinterpret_cast<cx<T>*>(base + EXCH_OFF) + (size_t)c * SLOT;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + BAR_OFF);
+  T* PDSP_RESTRICT ore = static_cast<T*>(p.out_re);
+  T* PDSP_RESTRICT oim = static_cast<T*>(p.out_im);
+  const T scale = (T)p.scale;
+  const bool has_im = p.in_im != nullptr;
+  const long long total = p.n_groups * p.n_frames;
+  const long long n_hi = p.n_groups / p.n_lo;  // O
+
+  auto issue = [&](long long w, int stage) {  // one thread: arm the barrier and launch the tile's box loads
+    const long long fb = w / p.n_groups, g = w % p.n_groups;
+    const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
+    const int x = (int)(g_lo * C);
+    const int y = (int)((fb * n_hi + g_hi) * L);
+    simt::mbar_expect_tx(&bars[stage], (unsigned)((has_im ? 2 : 1) * PLANE));
+    unsigned char* tile = base + (size_t)stage * 2 * PLANE;
+    for (int j = 0; j < NBOX; ++j) {
+      simt::tma_load_2d(tile + (size_t)j * BOX_ROWS * C * sizeof(T), &tm_re, x, y + j * BOX_ROWS, &bars[stage]);
+      if (has_im)
+        simt::tma_load_2d(tile + PLANE + (size_t)j * BOX_ROWS * C * sizeof(T), &tm_im, x, y + j * BOX_ROWS, &bars[stage]);
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) simt::mbar_init(&bars[s], 1);
+  }
+  simt::sync_block();
+  unsigned phase[2] = {0u, 0u};
+  if (STAGES == 2 && tid == 0 && simt::bid() < total) issue(simt::bid(), 0);
+
+  long long it = 0;
+  for (long long w = simt::bid(); w < total; w += simt::nblocks(), ++it) {
+    const int stage = STAGES == 2 ? (int)(it & 1) : 0;
+    if (STAGES == 2) {
+      // prefetch the next tile into the other stage (its previous contents were consumed one iteration ago)
+      if (tid == 0 && w + simt::nblocks() < total) issue(w + simt::nblocks(), stage ^ 1);
+    } else {
+      // the tile shares memory with the exchange buffers of the previous item: order those generic-proxy
+      // accesses before the async-proxy writes of the bulk copy
+      simt::fence_proxy_async();
+      simt::sync_block();
+      if (tid == 0) issue(w, 0);
+    }
+    simt::mbar_wait(&bars[stage], phase[stage]);
+    phase[stage] ^= 1u;
+
+    const T* tre = reinterpret_cast<const T*>(base + (size_t)stage * 2 * PLANE);
+    const T* tim = reinterpret_cast<const T*>(base + (size_t)stage * 2 * PLANE + PLANE);
+    cx<T> v[P];
+    static_for<0, P>([&](auto qi) {
+      constexpr int q = decltype(qi)::value;
+      const int e = t + TF * q;
+      const T re = tre[e * C + c];
+      const T im = has_im ? tim[e * C + c] : (T)0;
+      v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+    });
+    simt::sync_block();  // tile consumed: it may be refilled (STAGES 2) / overwritten by the exchanges (STAGES 1)
+
+    E::template fft<true>(v, t, sm, static_cast<const cx<T>*>(p.tw), 0, 1);
+
+    const long long fb = w / p.n_groups, g = w % p.n_groups;
+    const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
+    if (p.tw_hi != nullptr) {
+      const cx<T>* PDSP_RESTRICT hi = static_cast<const cx<T>*>(p.tw_hi);
+      const cx<T>* PDSP_RESTRICT lo = static_cast<const cx<T>*>(p.tw_lo);
+      const long long i = g_lo * C + c;
+      cx<T> wv = big_twiddle(hi, lo, (long long)t * i, p.log_b);
+      const cx<T> step = big_twiddle(hi, lo, (long long)TF * i, p.log_b);
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        v[q] = cmul(v[q], wv);
+        if constexpr (q + 1 < P) wv = cmul(wv, step);
+      });
+    }
+    const long long out_base = fb * p.out_frame + g_hi * p.out_hi + g_lo * p.out_lo;
+    static_for<0, P>([&](auto qi) {
+      constexpr int q = decltype(qi)::value;
+      const long long a = out_base + c * p.out_c + (long long)(t + TF * q) * p.out_e;
+      const T x = v[q].x * scale, y = v[q].y * scale;
+      ore[a] = p.swap_out ? y : x;
+      oim[a] = p.swap_out ? x : y;
+    });
+  }
+}
+
+// shared-memory plan of the TMA kernel for (T, LOG2L, C): two stages when both tiles and the exchange
+// buffers fit in 200 KB, otherwise one aliased stage
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C>
+struct BigTmaSmem {
+  using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
+  static constexpr size_t PLANE = sizeof(T) * (size_t)E::M * C;
+  static constexpr size_t EXCH = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * C;
+  static constexpr int STAGES = (4 * PLANE + EXCH + 512 <= 200 * 1024) ? 2 : 1;
+  static constexpr size_t BYTES = (STAGES == 2 ? 4 * PLANE + EXCH : (2 * PLANE > EXCH ? 2 * PLANE : EXCH)) + 16 + 32 + 128;
+};
+
 // Pass configuration for a sub-transform length 2^LOG2L.
 template <typename T, int LOG2L>
 struct BigCfg {

@@ -41,7 +41,10 @@ PDSP_GROUPS(X)
 
 // multi-pass large-N path (bigfft.cu)
 int big_pass_c(int log2l);
+void big_pass_tma_box(int log2l, int* cols, int* rows);
 cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const LaunchCtx& lc);
+cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, const simt::TensorMap2D& tm_re,
+                                const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
 
 // tuning variants (inst_var.cu), one symbol per (type, variant); not built into the emulated test library
 #ifdef PDSP_EMU
@@ -539,6 +542,44 @@ static int upload_big_twiddles(int log_nt, int log_b, void** d_hi, void** d_lo) 
   return 0;
 }
 
+// 2-D tensor map over one plane viewed as [rows][cols] (cols contiguous) with a {box_cols, box_rows} box.
+static int make_tensor_map(simt::TensorMap2D* tm, const void* base, bool f64, long long cols, long long rows,
+                           int box_cols, int box_rows) {
+#ifdef PDSP_EMU
+  tm->base = base;
+  tm->dim0 = cols;
+  tm->dim1 = rows;
+  tm->esize = f64 ? 8 : 4;
+  tm->stride1_bytes = cols * tm->esize;
+  tm->box0 = box_cols;
+  tm->box1 = box_rows;
+  return 0;
+#else
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t es = f64 ? 8 : 4;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(tm, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+#endif
+}
+
 // Builds (once) the pass structure of a large transform.  *out stays null when PDSP_BIG_FACTORS is
 // set but does not describe this size (the in-CTA kernel is used instead).
 static int big_plan(pdsp_plan* pl, BigPlan** out) {
@@ -670,7 +711,20 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
         p.out_e = Ls[0] * Ls[1];
         p.stage_in = 1;
       }
-      cudaError_t e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
+      cudaError_t e;
+      const char* tma_env = getenv("PDSP_BIG_TMA");
+      if (!last && !(tma_env && tma_env[0] == '0')) {
+        // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
+        simt::TensorMap2D tm_re, tm_im;
+        int bc = 0, br = 0;
+        big_pass_tma_box(bp->lg[j], &bc, &br);
+        const bool f64p = pl->precision == PDSP_F64;
+        if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+        if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+        e = launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
+      } else {
+        e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
+      }
       if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d): %s", j, pl->log2n, cudaGetErrorString(e));
       c->launches++;
       O *= L;

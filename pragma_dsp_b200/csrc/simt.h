@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
+#include <cuda.h>  // CUtensorMap (type only; the driver entry point is resolved at run time)
 
 #define PDSP_DEVICE __device__ __forceinline__
 #define PDSP_DEVICE_NOINLINE static __device__ __noinline__
@@ -19,6 +20,7 @@
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL _Pragma("unroll")
 #define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) kernel<<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__)
+#define PDSP_GRID_CONSTANT __grid_constant__
 
 namespace simt {
 PDSP_DEVICE int tid() { return (int)threadIdx.x; }
@@ -40,6 +42,40 @@ PDSP_DEVICE T shfl_xor(T v, int mask, int width) {
   return __shfl_xor_sync(0xffffffffu, v, mask, width);
 }
 PDSP_DEVICE bool any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier, the sm_90+/sm_100 bulk-copy path (SASS: UTMALDG, SYNCS)
+typedef CUtensorMap TensorMap2D;  // encoded on the host with cuTensorMapEncodeTiled, passed __grid_constant__
+PDSP_DEVICE unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PDSP_DEVICE void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PDSP_DEVICE void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tile load: box (tensor map's boxDim) at element coordinates (x = inner, y = outer) -> dense smem
+PDSP_DEVICE void tma_load_2d(void* smem_dst, const TensorMap2D* map, int x, int y, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+PDSP_DEVICE void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// order generic-proxy accesses to shared memory before later async-proxy (TMA) accesses to the same bytes
+PDSP_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 PDSP_DEVICE unsigned char* smem() {
   extern __shared__ __align__(16) unsigned char pdsp_smem_[];
   return pdsp_smem_;
@@ -64,6 +100,7 @@ PDSP_DEVICE T ldg(const T* p) {
 #define PDSP_KERNEL_LIMITS(threads, regs)
 #define PDSP_RESTRICT __restrict__
 #define PDSP_UNROLL
+#define PDSP_GRID_CONSTANT
 #define PDSP_LAUNCH(kernel, grid, threads, smem, stream, ...) \
   simt::emu_launch((grid), (threads), (smem), [=] { kernel(__VA_ARGS__); })
 
@@ -100,6 +137,36 @@ inline T shfl_xor(T v, int mask, int width) {
   emu_shfl(&v, &r, (int)sizeof(T), mask, width, true);
   return r;
 }
+// ---- emulated TMA: the "tensor map" is a plain description; a load copies the box synchronously and
+// completes the barrier's transaction count; waits spin on the phase bit like the hardware's try_wait.
+struct TensorMap2D {
+  const void* base;
+  long long dim0, dim1;       // extent in elements (inner, outer)
+  long long stride1_bytes;    // byte stride between consecutive outer indices
+  int box0, box1, esize;
+};
+void emu_mbar_init(unsigned long long* bar);
+void emu_mbar_expect_tx(unsigned long long* bar, unsigned bytes);
+void emu_mbar_complete_tx(unsigned long long* bar, unsigned bytes);
+void emu_mbar_wait(unsigned long long* bar, unsigned parity);
+inline void mbar_init(unsigned long long* bar, int) { emu_mbar_init(bar); }
+inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu_mbar_expect_tx(bar, bytes); }
+inline void tma_load_2d(void* smem_dst, const TensorMap2D* m, int x, int y, unsigned long long* bar) {
+  char* dst = static_cast<char*>(smem_dst);
+  for (int r = 0; r < m->box1; ++r) {
+    for (int c = 0; c < m->box0; ++c) {
+      const long long gx = x + c, gy = y + r;
+      char* d = dst + ((size_t)r * m->box0 + c) * m->esize;
+      if (gx < m->dim0 && gy < m->dim1)
+        memcpy(d, static_cast<const char*>(m->base) + gy * m->stride1_bytes + gx * m->esize, (size_t)m->esize);
+      else
+        memset(d, 0, (size_t)m->esize);  // out-of-bounds elements read as zero
+    }
+  }
+  emu_mbar_complete_tx(bar, (unsigned)(m->box0 * m->box1 * m->esize));
+}
+inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu_mbar_wait(bar, parity); }
+inline void fence_proxy_async() {}
 inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over the warp's lanes
   int acc = pred ? 1 : 0;
   for (int m = 16; m >= 1; m >>= 1) acc |= shfl_xor(acc, m, 32);

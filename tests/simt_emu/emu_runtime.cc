@@ -72,6 +72,42 @@ void emu_shfl(const void* in, void* out, int bytes, int src_lane, int width, boo
   emu_sync_warp();
 }
 
+// mbarrier emulation: the 64-bit word in shared memory holds {phase bit 63, pending tx bytes 0..31, armed bit 32}.
+// expect_tx arms the current phase with a byte count, complete_tx retires bytes and flips the phase at zero.
+static std::mutex g_mbar_mu;
+static std::condition_variable g_mbar_cv;
+void emu_mbar_init(unsigned long long* bar) {
+  std::lock_guard<std::mutex> lk(g_mbar_mu);
+  *bar = 0;
+}
+void emu_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  std::lock_guard<std::mutex> lk(g_mbar_mu);
+  const unsigned long long phase = *bar >> 63;
+  const long long pending = (long long)(int)(*bar & 0xffffffffull) + (long long)bytes;
+  if (pending == 0) {
+    *bar = (phase ^ 1ull) << 63;  // transfers finished before the arrive: phase completes now
+    g_mbar_cv.notify_all();
+  } else {
+    *bar = (phase << 63) | (1ull << 32) | (unsigned long long)(unsigned)(int)pending;
+  }
+}
+void emu_mbar_complete_tx(unsigned long long* bar, unsigned bytes) {
+  std::lock_guard<std::mutex> lk(g_mbar_mu);
+  const unsigned long long phase = *bar >> 63;
+  const bool armed = (*bar >> 32) & 1ull;
+  const long long pending = (long long)(int)(*bar & 0xffffffffull) - (long long)bytes;
+  if (armed && pending == 0) {
+    *bar = (phase ^ 1ull) << 63;
+    g_mbar_cv.notify_all();
+  } else {
+    *bar = (phase << 63) | ((armed ? 1ull : 0ull) << 32) | (unsigned long long)(unsigned)(int)pending;
+  }
+}
+void emu_mbar_wait(unsigned long long* bar, unsigned parity) {
+  std::unique_lock<std::mutex> lk(g_mbar_mu);
+  g_mbar_cv.wait(lk, [&] { return (unsigned)(*bar >> 63) != (parity & 1u); });
+}
+
 void emu_launch(int nblocks, int nthreads, size_t smem_bytes, const std::function<void()>& body) {
   ++g_launches;
   for (int bid = 0; bid < nblocks; ++bid) {
