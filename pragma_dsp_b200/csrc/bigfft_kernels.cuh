@@ -229,14 +229,15 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
   }
 }
 
-// shared-memory plan of the TMA kernel for (T, LOG2L, C): two stages when both tiles and the exchange
-// buffers fit in 200 KB, otherwise one aliased stage
+// shared-memory plan of the TMA kernel for (T, LOG2L, C)
 template <typename T, int LOG2L, int LOG2P, int MAXRB, int C>
 struct BigTmaSmem {
   using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
   static constexpr size_t PLANE = sizeof(T) * (size_t)E::M * C;
   static constexpr size_t EXCH = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * C;
-  static constexpr int STAGES = (4 * PLANE + EXCH + 512 <= 200 * 1024) ? 2 : 1;
+  // two stages only while two CTAs still fit an SM (more resident warps beat a deeper pipeline here:
+  // profiles/r1/README.md), otherwise one stage aliased onto the exchange buffers
+  static constexpr int STAGES = (4 * PLANE + EXCH + 512 <= 100 * 1024) ? 2 : 1;
   static constexpr size_t BYTES = (STAGES == 2 ? 4 * PLANE + EXCH : (2 * PLANE > EXCH ? 2 * PLANE : EXCH)) + 16 + 32 + 128;
 };
 
