@@ -65,7 +65,13 @@ cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, con
 }
 
 int big_pass_c(int log2l) {
-  return log2l == 10 ? BigCfg<double, 10>::C : BigCfg<double, 9>::C;
+  switch (log2l) {
+    case 6: return BigCfg<double, 6>::C;
+    case 7: return BigCfg<double, 7>::C;
+    case 8: return BigCfg<double, 8>::C;
+    case 9: return BigCfg<double, 9>::C;
+    default: return BigCfg<double, 10>::C;
+  }
 }
 
 cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const LaunchCtx& lc) {

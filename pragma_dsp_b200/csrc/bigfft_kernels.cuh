@@ -244,11 +244,13 @@ struct BigTmaSmem {
 // Pass configuration for a sub-transform length 2^LOG2L.
 template <typename T, int LOG2L>
 struct BigCfg {
-  static constexpr int LOG2P = LOG2L >= 9 ? 4 : 3;
-  static constexpr int MAXRB = 3;
+  static constexpr int LOG2P = LOG2L >= 8 ? 4 : 3;
+  static constexpr int MAXRB = LOG2P == 4 ? 4 : 3;
   static constexpr int TF = (1 << LOG2L) >> LOG2P;
-  // sequences per CTA: 16 (128-byte segments of doubles); 8 for L = 1024 (512 threads, <= 148 KB smem)
-  static constexpr int C = LOG2L == 10 ? 8 : 16;
+  // sequences per CTA = contiguous elements per row of the strided tile: as many as 512 threads and
+  // 148 KB of exchange buffers allow (32 -> 256-byte rows of doubles; DRAM efficiency of the column
+  // gather grows with the row length, profiles/r1/README.md)
+  static constexpr int C = LOG2L == 10 ? 8 : (LOG2L == 9 ? 16 : 32);
 };
 constexpr int kBigMinLog2L = 6, kBigMaxLog2L = 10;
 
