@@ -5,7 +5,7 @@ namespace pdsp {
 
 constexpr int kMaxLog2M = 13;      // largest in-CTA complex length 8192 (real frames up to 16384)
 constexpr int kMinSpecLog2M = 5;   // sizes below this only get the generic (runtime-flag) kernel
-constexpr int kNumVariants = 14;   // tuning variants compiled for kVariantLog2M (see inst_var.cu)
+constexpr int kNumVariants = 18;   // tuning variants compiled for kVariantLog2M (see inst_var.cu)
 constexpr int kVariantLog2M = 9;   // N = 1024, the headline size
 
 // Points per thread / radix / CTA size / occupancy target for a complex length 2^LOG2M.
@@ -51,6 +51,10 @@ PDSP_VARIANT(10, 4, 4, 32, 1, 1, 112, 80)   // same, hard caps 112 / 80 register
 PDSP_VARIANT(11, 4, 3, 32, 18, 24, 0, 0)    // 8 x 8 x 8, single-warp CTAs
 PDSP_VARIANT(12, 4, 4, 32, 1, 1, 120, 88)   // 16 x 16 x 2, hard caps 120 / 88 registers
 PDSP_VARIANT(13, 4, 4, 32, 16, 21, 0, 0)    // 16 x 16 x 2, single-warp CTAs at the baseline occupancy
+PDSP_VARIANT(14, 5, 5, 32, 8, 20, 0, 0)     // fp32 default mapping (32 x 16) at 20 warps/SM (96 regs)
+PDSP_VARIANT(15, 5, 5, 32, 8, 24, 0, 0)     // ... 24 warps/SM (80 regs)
+PDSP_VARIANT(16, 5, 5, 64, 4, 10, 0, 0)     // ... two-warp CTAs, 20 warps/SM
+PDSP_VARIANT(17, 5, 5, 32, 8, 1, 0, 112)    // ... hard cap 112 registers (18 warps/SM)
 #undef PDSP_VARIANT
 
 }  // namespace pdsp

@@ -50,7 +50,7 @@ cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, con
 #ifdef PDSP_EMU
 #define PDSP_VARS(X)
 #else
-#define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+#define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
 #endif
 #define X(v)                                                                           \
   cudaError_t launch_r2c_var_f64_##v(int, const R2CParams&, const LaunchCtx&);         \

@@ -84,7 +84,7 @@ extern "C" int emu_r2c_var(int f64, int var, const R2CParams* p, int nblocks, in
 #define X(V) \
   case V:    \
     return f64 ? run_var<double, V>(*p, nblocks, mode) : run_var<float, V>(*p, nblocks, mode);
-    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
 #undef X
   }
   return -1;
@@ -106,7 +106,7 @@ extern "C" int emu_cfg(int f64, int log2m, int var, int* out) {
   case V:    \
     f64 ? cfg_of<double, kVariantLog2M, V>(out) : cfg_of<float, kVariantLog2M, V>(out); \
     return 0;
-      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+      X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
 #undef X
     }
     return -1;
