@@ -296,3 +296,17 @@ def test_fused_peer_scatter_single_gpu(ctx):
         rec = t_.cpu().numpy().view(PEAK_F32).reshape(-1)
         assert (rec[offset:offset + batch] == loc).all()
         assert (rec[:offset]["index"] == 0).all() and (rec[offset + batch:]["index"] == 0).all()
+
+
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_large_fft_tma_and_plain_paths_agree(ctx, monkeypatch, tma):
+    """K2's strided passes have two implementations: TMA tile loads (cp.async.bulk.tensor + mbarrier,
+    the default) and per-thread coalesced loads (PDSP_BIG_TMA=0).  Both must give the same transform."""
+    from pragma_dsp_b200.core import ComplexArray, Radix2Fft
+    monkeypatch.setenv("PDSP_BIG_TMA", tma)
+    for log2n in (14, 18, 22):
+        n = 1 << log2n
+        rng = np.random.default_rng(log2n)
+        re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
+        assert rel_l2(out.real + 1j * out.imag, np.fft.fft(re + 1j * im)) <= 1e-12 * log2n
