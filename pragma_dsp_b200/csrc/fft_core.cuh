@@ -34,6 +34,33 @@ PDSP_DEVICE cx<T> cmul(cx<T> a, cx<T> w) {
   return cx<T>{a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x};
 }
 
+// elementwise a * s + b and a * s (per component, not complex products)
+template <typename T>
+PDSP_DEVICE cx<T> ew_fma(cx<T> a, cx<T> s, cx<T> b) {
+  return cx<T>{a.x * s.x + b.x, a.y * s.y + b.y};
+}
+template <typename T>
+PDSP_DEVICE cx<T> ew_mul(cx<T> a, cx<T> s) {
+  return cx<T>{a.x * s.x, a.y * s.y};
+}
+
+#if defined(__CUDACC__) && !defined(PDSP_EMU)
+// fp32 on sm_100a: a complex number is one 64-bit register pair, and Blackwell's packed fp32 pipe
+// instructions (add/mul/fma.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, with scalar-broadcast and half-swap
+// operand modes) do both components at once: a complex add is 1 instruction instead of 2, a complex
+// multiply 2 instead of 4.  The fp32 kernels are issue-bound (profiles/r1), so this is their main lever.
+PDSP_DEVICE float2 as_f2(cx<float> a) { return make_float2(a.x, a.y); }
+PDSP_DEVICE cx<float> as_cx(float2 a) { return cx<float>{a.x, a.y}; }
+PDSP_DEVICE cx<float> cadd(cx<float> a, cx<float> b) { return as_cx(__fadd2_rn(as_f2(a), as_f2(b))); }
+PDSP_DEVICE cx<float> csub(cx<float> a, cx<float> b) { return as_cx(__fadd2_rn(as_f2(a), make_float2(-b.x, -b.y))); }
+PDSP_DEVICE cx<float> cmul(cx<float> a, cx<float> w) {
+  // (a.x*w.x - a.y*w.y, a.x*w.y + a.y*w.x) = a.x * (w.x, w.y) + a.y * (-w.y, w.x)
+  return as_cx(__ffma2_rn(make_float2(a.x, a.x), as_f2(w), __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x))));
+}
+PDSP_DEVICE cx<float> ew_fma(cx<float> a, cx<float> s, cx<float> b) { return as_cx(__ffma2_rn(as_f2(a), as_f2(s), as_f2(b))); }
+PDSP_DEVICE cx<float> ew_mul(cx<float> a, cx<float> s) { return as_cx(__fmul2_rn(as_f2(a), as_f2(s))); }
+#endif
+
 // read-only (non-coherent) load of a table entry
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
 PDSP_DEVICE cx<double> ldg_cx(const cx<double>* p) {
@@ -120,6 +147,11 @@ PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
     return d;
   } else if constexpr (K == 8) {  // -i
     return cx<T>{d.y, -d.x};
+  } else if constexpr (sizeof(T) == 4) {
+    // fp32: every non-trivial constant twiddle is one packed multiply + one packed fma (cmul overload)
+    constexpr T wr = (T)w32_re(K);
+    constexpr T wi = (T)w32_im(K);
+    return cmul(d, cx<T>{wr, wi});
   } else if constexpr (K == 4) {  // (1-i)/sqrt2
     constexpr T c = (T)cos16(4);
     return cx<T>{(d.x + d.y) * c, (d.y - d.x) * c};

@@ -238,8 +238,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         static_for<0, P>([&](auto qi) {
           constexpr int q = decltype(qi)::value;
           const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
-          v[q].x *= w.x;
-          v[q].y *= w.y;
+          v[q] = ew_mul(v[q], w);
         });
       }
     } else {
@@ -398,16 +397,16 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
             zp = (t == 0) ? v[(P - q) % P] : got;
           }
           const cx<T> a = v[q];
-          const cx<T> sum{a.x + zp.x, a.y - zp.y};  // A + conj(Zp)
-          const cx<T> dif{a.x - zp.x, a.y + zp.y};  // A - conj(Zp)
-          cx<T> w;                                   // (wi/2, -wr/2): W_N^k * (-i/2)
+          const cx<T> sum = ew_fma(zp, cx<T>{(T)1, (T)-1}, a);  // A + conj(Zp)
+          const cx<T> dif = ew_fma(zp, cx<T>{(T)-1, (T)1}, a);  // A - conj(Zp)
+          cx<T> w;                                               // (wi/2, -wr/2): W_N^k * (-i/2)
           if constexpr (DERIVE)
             w = mul_w32<(q * 16 / P) % 16>(post0);
           else
             w = ldg_cx(post + k);
           const cx<T> tt = cmul(dif, w);
-          cx<T> xa{(T)0.5 * sum.x + tt.x, (T)0.5 * sum.y + tt.y};     // X[k]
-          cx<T> xb{(T)0.5 * sum.x - tt.x, -((T)0.5 * sum.y - tt.y)};  // X[M-k] = conj(E - W*O)
+          cx<T> xa = ew_fma(sum, cx<T>{(T)0.5, (T)0.5}, tt);                                     // X[k]
+          cx<T> xb = ew_fma(sum, cx<T>{(T)0.5, (T)-0.5}, cx<T>{-tt.x, tt.y});                    // X[M-k] = conj(E - W*O)
           if constexpr (q == 0) {
             // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
             // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
