@@ -108,7 +108,7 @@ PDSP_GLOBAL void k_phase(const double* PDSP_RESTRICT re, const double* PDSP_REST
                          double* PDSP_RESTRICT out) {
   const long long stride = (long long)simt::nblocks() * simt::nthreads();
   for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride)
-    out[i] = atan2(im[i], re[i]);
+    out[i] = fast_atan2(im[i], re[i]);
 }
 // applyWindow (src/xform/fourier.ts:54-67) and fftShift (:122-134) on caller arrays
 PDSP_GLOBAL void k_apply_window(const double* PDSP_RESTRICT in, const double* PDSP_RESTRICT w, long long n,

@@ -310,3 +310,29 @@ def test_large_fft_tma_and_plain_paths_agree(ctx, monkeypatch, tma):
         re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
         out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
         assert rel_l2(out.real + 1j * out.imag, np.fft.fft(re + 1j * im)) <= 1e-12 * log2n
+
+
+def test_fast_atan2_accuracy_and_special_values(ctx):
+    """The phase rows use a hand-written atan2 (one division + odd minimax polynomial).  Check the device
+    implementation through phase() against libm over all quadrants, ratios near the octant folds, huge /
+    tiny magnitudes (libdevice escape path) and the signed-zero cases Math.atan2 defines."""
+    from pragma_dsp_b200.core import ComplexArray
+    from pragma_dsp_b200.xform import phase
+    rng = np.random.default_rng(2)
+    n = 1 << 18
+    re = rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 6, n)
+    im = rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 6, n)
+    # ratios around tan(pi/8), 1 and the axes
+    k = 4096
+    ang = np.concatenate([np.linspace(-np.pi, np.pi, k), np.pi / 8 + np.linspace(-1e-9, 1e-9, k), np.pi / 4 + np.linspace(-1e-9, 1e-9, k)])
+    re[:ang.size], im[:ang.size] = np.cos(ang) * 3.7, np.sin(ang) * 3.7
+    re[20000:20004], im[20000:20004] = [1e300, -1e300, 1e-300, -1e-300], [1e300, 1e-300, 1e-300, 1e300]
+    got = phase(ComplexArray(re, im))
+    ref = np.arctan2(im, re)
+    err = np.abs(got - ref)
+    assert err.max() <= 4 * np.finfo(np.float64).eps * np.pi, err.max()
+    sp_re = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, 0.0, -2.0, 2.0])
+    sp_im = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, 1.0, -1.0, -0.0, -0.0])
+    got = phase(ComplexArray(sp_re, sp_im))
+    ref = np.arctan2(sp_im, sp_re)
+    assert (got == ref).all() and (np.signbit(got) == np.signbit(ref)).all(), (got, ref)
