@@ -102,10 +102,9 @@ PDSP_DEVICE double fast_atan2(double y, double x) {
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-  r = fma(fma(-den, r, 1.0), r, r);
-  r = fma(fma(-den, r, 1.0), r, r);
+  r = fma(fma(-den, r, 1.0), r, r);  // 2^-23 -> 2^-46
   t = num * r;
-  t = fma(fma(-den, t, num), r, t);
+  t = fma(fma(-den, t, num), r, t);  // residual correction: ~2^-90, i.e. correctly rounded but for the last bit
 #else
   t = num / den;
 #endif
