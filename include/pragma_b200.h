@@ -136,6 +136,13 @@ int pdsp_fft_forward_real_dev(pdsp_plan* plan, const void* d_in, int in_dtype, i
 int pdsp_fft_complex_dev(pdsp_plan* plan, const void* d_in_re, const void* d_in_im, int64_t batch, void* d_out_re,
                          void* d_out_im, int inverse, void* stream);
 
+/* "next" row: frequency-domain product on device-resident planar arrays, so that
+ * forward -> multiply -> inverse (FFT convolution, test/fluent/chain.test.ts:287-316) needs no host round
+ * trip: out = a * (conj_b ? conj(b) : b) * scale (src/math/complex.ts:87-105 mul, conj, scale fused). */
+int pdsp_complex_mul_dev(pdsp_ctx* ctx, int precision, const void* d_a_re, const void* d_a_im, const void* d_b_re,
+                         const void* d_b_im, int conj_b, double scale, int64_t n, void* d_out_re, void* d_out_im,
+                         void* stream);
+
 /* ---- device / pinned-host buffers owned by the library (what createComplexArray hands out
  *      behind the addon: src/core/fft.ts:6-14) ------------------------------------------------ */
 int pdsp_dev_alloc(pdsp_ctx* ctx, size_t bytes, void** d_ptr);

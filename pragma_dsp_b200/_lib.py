@@ -65,6 +65,7 @@ SYMBOLS = {
     "pdsp_ipc_close": (C.c_int, [_vp, _vp]),
     "pdsp_fft_forward_real_dev": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, C.c_int, _vp]),
     "pdsp_fft_complex_dev": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_int, _vp]),
+    "pdsp_complex_mul_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_double, _i64, _vp, _vp, _vp]),
     "pdsp_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "pdsp_dev_free": (C.c_int, [_vp, _vp]),
     "pdsp_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),

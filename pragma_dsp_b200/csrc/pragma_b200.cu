@@ -125,6 +125,19 @@ PDSP_GLOBAL void k_fft_shift(const double* PDSP_RESTRICT in, long long n, double
     out[i] = in[j];
   }
 }
+// out = a * (conj?) b * scale on planar arrays (src/math/complex.ts:87-105 mul / conj / scale, fused)
+template <typename T>
+PDSP_GLOBAL void k_complex_mul(const T* PDSP_RESTRICT are, const T* PDSP_RESTRICT aim, const T* PDSP_RESTRICT bre,
+                               const T* PDSP_RESTRICT bim, int conj_b, T scale, long long n, T* PDSP_RESTRICT ore,
+                               T* PDSP_RESTRICT oim) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < n; i += stride) {
+    const T ar = are[i], ai = aim[i], br = bre[i];
+    const T bi = conj_b ? -bim[i] : bim[i];
+    ore[i] = (ar * br - ai * bi) * scale;
+    oim[i] = (ar * bi + ai * br) * scale;
+  }
+}
 // N = 1: X[0] = x[0] * w[0] (createWindow(size 1) = [1]); one thread per frame
 template <typename T>
 PDSP_GLOBAL void k_r2c_n1(const R2CParams p) {
@@ -1263,6 +1276,28 @@ PDSP_EXPORT int pdsp_apply_window(pdsp_ctx* c, const double* input, const double
 }
 PDSP_EXPORT int pdsp_fft_shift(pdsp_ctx* c, const double* input, int64_t n, double* out) {
   return host_elementwise(c, input, nullptr, n, out, 3);
+}
+
+PDSP_EXPORT int pdsp_complex_mul_dev(pdsp_ctx* c, int precision, const void* a_re, const void* a_im, const void* b_re,
+                                     const void* b_im, int conj_b, double scale, int64_t n, void* out_re, void* out_im,
+                                     void* stream) {
+  if (!c || !a_re || !a_im || !b_re || !b_im || !out_re || !out_im) return fail("null argument");
+  if (precision != PDSP_F32 && precision != PDSP_F64) return fail("unknown precision %d", precision);
+  if (n < 0) return fail("negative length");
+  if (set_device(c)) return 1;
+  if (n == 0) return 0;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+  if (precision == PDSP_F64)
+    PDSP_LAUNCH(k_complex_mul<double>, (int)blocks, 256, 0, st, (const double*)a_re, (const double*)a_im,
+                (const double*)b_re, (const double*)b_im, conj_b, scale, (long long)n, (double*)out_re, (double*)out_im);
+  else
+    PDSP_LAUNCH(k_complex_mul<float>, (int)blocks, 256, 0, st, (const float*)a_re, (const float*)a_im, (const float*)b_re,
+                (const float*)b_im, conj_b, (float)scale, (long long)n, (float*)out_re, (float*)out_im);
+  CU(cudaGetLastError());
+  c->launches++;
+  return 0;
 }
 
 PDSP_EXPORT int pdsp_dev_alloc(pdsp_ctx* c, size_t bytes, void** p) {

@@ -336,3 +336,33 @@ def test_fast_atan2_accuracy_and_special_values(ctx):
     got = phase(ComplexArray(sp_re, sp_im))
     ref = np.arctan2(sp_im, sp_re)
     assert (got == ref).all() and (np.signbit(got) == np.signbit(ref)).all(), (got, ref)
+
+
+def test_device_resident_fft_convolution(ctx):
+    """forward -> frequency-domain product -> inverse without leaving the device
+    (the fluent layer's convolution, test/fluent/chain.test.ts:287-316, at N = 4096 x 64 frames)."""
+    import torch
+    from pragma_dsp_b200._lib import F64, check, lib
+    L = lib()
+    n, batch = 4096, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((batch, n), generator=g, device="cuda", dtype=torch.float64)
+    b = torch.randn((batch, n), generator=g, device="cuda", dtype=torch.float64)
+    plan = ctx.plan(n, F64)
+    st = torch.cuda.Stream()
+    s = C.c_void_p(st.cuda_stream)
+    vp = lambda t_: C.c_void_p(t_.data_ptr())  # noqa: E731
+    bufs = [torch.empty((batch, n), dtype=torch.float64, device="cuda") for _ in range(8)]
+    are, aim, bre, bim, pre, pim, ore, oim = bufs
+    check(L.pdsp_fft_forward_real_dev(plan, vp(a), F64, batch, vp(are), vp(aim), 1, s))
+    check(L.pdsp_fft_forward_real_dev(plan, vp(b), F64, batch, vp(bre), vp(bim), 1, s))
+    check(L.pdsp_complex_mul_dev(ctx.h, F64, vp(are), vp(aim), vp(bre), vp(bim), 0, 1.0, batch * n, vp(pre), vp(pim), s))
+    check(L.pdsp_fft_complex_dev(plan, vp(pre), vp(pim), batch, vp(ore), vp(oim), 1, s))
+    st.synchronize()
+    ref = np.fft.ifft(np.fft.fft(a.cpu().numpy(), axis=1) * np.fft.fft(b.cpu().numpy(), axis=1), axis=1)
+    assert np.abs(ore.cpu().numpy() - ref.real).max() <= 1e-10 and np.abs(oim.cpu().numpy()).max() <= 1e-10
+    # correlation: conj on the second operand, scale folded in
+    check(L.pdsp_complex_mul_dev(ctx.h, F64, vp(are), vp(aim), vp(bre), vp(bim), 1, 0.5, batch * n, vp(pre), vp(pim), s))
+    st.synchronize()
+    refp = 0.5 * np.fft.fft(a.cpu().numpy(), axis=1) * np.conj(np.fft.fft(b.cpu().numpy(), axis=1))
+    assert np.abs(pre.cpu().numpy() - refp.real).max() <= 1e-9 and np.abs(pim.cpu().numpy() - refp.imag).max() <= 1e-9
