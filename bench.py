@@ -54,6 +54,11 @@ WORKLOADS = {
     # Float32Array frames (spectrumStream's element type) computed in fp64 like the reference
     "c3": dict(prec="f64", sdtype="f32", window="hann", outputs=("amplitude", "phase"), frames=28122, n=4096, hop=1024,
                desc="STFT: 28,800,000 fp32 samples (10 min @48kHz), N=4096 hop 1024 Hann, fp64 amplitude + phase, 28122 frames"),
+    # bench/run.ts's own workloads: FFT.forward(input, out) on real fp64 frames, all N bins out
+    "run_ts_2048": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=32768, n=2048, kind="r2c_forward",
+                        desc="bench/run.ts shape: FFT.forward(input, out), N=2048 real fp64 -> N complex bins, 32768 frames"),
+    "run_ts_4096": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=16384, n=4096, kind="r2c_forward",
+                        desc="bench/run.ts shape: FFT.forward(input, out), N=4096 real fp64 -> N complex bins, 16384 frames"),
     # BASELINE config C4: large single complex fp64 transforms (multi-pass path); a "frame" is one transform
     "c4_2e20": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=8, n=1 << 20, kind="c2c",
                     desc="complex fp64 FFT, N=2^20, 8 transforms per step (multi-pass 1024x1024)"),
@@ -70,6 +75,8 @@ def algorithmic_bytes_per_frame(w) -> int:
     os_ = 8 if w["prec"] == "f64" else 4
     if w.get("kind") == "c2c":
         return 2 * 2 * es * w["n"]  # both planes in, both planes out
+    if w.get("kind") == "r2c_forward":
+        return es * w["n"] + 2 * os_ * w["n"]  # real frame in, both planes (all N bins) out
     bins = w["n"] // 2 + 1
     b = w.get("hop", w["n"]) * es  # unique input bytes per frame (overlap re-reads are expected to hit L2)
     if "amplitude" in w["outputs"]:
@@ -101,23 +108,26 @@ def run_reference(args, w):
 
     threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1; the oracle takes an explicit count
     n = w["n"]
-    if w.get("kind") == "c2c":
+    if w.get("kind") in ("c2c", "r2c_forward"):
         rng = np.random.default_rng(SEED)
-        re, im = rng.uniform(-1, 1, (1, n)), rng.uniform(-1, 1, (1, n))
+        nf = 1 if w["kind"] == "c2c" else min(w["frames"], 2048 * threads)
+        re, im = rng.uniform(-1, 1, (nf, n)), rng.uniform(-1, 1, (nf, n))
         plan = oracle.FFT(n)
+        run = (lambda: plan.forwardComplex(re, im)) if w["kind"] == "c2c" else (lambda: plan.forward(re, threads=threads))
         for _ in range(min(args.warmup, 1)):
-            plan.forwardComplex(re, im)
+            run()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            plan.forwardComplex(re, im)
+            run()
         dt = time.perf_counter() - t0
-        fps = args.steps / dt
+        fps = nf * args.steps / dt
         emit_line({"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
-                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                                           "sample": "one transform per step (a single radix-2 transform does not thread)"},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1 if w["kind"] == "c2c" else threads, "kind": "port",
+                                           "sample": "one transform per step (a single radix-2 transform does not thread)"
+                                           if w["kind"] == "c2c" else f"{nf} frames per step, frames split over threads"},
                           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
     # bounded sample: about 0.5 s of all-core work per step
@@ -555,17 +565,21 @@ def run_b200_c2c(args, w):
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local)
     L = lib()
-    n, frames = w["n"], w["frames"]
+    n, frames = w["n"], args.frames or w["frames"]
+    real_in = w.get("kind") == "r2c_forward"
     plan = ctx.plan(n, F64)
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     re = torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
-    im = torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    im = None if real_in else torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
     ore, oim = torch.empty_like(re), torch.empty_like(re)
     st = torch.cuda.Stream(device=dev)
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     def step():
-        check(L.pdsp_fft_complex_dev(plan, vp(re), vp(im), frames, vp(ore), vp(oim), 0, C.c_void_p(st.cuda_stream)))
+        if real_in:
+            check(L.pdsp_fft_forward_real_dev(plan, vp(re), F64, frames, vp(ore), vp(oim), 1, C.c_void_p(st.cuda_stream)))
+        else:
+            check(L.pdsp_fft_complex_dev(plan, vp(re), vp(im), frames, vp(ore), vp(oim), 0, C.c_void_p(st.cuda_stream)))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -601,11 +615,15 @@ def run_b200_c2c(args, w):
         elapsed_ms = float(tt[0])
     # e2e: host planes (pinned) through pdsp_fft_forward_complex
     e2e_steps = 1 if args.quick else max(2, min(args.steps, 5))
-    hre, him = re.cpu().pin_memory(), im.cpu().pin_memory()
+    hre = re.cpu().pin_memory()
+    him = None if real_in else im.cpu().pin_memory()
     hor, hoi = torch.empty_like(hre).pin_memory(), torch.empty_like(hre).pin_memory()
 
     def e2e_step():
-        check(L.pdsp_fft_forward_complex(plan, vp(hre), vp(him), frames, vp(hor), vp(hoi)))
+        if real_in:
+            check(L.pdsp_fft_forward_real(plan, vp(hre), F64, frames, vp(hor), vp(hoi)))
+        else:
+            check(L.pdsp_fft_forward_complex(plan, vp(hre), vp(him), frames, vp(hor), vp(hoi)))
 
     e2e_step()
     barrier()
@@ -615,17 +633,21 @@ def run_b200_c2c(args, w):
     e2e_s = time.perf_counter() - t0
     parity = cpu_baseline = None
     if rank == 0:
-        ref = np.fft.fft(hre[0].numpy() + 1j * him[0].numpy())
+        ref = np.fft.fft(hre[0].numpy() if real_in else hre[0].numpy() + 1j * him[0].numpy())
         got = hor[0].numpy() + 1j * hoi[0].numpy()
         parity = {"frames": 1, "rel_l2_vs_numpy": float(np.linalg.norm(got - ref) / np.linalg.norm(ref)),
                   "bound": 1e-12 * np.log2(n)}
         if world == 1 and not args.quick:
             import oracle
             plan_o = oracle.FFT(n)
+            ns = 1 if n > 65536 else min(frames, 4096)
             t0 = time.perf_counter()
-            plan_o.forwardComplex(hre[0].numpy(), him[0].numpy())
-            cpu_baseline = {"value": 1.0 / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
-                            "sample": "one transform of the same size through oracle/pragma_oracle.c (radix-2, single thread)"}
+            if real_in:
+                plan_o.forward(hre[:ns].numpy())
+            else:
+                plan_o.forwardComplex(hre[:ns].numpy(), him[:ns].numpy())
+            cpu_baseline = {"value": ns / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
+                            "sample": f"{ns} transform(s) of the same size through oracle/pragma_oracle.c (radix-2, single thread)"}
         bpf = algorithmic_bytes_per_frame(w)
         peak, peak_src = measured_hbm_peak()
         fps = frames * world * args.steps / (elapsed_ms * 1e-3)
@@ -640,11 +662,13 @@ def run_b200_c2c(args, w):
                        "parallelism": f"replicas x{world}"},
             "hbm_gbs": fps * bpf / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "bigfft_pass_kernel (all passes of a transform)",
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "r2c_kernel (MD_CPLX)" if real_in else "bigfft_pass(_tma)_kernel (all passes of a transform)",
                          "algorithmic_bytes_per_frame": bpf, "kernel_ms": step_ms},
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": frames * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 16 * n * frames,
-                    "d2h_bytes_per_step": 16 * n * frames, "steps": e2e_steps, "api": "pdsp_fft_forward_complex (host pinned)"},
+            "e2e": {"value": frames * world * e2e_steps / e2e_s, "unit": "frames/s",
+                    "h2d_bytes_per_step": (8 if real_in else 16) * n * frames, "d2h_bytes_per_step": 16 * n * frames,
+                    "steps": e2e_steps, "api": "pdsp_fft_forward_real (host pinned)" if real_in else "pdsp_fft_forward_complex (host pinned)"},
             "gpu_launches": launches * world, "clocks": sampler.summary() if sampler else None, "parity": parity,
         }
         emit_line(line)
