@@ -715,7 +715,7 @@ def main():
     try:
         if args.impl == "reference":
             return run_reference(args, w)
-        if w.get("kind") == "c2c":
+        if w.get("kind") in ("c2c", "r2c_forward"):
             return run_b200_c2c(args, w)
         return run_b200(args, w)
     finally:
