@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""Fraction of the HBM roofline across FFT sizes (amplitude + peak, Hann) for both precisions.
+
+    python scripts/sweep_sizes.py > gpurun_out/sweep_sizes.jsonl
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from pragma_dsp_b200 import _lib  # noqa: E402
+from pragma_dsp_b200._lib import F32, F64, SIDES, WINDOWS, SpectrumDesc, check, lib  # noqa: E402
+
+ctx = _lib.Context(0)
+L = lib()
+peak, _ = bench.measured_hbm_peak()
+dev = torch.device("cuda", 0)
+st = torch.cuda.Stream(device=dev)
+for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.float32)):
+    for log2n in range(5, 15):
+        n = 1 << log2n
+        frames = max(64, (1 << 26) // n)  # ~64M samples per launch: far beyond L2
+        x = torch.randn((frames, n), device=dev, dtype=tdt)
+        bins = n // 2 + 1
+        amp = torch.empty((frames, bins), dtype=tdt, device=dev)
+        pk = torch.zeros((frames, 32), dtype=torch.uint8, device=dev)
+        plan = ctx.plan(n, prec)
+        d = SpectrumDesc(sample_dtype=prec, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
+                         sample_rate=48000.0, raw_magnitude=0)
+
+        def go():
+            check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(amp.data_ptr()), None,
+                                      C.c_void_p(pk.data_ptr()), C.c_void_p(st.cuda_stream)))
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10):
+            go()
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        es = 8 if prec == F64 else 4
+        bpf = n * es + bins * es + (32 if prec == F64 else 16)
+        gbs = frames * bpf / (ms * 1e-3) / 1e9
+        print(json.dumps({"precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+                          "gbs": gbs, "frac_of_measured_hbm": gbs / peak}), flush=True)
+        del x, amp, pk
