@@ -21,7 +21,8 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpragma_b200.so")
 NVCC = os.environ.get("PDSP_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+EXTRA = os.environ.get("PDSP_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DPDSP_F32_P32_FROM=7)
+FLAGS = ARCH + EXTRA + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                 "-ccbin", "/usr/bin/g++"]
 
 

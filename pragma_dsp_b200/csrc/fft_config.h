@@ -16,7 +16,15 @@ struct KCfg {
   // doubles: 16 points per thread from M = 512 up (radix 16 passes: 512 = 16 x 16 x 2, one warp per frame);
   // floats: 32 points per thread (radix 32: 512 = 32 x 16, a single exchange) - registers allow it and the
   // fp32 kernels are issue-bound, so fewer exchange instructions win (profiles/r1 sweep).  Below 512: 8.
-  static constexpr int LOG2P = LOG2M < 3 ? LOG2M : (LOG2M >= 9 ? (sizeof(T) == 4 ? 5 : 4) : 3);
+#ifndef PDSP_F32_P32_FROM
+#define PDSP_F32_P32_FROM 9  // smallest log2(M) at which fp32 kernels hold 32 points per thread
+#endif
+#ifndef PDSP_F32_SMALL_LOG2P
+#define PDSP_F32_SMALL_LOG2P 4  // fp32, M = 128 / 256: 16 points per thread (N = 512: 0.55 -> 0.70 of roofline)
+#endif
+  static constexpr int LOG2P = LOG2M < 3 ? LOG2M
+                               : sizeof(T) == 4 ? (LOG2M >= PDSP_F32_P32_FROM ? 5 : (LOG2M >= 7 ? PDSP_F32_SMALL_LOG2P : 3))
+                                                : (LOG2M >= 9 ? 4 : 3);
   static constexpr int MAXRB = LOG2P >= 4 ? LOG2P : 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
   static constexpr int THREADS = (sizeof(T) == 4 && LOG2P == 5) ? (TF > 32 ? TF : 32) : (TF > 128 ? TF : 128);
