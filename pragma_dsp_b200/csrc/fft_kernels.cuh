@@ -239,15 +239,24 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   static_assert(THREADS % TF == 0 && SLOTS >= 1, "CTA must hold whole frames");
   constexpr bool GEN = MODE == MD_GENERIC;
   constexpr bool PHASE = GEN || (MODE & MD_PHASE) != 0;
-  constexpr bool POST_SMEM = TF > 32;  // partner bin via shared memory instead of shuffle
-  constexpr int SLOT_ELEMS = (E::NEEDS_SMEM || POST_SMEM) ? E::SMEM_ELEMS : 0;
+  // Frames wider than a warp: the frame's threads are laid out so that the owners of bins k and M-k always
+  // share a warp (lanes l and l^16), and the Hermitian post-pass can shuffle instead of taking a third trip
+  // through shared memory.  Warp w of the frame holds logical threads 16w..16w+15 on lanes 0-15 and their
+  // partners TF-16w..TF-16w-15 on lanes 16-31; t = 0 and t = TF/2 pair with themselves (warp 0, lanes 0 and 16).
+  constexpr bool PAIRED = TF > 32;
+  constexpr int SLOT_ELEMS = E::NEEDS_SMEM ? E::SMEM_ELEMS : 0;
   // peak-only kernels rank bins by |X|^2 (no square root per bin); the winner's amplitude is computed
   // once, in the finishing loop.  Frames spanning several warps keep the linear key.
   constexpr bool KEYSQ = MODE == MD_PEAK && TF <= 32;
 
   const int tid = simt::tid();
   const int slot = tid / TF;
-  const int t = tid % TF;
+  const int tl = tid % TF;  // position inside the frame's thread group
+  int t = tl;               // logical thread: holds elements t + TF*q
+  if constexpr (PAIRED) {
+    const int w = tl >> 5, l = tl & 31;
+    t = l < 16 ? 16 * w + l : (tl == 16 ? TF / 2 : TF - (16 * w + (l - 16)));
+  }
   cx<T>* sm = reinterpret_cast<cx<T>*>(simt::smem()) + (size_t)slot * SLOT_ELEMS;
   const cx<T>* PDSP_RESTRICT tw = static_cast<const cx<T>*>(p.tw);
   const cx<T>* PDSP_RESTRICT post = static_cast<const cx<T>*>(p.post);
@@ -466,8 +475,12 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           constexpr int q = decltype(qi)::value;
           const int k = t + TF * q;  // 0 <= k < M/2
           cx<T> zp;                  // Z[(M - k) % M]
-          if constexpr (POST_SMEM) {
-            zp = sm[E::pad((M - k) & (M - 1))];
+          if constexpr (PAIRED) {
+            const cx<T> mine = v[P - 1 - q];
+            cx<T> got;
+            got.x = simt::shfl_xor(mine.x, 16, 32);
+            got.y = simt::shfl_xor(mine.y, 16, 32);
+            zp = (t == 0) ? v[(P - q) % P] : (t == TF / 2 ? mine : got);
           } else if constexpr (TF == 1) {
             zp = v[(P - q) % P];
           } else {
@@ -514,10 +527,6 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       return verdict;
     };
 
-    if constexpr (M > 1 && POST_SMEM) {
-      static_for<0, P>([&](auto q) { sm[E::pad(t + TF * decltype(q)::value)] = v[decltype(q)::value]; });
-      frame_sync<TF>(slot, SLOTS);
-    }
     {
       int verdict = post_pass(std::false_type{});
       if (!valid) verdict = 0;  // tail slots hold no frame
@@ -534,7 +543,6 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         if (redo) post_pass(std::true_type{});
       }
     }
-    if constexpr (M > 1 && POST_SMEM) frame_sync<TF>(slot, SLOTS);  // partner reads done before smem is reused
 
     // ---- findPeak: (value desc, index asc) reduction over the frame's threads
     if (want_peak) {
@@ -555,9 +563,9 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         constexpr int NW = TF / 32;
         T* rv = reinterpret_cast<T*>(sm);
         int* rk = reinterpret_cast<int*>(rv + NW);
-        if ((t & 31) == 0) {
-          rv[t >> 5] = bv;
-          rk[t >> 5] = bk;
+        if ((tl & 31) == 0) {
+          rv[tl >> 5] = bv;
+          rk[tl >> 5] = bk;
         }
         frame_sync<TF>(slot, SLOTS);
         bv = rv[0];

@@ -49,8 +49,7 @@ cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS;
   constexpr int SLOTS = THREADS / E::TF;
-  constexpr bool POST_SMEM = E::TF > 32;
-  constexpr size_t SMEM = (E::NEEDS_SMEM || POST_SMEM) ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
+  constexpr size_t SMEM = E::NEEDS_SMEM ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
   auto kern = [] {
     if constexpr (C::MAXREG > 0)
       return r2c_kernel_mr<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MAXREG, MODE>;
