@@ -19,18 +19,22 @@ struct KCfg {
 #ifndef PDSP_F32_P32_FROM
 #define PDSP_F32_P32_FROM 9  // smallest log2(M) at which fp32 kernels hold 32 points per thread
 #endif
+#ifndef PDSP_F64_P32_AT
+#define PDSP_F64_P32_AT -1  // experiment: log2(M) at which fp64 kernels hold 32 points per thread (one warp per frame)
+#endif
 #ifndef PDSP_F32_SMALL_LOG2P
 #define PDSP_F32_SMALL_LOG2P 4  // fp32, M = 128 / 256: 16 points per thread (N = 512: 0.55 -> 0.70 of roofline)
 #endif
   static constexpr int LOG2P = LOG2M < 3 ? LOG2M
                                : sizeof(T) == 4 ? (LOG2M >= PDSP_F32_P32_FROM ? 5 : (LOG2M >= 7 ? PDSP_F32_SMALL_LOG2P : 3))
-                                                : (LOG2M >= 9 ? 4 : 3);
+                                                : (LOG2M == PDSP_F64_P32_AT ? 5 : (LOG2M >= 9 ? 4 : 3));
   static constexpr int MAXRB = LOG2P >= 4 ? LOG2P : 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
-  static constexpr int THREADS = (sizeof(T) == 4 && LOG2P == 5) ? (TF > 32 ? TF : 32) : (TF > 128 ? TF : 128);
+  static constexpr int THREADS = LOG2P == 5 ? (TF > 32 ? TF : 32) : (TF > 128 ? TF : 128);
   // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread, except 96 for floats holding
   // 8 or 16 points.  MAXREG > 0 selects a hard __maxnreg__ cap instead (tuning variants).
-  static constexpr int MINB = (sizeof(T) == 4 && LOG2P < 5 && THREADS <= 128) ? 5 : (512 / THREADS > 0 ? 512 / THREADS : 1);
+  static constexpr int MINB = (sizeof(T) == 8 && LOG2P == 5) ? (256 / THREADS > 0 ? 256 / THREADS : 1)
+                              : (sizeof(T) == 4 && LOG2P < 5 && THREADS <= 128) ? 5 : (512 / THREADS > 0 ? 512 / THREADS : 1);
   static constexpr int MAXREG = 0;
 };
 

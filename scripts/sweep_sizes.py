@@ -2,6 +2,7 @@
 """Fraction of the HBM roofline across FFT sizes (amplitude + peak, Hann) for both precisions.
 
     python scripts/sweep_sizes.py > gpurun_out/sweep_sizes.jsonl
+    SWEEP_MODE=amp|amp_peak|peak|cplx SWEEP_LOG2N=10,11,12 python scripts/sweep_sizes.py
 """
 import ctypes as C
 import json
@@ -19,10 +20,12 @@ from pragma_dsp_b200._lib import F32, F64, SIDES, WINDOWS, SpectrumDesc, check, 
 ctx = _lib.Context(0)
 L = lib()
 peak, _ = bench.measured_hbm_peak()
+MODE = os.environ.get("SWEEP_MODE", "amp_peak")
+SIZES = [int(v) for v in os.environ.get("SWEEP_LOG2N", ",".join(str(i) for i in range(5, 15))).split(",")]
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev)
 for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.float32)):
-    for log2n in range(5, 15):
+    for log2n in SIZES:
         n = 1 << log2n
         frames = max(64, (1 << 26) // n)  # ~64M samples per launch: far beyond L2
         x = torch.randn((frames, n), device=dev, dtype=tdt)
@@ -33,9 +36,16 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         d = SpectrumDesc(sample_dtype=prec, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
                          sample_rate=48000.0, raw_magnitude=0)
 
+        im = torch.empty((frames, bins), dtype=tdt, device=dev) if MODE == "cplx" else None
+
         def go():
-            check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(amp.data_ptr()), None,
-                                      C.c_void_p(pk.data_ptr()), C.c_void_p(st.cuda_stream)))
+            if MODE == "cplx":
+                check(L.pdsp_fft_forward_real_dev(plan, C.c_void_p(x.data_ptr()), prec, frames, C.c_void_p(amp.data_ptr()),
+                                                  C.c_void_p(im.data_ptr()), 0, C.c_void_p(st.cuda_stream)))
+                return
+            check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()),
+                                      C.c_void_p(amp.data_ptr()) if "amp" in MODE else None, None,
+                                      C.c_void_p(pk.data_ptr()) if "peak" in MODE else None, C.c_void_p(st.cuda_stream)))
         for _ in range(3):
             go()
         torch.cuda.synchronize()
@@ -47,8 +57,9 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         es = 8 if prec == F64 else 4
-        bpf = n * es + bins * es + (32 if prec == F64 else 16)
+        bpf = n * es + (2 * bins * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0)
+                        + ((32 if prec == F64 else 16) if "peak" in MODE else 0))
         gbs = frames * bpf / (ms * 1e-3) / 1e9
-        print(json.dumps({"precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+        print(json.dumps({"mode": MODE, "precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
                           "gbs": gbs, "frac_of_measured_hbm": gbs / peak}), flush=True)
-        del x, amp, pk
+        del x, amp, pk, im
