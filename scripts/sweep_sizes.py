@@ -36,12 +36,14 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         d = SpectrumDesc(sample_dtype=prec, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
                          sample_rate=48000.0, raw_magnitude=0)
 
-        im = torch.empty((frames, bins), dtype=tdt, device=dev) if MODE == "cplx" else None
+        if MODE == "cplx":  # Radix2Fft.forward: all N bins, two planes
+            amp = torch.empty((frames, n), dtype=tdt, device=dev)
+        im = torch.empty((frames, n), dtype=tdt, device=dev) if MODE == "cplx" else None
 
         def go():
             if MODE == "cplx":
                 check(L.pdsp_fft_forward_real_dev(plan, C.c_void_p(x.data_ptr()), prec, frames, C.c_void_p(amp.data_ptr()),
-                                                  C.c_void_p(im.data_ptr()), 0, C.c_void_p(st.cuda_stream)))
+                                                  C.c_void_p(im.data_ptr()), 1, C.c_void_p(st.cuda_stream)))
                 return
             check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()),
                                       C.c_void_p(amp.data_ptr()) if "amp" in MODE else None, None,
@@ -57,7 +59,7 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         es = 8 if prec == F64 else 4
-        bpf = n * es + (2 * bins * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0)
+        bpf = n * es + (2 * n * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0)
                         + ((32 if prec == F64 else 16) if "peak" in MODE else 0))
         gbs = frames * bpf / (ms * 1e-3) / 1e9
         print(json.dumps({"mode": MODE, "precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
