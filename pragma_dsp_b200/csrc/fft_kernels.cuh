@@ -90,11 +90,22 @@ PDSP_DEVICE double t_sqrt<double>(double v) {
 //   reduce to t = num/den with |t| <= tan(pi/8) using one division (a rotation by pi/4 is folded into the
 //   choice of numerator/denominator), odd minimax polynomial in t (degree 25 for fp64: 3e-18 relative;
 //   degree 11 for fp32), then undo the octant/quadrant folds.  Measured max error vs libm: see tests.
-PDSP_DEVICE double fast_atan2(double y, double x) {
+// Polynomial coefficients live in the constant bank so that each DFMA takes its coefficient as a c[][] operand;
+// as literals every call site re-materialised them with two UMOVs apiece (14 % of the C3 kernel's issue slots).
+#if defined(__CUDACC__) && !defined(PDSP_EMU)
+static __constant__ double kAtanC[12] = {
+#else
+static const double kAtanC[12] = {
+#endif
+    0.016285756855221028, -0.034570561981427744, 0.04551593220626549,  -0.05230454270650244,
+    0.05878928997834775,  -0.06666424885738255,  0.07692296375032143,  -0.09090908753500877,
+    0.11111111105155447,  -0.14285714285659828,  0.19999999999999804,  -0.3333333333333333};
+// branch-free core; `rare` is set when the caller must redo the value with libdevice's atan2
+PDSP_DEVICE double fast_atan2_core(double y, double x, bool& rare) {
   const double ax = fabs(x), ay = fabs(y);
   const double mx = fmax(ax, ay), mn = fmin(ax, ay);
   const unsigned ex = ((unsigned)__double2hiint(mx) >> 20) & 0x7ffu;
-  if (ex - 64u >= 1920u && mx != 0.0) return atan2(y, x);  // |max| outside [2^-959, 2^961): rare, let libdevice do it
+  rare = ex - 64u >= 1920u && mx != 0.0;  // |max| outside [2^-959, 2^961) (incl. inf / NaN)
   const bool big = mn > 0.41421356237309503 * mx;          // above tan(pi/8): atan(z) = pi/4 + atan((z-1)/(z+1))
   const double num = big ? mn - mx : mn;
   const double den = big ? mn + mx : mx;
@@ -110,29 +121,36 @@ PDSP_DEVICE double fast_atan2(double y, double x) {
 #endif
   if (mx == 0.0) t = 0.0;
   const double u = t * t;
-  double p = 0.016285756855221028;
-  p = fma(p, u, -0.034570561981427744);
-  p = fma(p, u, 0.04551593220626549);
-  p = fma(p, u, -0.05230454270650244);
-  p = fma(p, u, 0.05878928997834775);
-  p = fma(p, u, -0.06666424885738255);
-  p = fma(p, u, 0.07692296375032143);
-  p = fma(p, u, -0.09090908753500877);
-  p = fma(p, u, 0.11111111105155447);
-  p = fma(p, u, -0.14285714285659828);
-  p = fma(p, u, 0.19999999999999804);
-  p = fma(p, u, -0.3333333333333333);
+  // even / odd split (two half-length Horner chains in u^2): the serial depth drops from 12 to 7 DFMAs
+  const double u2 = u * u;
+  double po = kAtanC[0], pe = kAtanC[1];
+  po = fma(po, u2, kAtanC[2]);
+  pe = fma(pe, u2, kAtanC[3]);
+  po = fma(po, u2, kAtanC[4]);
+  pe = fma(pe, u2, kAtanC[5]);
+  po = fma(po, u2, kAtanC[6]);
+  pe = fma(pe, u2, kAtanC[7]);
+  po = fma(po, u2, kAtanC[8]);
+  pe = fma(pe, u2, kAtanC[9]);
+  po = fma(po, u2, kAtanC[10]);
+  pe = fma(pe, u2, kAtanC[11]);
+  const double p = fma(po, u, pe);
   double a = fma(t * u, p, t);
   if (big) a += 0.78539816339744831;
   if (ay > ax) a = 1.5707963267948966 - a;
   if (__double2hiint(x) < 0) a = 3.141592653589793 - a;  // sign bit, so that atan2(+-0, -0) = +-pi
   return copysign(a, y);
 }
-PDSP_DEVICE float fast_atan2(float y, float x) {
+PDSP_DEVICE double fast_atan2(double y, double x) {
+  bool rare;
+  const double a = fast_atan2_core(y, x, rare);
+  return rare ? atan2(y, x) : a;
+}
+PDSP_DEVICE float fast_atan2_core(float y, float x, bool& rare) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
   const unsigned ex = ((unsigned)__float_as_int(mx) >> 23) & 0xffu;
-  if (ex - 16u >= 224u && mx != 0.0f) return atan2f(y, x);  // |max| outside [2^-111, 2^113)
+  rare = ex - 16u >= 224u && mx != 0.0f;  // |max| outside [2^-111, 2^113)
   const bool big = mn > 0.41421356f * mx;
   const float num = big ? mn - mx : mn;
   const float den = big ? mn + mx : mx;
@@ -158,8 +176,36 @@ PDSP_DEVICE float fast_atan2(float y, float x) {
   if (__float_as_int(x) < 0) a = 3.14159265f - a;
   return copysignf(a, y);
 }
+PDSP_DEVICE float fast_atan2(float y, float x) {
+  bool rare;
+  const float a = fast_atan2_core(y, x, rare);
+  return rare ? atan2f(y, x) : a;
+}
 PDSP_DEVICE_NOINLINE float t_atan2(float y, float x) { return fast_atan2(y, x); }
 PDSP_DEVICE_NOINLINE double t_atan2(double y, double x) { return fast_atan2(y, x); }
+// two independent arguments per call: the two dependency chains interleave (the per-bin phase of the two
+// streams of a thread), which a single noinline call per bin cannot offer the scheduler
+#ifdef PDSP_ATAN2_INLINE
+#define PDSP_ATAN2X2_LINKAGE PDSP_DEVICE
+#else
+#define PDSP_ATAN2X2_LINKAGE PDSP_DEVICE_NOINLINE
+#endif
+template <typename T>
+struct Pair2 {
+  T a, b;
+};
+PDSP_ATAN2X2_LINKAGE Pair2<float> t_atan2_x2(float y0, float x0, float y1, float x1) {
+  bool r0, r1;
+  Pair2<float> o{fast_atan2_core(y0, x0, r0), fast_atan2_core(y1, x1, r1)};
+  if (r0 || r1) o = Pair2<float>{t_atan2(y0, x0), t_atan2(y1, x1)};
+  return o;
+}
+PDSP_ATAN2X2_LINKAGE Pair2<double> t_atan2_x2(double y0, double x0, double y1, double x1) {
+  bool r0, r1;
+  Pair2<double> o{fast_atan2_core(y0, x0, r0), fast_atan2_core(y1, x1, r1)};
+  if (r0 || r1) o = Pair2<double>{t_atan2(y0, x0), t_atan2(y1, x1)};
+  return o;
+}
 PDSP_DEVICE_NOINLINE float t_hypot_slow(float x, float y) { return hypotf(x, y); }
 PDSP_DEVICE_NOINLINE double t_hypot_slow(double x, double y) { return hypot(x, y); }
 
@@ -390,7 +436,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       PeakCand<T> c1{sizeof(T) == 8 ? (T)4.9406564584124654e-324 : (T)1.401298464324817e-45, 0, (T)0, (T)0};
       unsigned hi_max = 0u, lo_min = 0xffffffffu;  // exponent range of re^2+im^2 seen by this thread (fp64)
 
-      auto emit = [&](auto stream_c, auto off_c, auto edge_c, int k, cx<T> X) {
+      auto emit = [&](auto stream_c, auto off_c, auto edge_c, int k, cx<T> X, T ph) {
         constexpr int STREAM = decltype(stream_c)::value;
         constexpr int OFF = decltype(off_c)::value;    // element offset from the stream's base pointer
         constexpr bool EDGE = decltype(edge_c)::value;  // k may be 0 or M (DC / Nyquist)
@@ -452,7 +498,6 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         }
         if constexpr (PHASE) {
           if (want_phase && o_ph != nullptr) {
-            const T ph = t_atan2(X.y, X.x);
             (o_ph + b0)[OFF] = ph;
             if (two_sided && (!EDGE || (k != 0 && k != M))) (o_ph + m0)[-OFF] = -ph;
           }
@@ -463,8 +508,13 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
 
       if constexpr (M == 1) {
         // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
-        emit(I0{}, I0{}, std::true_type{}, 0, cx<T>{v[0].x + v[0].y, (T)0});
-        emit(I1{}, I0{}, std::true_type{}, 1, cx<T>{v[0].x - v[0].y, (T)0});
+        const cx<T> x0{v[0].x + v[0].y, (T)0}, x1{v[0].x - v[0].y, (T)0};
+        Pair2<T> ph{(T)0, (T)0};
+        if constexpr (PHASE) {
+          if (want_phase) ph = t_atan2_x2(x0.y, x0.x, x1.y, x1.x);
+        }
+        emit(I0{}, I0{}, std::true_type{}, 0, x0, ph.a);
+        emit(I1{}, I0{}, std::true_type{}, 1, x1, ph.b);
       } else {
         // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
         // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
@@ -509,11 +559,22 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
               xb.y = (T)0;
             }
           }
-          emit(I0{}, std::integral_constant<int, TF * q>{}, std::bool_constant<q == 0>{}, k, xa);
-          emit(I1{}, std::integral_constant<int, -TF * q>{}, std::bool_constant<q == 0>{}, M - k, xb);
+          Pair2<T> ph{(T)0, (T)0};
+          if constexpr (PHASE) {
+            if (want_phase) ph = t_atan2_x2(xa.y, xa.x, xb.y, xb.x);
+          }
+          emit(I0{}, std::integral_constant<int, TF * q>{}, std::bool_constant<q == 0>{}, k, xa, ph.a);
+          emit(I1{}, std::integral_constant<int, -TF * q>{}, std::bool_constant<q == 0>{}, M - k, xb, ph.b);
         });
         // self-paired bin M/2 = conj(Z[M/2]) (thread 0; above every stream-0 bin of that thread)
-        if (t == 0) emit(I0{}, std::integral_constant<int, M / 2>{}, std::false_type{}, M / 2, cx<T>{v[P / 2].x, -v[P / 2].y});
+        if (t == 0) {
+          const cx<T> xh{v[P / 2].x, -v[P / 2].y};
+          T ph = (T)0;
+          if constexpr (PHASE) {
+            if (want_phase) ph = t_atan2(xh.y, xh.x);
+          }
+          emit(I0{}, std::integral_constant<int, M / 2>{}, std::false_type{}, M / 2, xh, ph);
+        }
       }
       int verdict = 0;  // bit 0: a sum of squares left the safe range; bit 1: every sum of this thread was 0
       if constexpr (sizeof(T) == 8 && !CAREFUL) {
