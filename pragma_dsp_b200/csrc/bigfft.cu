@@ -6,13 +6,13 @@ namespace pdsp {
 
 int big_pass_c(int log2l);
 
-template <typename T, int LOG2L>
-static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
+template <typename T, int LOG2L, int IO>
+static cudaError_t launch_big_io(const BigPassParams& p, const LaunchCtx& lc) {
   using B = BigCfg<T, LOG2L>;
   using E = FftEngine<T, LOG2L, B::LOG2P, B::MAXRB>;
   constexpr int THREADS = B::TF * B::C;
   constexpr size_t SMEM = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * B::C;
-  auto kern = bigfft_pass_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C>;
+  auto kern = bigfft_pass_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C, IO>;
   static int bps[kMaxDevices] = {0};
   if (p.n_groups <= 0 || p.n_frames <= 0) return cudaSuccess;
   int grid = 0;
@@ -26,13 +26,23 @@ static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
 }
 
 template <typename T, int LOG2L>
-static cudaError_t launch_big_tma_t(const BigPassParams& p, const simt::TensorMap2D& tm_re, const simt::TensorMap2D& tm_im,
-                                    const LaunchCtx& lc) {
+static cudaError_t launch_big_t(const BigPassParams& p, const LaunchCtx& lc) {
+  switch ((p.in_cplx ? 1 : 0) | (p.out_cplx ? 2 : 0)) {
+    case 0: return launch_big_io<T, LOG2L, 0>(p, lc);
+    case 1: return launch_big_io<T, LOG2L, 1>(p, lc);
+    case 2: return launch_big_io<T, LOG2L, 2>(p, lc);
+    default: return launch_big_io<T, LOG2L, 3>(p, lc);
+  }
+}
+
+template <typename T, int LOG2L, int IO>
+static cudaError_t launch_big_tma_io(const BigPassParams& p, const simt::TensorMap2D& tm_re, const simt::TensorMap2D& tm_im,
+                                     const LaunchCtx& lc) {
   using B = BigCfg<T, LOG2L>;
   using E = FftEngine<T, LOG2L, B::LOG2P, B::MAXRB>;
   using S = BigTmaSmem<T, LOG2L, B::LOG2P, B::MAXRB, B::C>;
   constexpr int THREADS = B::TF * B::C;
-  auto kern = bigfft_pass_tma_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C, S::STAGES>;
+  auto kern = bigfft_pass_tma_kernel<T, LOG2L, B::LOG2P, B::MAXRB, B::C, S::STAGES, IO>;
   static int bps[kMaxDevices] = {0};
   if (p.n_groups <= 0 || p.n_frames <= 0) return cudaSuccess;
   int grid = 0;
@@ -43,6 +53,18 @@ static cudaError_t launch_big_tma_t(const BigPassParams& p, const simt::TensorMa
   if (!q.tw) return cudaErrorInvalidValue;
   PDSP_LAUNCH(kern, grid, THREADS, S::BYTES, lc.stream, q, tm_re, tm_im);
   return cudaGetLastError();
+}
+
+template <typename T, int LOG2L>
+static cudaError_t launch_big_tma_t(const BigPassParams& p, const simt::TensorMap2D& tm_re, const simt::TensorMap2D& tm_im,
+                                    const LaunchCtx& lc) {
+  // never the last pass: the output kind equals the work-buffer kind
+  switch ((p.in_cplx ? 1 : 0) | (p.out_cplx ? 2 : 0)) {
+    case 0: return launch_big_tma_io<T, LOG2L, 0>(p, tm_re, tm_im, lc);
+    case 2: return launch_big_tma_io<T, LOG2L, 2>(p, tm_re, tm_im, lc);
+    case 3: return launch_big_tma_io<T, LOG2L, 3>(p, tm_re, tm_im, lc);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // box of the TMA tile of a pass: {C columns, min(L, 256) rows}

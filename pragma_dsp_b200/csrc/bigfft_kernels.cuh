@@ -36,6 +36,12 @@ struct BigPassParams {
   int swap_in;   // inverse transform = swap(FFT(swap(x))) / N
   int swap_out;
   double scale;  // applied on the way out (1/N on the last pass of an inverse)
+  int l2_prefetch;  // 1: pull the CTA's next tile into L2 while the current one is transformed
+  // Intermediate passes exchange data through an INTERLEAVED work buffer (cx<T> elements, pointer in in_re /
+  // out_re, strides still in complex elements): a tile row is then 2*C*sizeof(T) contiguous bytes instead of
+  // two segments of half that, which is what the strided rows' DRAM efficiency depends on.  Caller-facing
+  // input (first pass) and output (last pass) stay planar like the reference's ComplexArray.
+  int in_cplx, out_cplx;
 };
 
 template <typename T>
@@ -45,8 +51,11 @@ PDSP_DEVICE cx<T> big_twiddle(const cx<T>* PDSP_RESTRICT hi, const cx<T>* PDSP_R
   return cmul(a, b);
 }
 
-template <typename T, int LOG2L, int LOG2P, int MAXRB, int C>
+// IO: bit 0 = the input is the interleaved work buffer, bit 1 = the output is (compile time: a run-time test
+// inside the unrolled load / store loops cost 25-50 % of the kernel)
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO>
 PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_kernel(const BigPassParams p) {
+  constexpr bool IN_CPLX = (IO & 1) != 0, OUT_CPLX = (IO & 2) != 0;
   using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
   constexpr int L = E::M, P = E::P, TF = E::TF;
   constexpr int THREADS = TF * C;
@@ -61,6 +70,8 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
   const T* PDSP_RESTRICT iim = static_cast<const T*>(p.in_im);
   T* PDSP_RESTRICT ore = static_cast<T*>(p.out_re);
   T* PDSP_RESTRICT oim = static_cast<T*>(p.out_im);
+  const cx<T>* PDSP_RESTRICT icx = static_cast<const cx<T>*>(p.in_re);  // when p.in_cplx
+  cx<T>* PDSP_RESTRICT ocx = static_cast<cx<T>*>(p.out_re);              // when p.out_cplx
   const T scale = (T)p.scale;
 
   for (long long w = simt::bid(); w < p.n_groups * p.n_frames; w += simt::nblocks()) {
@@ -74,9 +85,13 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
       for (int idx = tid; idx < C * L; idx += THREADS) {
         const int cc = idx >> LOG2L, e = idx & (L - 1);
         const long long a = in_base + cc * p.in_c + e * p.in_e;
-        const T re = ire[a];
-        const T im = iim != nullptr ? iim[a] : (T)0;
-        smem[(size_t)cc * SLOT + E::pad(e)] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        if constexpr (IN_CPLX) {
+          smem[(size_t)cc * SLOT + E::pad(e)] = ldg_cx(icx + a);
+        } else {
+          const T re = ire[a];
+          const T im = iim != nullptr ? iim[a] : (T)0;
+          smem[(size_t)cc * SLOT + E::pad(e)] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        }
       }
       simt::sync_block();
       static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[E::pad(t + TF * decltype(q)::value)]; });
@@ -85,10 +100,37 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
       static_for<0, P>([&](auto qi) {
         constexpr int q = decltype(qi)::value;
         const long long a = in_base + c * p.in_c + (long long)(t + TF * q) * p.in_e;
-        const T re = ire[a];
-        const T im = iim != nullptr ? iim[a] : (T)0;
-        v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        if constexpr (IN_CPLX) {
+          v[q] = ldg_cx(icx + a);
+        } else {
+          const T re = ire[a];
+          const T im = iim != nullptr ? iim[a] : (T)0;
+          v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        }
       });
+    }
+
+    if (p.l2_prefetch && w + simt::nblocks() < p.n_groups * p.n_frames) {
+      // this CTA is the only one on its SM and load -> transform -> store do not overlap: have the next tile
+      // waiting in L2.  One bulk prefetch per contiguous segment (C elements per row, or a whole row).
+      const long long w2 = w + simt::nblocks();
+      const long long fb2 = w2 / p.n_groups, g2 = w2 % p.n_groups;
+      const long long nb = fb2 * p.in_frame + (g2 / p.n_lo) * p.in_hi + (g2 % p.n_lo) * p.in_lo;
+      const int nseg = p.stage_in ? C : L;                                  // segments per plane
+      const long long seg_stride = p.stage_in ? p.in_c : p.in_e;            // elements between segments
+      const unsigned seg_bytes = (unsigned)((p.stage_in ? L : C) * sizeof(T)) * (IN_CPLX ? 2u : 1u);
+      for (int idx = tid; idx < (IN_CPLX ? 1 : 2) * nseg; idx += THREADS) {
+        const long long off = nb + (long long)(idx % nseg) * seg_stride;
+        const void* a;
+        if constexpr (IN_CPLX) {
+          a = icx + off;
+        } else {
+          const T* plane = idx < nseg ? ire : iim;
+          if (plane == nullptr) continue;
+          a = plane + off;
+        }
+        if (((reinterpret_cast<uintptr_t>(a) | seg_bytes) & 15u) == 0) simt::prefetch_l2_bulk(a, seg_bytes);
+      }
     }
 
     E::template fft<true>(v, t, sm, tw, 0, 1);
@@ -110,9 +152,13 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
     static_for<0, P>([&](auto qi) {
       constexpr int q = decltype(qi)::value;
       const long long a = out_base + c * p.out_c + (long long)(t + TF * q) * p.out_e;
-      const T x = v[q].x * scale, y = v[q].y * scale;
-      ore[a] = p.swap_out ? y : x;
-      oim[a] = p.swap_out ? x : y;
+      if constexpr (OUT_CPLX) {
+        ocx[a] = v[q];
+      } else {
+        const T x = v[q].x * scale, y = v[q].y * scale;
+        ore[a] = p.swap_out ? y : x;
+        oim[a] = p.swap_out ? x : y;
+      }
     });
   }
 }
@@ -124,7 +170,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
 // the tile aliases the exchange buffers.  Results are stored with the same coalesced per-thread stores
 // as the plain kernel.  Requires frames to be contiguous (in_frame = N) and the inner index to be the
 // tensor's contiguous dimension - i.e. any pass but the last.
-template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int STAGES>
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int STAGES, int IO>
 PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
     bigfft_pass_tma_kernel(const BigPassParams p, const PDSP_GRID_CONSTANT simt::TensorMap2D tm_re,
                            const PDSP_GRID_CONSTANT simt::TensorMap2D tm_im) {
@@ -148,18 +194,41 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + BAR_OFF);
   T* PDSP_RESTRICT ore = static_cast<T*>(p.out_re);
   T* PDSP_RESTRICT oim = static_cast<T*>(p.out_im);
+  cx<T>* PDSP_RESTRICT ocx = static_cast<cx<T>*>(p.out_re);  // when p.out_cplx
   const T scale = (T)p.scale;
-  const bool has_im = p.in_im != nullptr;
+  constexpr bool in_cplx = (IO & 1) != 0;  // tm_re then maps the interleaved buffer as [rows][2*I], {2*C, BOX_ROWS/2} box
+  constexpr bool OUT_CPLX = (IO & 2) != 0;
+  const bool has_im = p.in_im != nullptr && !in_cplx;
   const long long total = p.n_groups * p.n_frames;
   const long long n_hi = p.n_groups / p.n_lo;  // O
 
+  auto prefetch = [&](long long w) {  // one thread: L2 prefetch of a tile's boxes
+    const long long fb = w / p.n_groups, g = w % p.n_groups;
+    const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
+    const int x = (int)(g_lo * C);
+    const int y = (int)((fb * n_hi + g_hi) * L);
+    if constexpr (in_cplx) {
+      for (int j = 0; j < 2 * NBOX; ++j) simt::tma_prefetch_2d(&tm_re, 2 * x, y + j * (BOX_ROWS / 2));
+      return;
+    }
+    for (int j = 0; j < NBOX; ++j) {
+      simt::tma_prefetch_2d(&tm_re, x, y + j * BOX_ROWS);
+      if (has_im) simt::tma_prefetch_2d(&tm_im, x, y + j * BOX_ROWS);
+    }
+  };
   auto issue = [&](long long w, int stage) {  // one thread: arm the barrier and launch the tile's box loads
     const long long fb = w / p.n_groups, g = w % p.n_groups;
     const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
     const int x = (int)(g_lo * C);
     const int y = (int)((fb * n_hi + g_hi) * L);
-    simt::mbar_expect_tx(&bars[stage], (unsigned)((has_im ? 2 : 1) * PLANE));
+    simt::mbar_expect_tx(&bars[stage], (unsigned)((has_im || in_cplx ? 2 : 1) * PLANE));
     unsigned char* tile = base + (size_t)stage * 2 * PLANE;
+    if constexpr (in_cplx) {  // interleaved rows: the tile is [L][C] cx<T>, fetched as 2*NBOX boxes of BOX_ROWS/2 rows
+      for (int j = 0; j < 2 * NBOX; ++j)
+        simt::tma_load_2d(tile + (size_t)j * (BOX_ROWS / 2) * C * sizeof(cx<T>), &tm_re, 2 * x, y + j * (BOX_ROWS / 2),
+                          &bars[stage]);
+      return;
+    }
     for (int j = 0; j < NBOX; ++j) {
       simt::tma_load_2d(tile + (size_t)j * BOX_ROWS * C * sizeof(T), &tm_re, x, y + j * BOX_ROWS, &bars[stage]);
       if (has_im)
@@ -185,7 +254,10 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
       // accesses before the async-proxy writes of the bulk copy
       simt::fence_proxy_async();
       simt::sync_block();
-      if (tid == 0) issue(w, 0);
+      if (tid == 0) {
+        issue(w, 0);
+        if (p.l2_prefetch && w + simt::nblocks() < total) prefetch(w + simt::nblocks());
+      }
     }
     simt::mbar_wait(&bars[stage], phase[stage]);
     phase[stage] ^= 1u;
@@ -196,9 +268,13 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
     static_for<0, P>([&](auto qi) {
       constexpr int q = decltype(qi)::value;
       const int e = t + TF * q;
-      const T re = tre[e * C + c];
-      const T im = has_im ? tim[e * C + c] : (T)0;
-      v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+      if constexpr (in_cplx) {
+        v[q] = reinterpret_cast<const cx<T>*>(tre)[e * C + c];
+      } else {
+        const T re = tre[e * C + c];
+        const T im = has_im ? tim[e * C + c] : (T)0;
+        v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+      }
     });
     simt::sync_block();  // tile consumed: it may be refilled (STAGES 2) / overwritten by the exchanges (STAGES 1)
 
@@ -222,9 +298,13 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
     static_for<0, P>([&](auto qi) {
       constexpr int q = decltype(qi)::value;
       const long long a = out_base + c * p.out_c + (long long)(t + TF * q) * p.out_e;
-      const T x = v[q].x * scale, y = v[q].y * scale;
-      ore[a] = p.swap_out ? y : x;
-      oim[a] = p.swap_out ? x : y;
+      if constexpr (OUT_CPLX) {
+        ocx[a] = v[q];
+      } else {
+        const T x = v[q].x * scale, y = v[q].y * scale;
+        ore[a] = p.swap_out ? y : x;
+        oim[a] = p.swap_out ? x : y;
+      }
     });
   }
 }
@@ -250,7 +330,10 @@ struct BigCfg {
   // sequences per CTA = contiguous elements per row of the strided tile: as many as 512 threads and
   // 148 KB of exchange buffers allow (32 -> 256-byte rows of doubles; DRAM efficiency of the column
   // gather grows with the row length, profiles/r1/README.md)
-  static constexpr int C = LOG2L == 10 ? 8 : (LOG2L == 9 ? 16 : 32);
+#ifndef PDSP_BIG_C_SMALL
+#define PDSP_BIG_C_SMALL 32
+#endif
+  static constexpr int C = LOG2L == 10 ? 8 : (LOG2L == 9 ? 16 : PDSP_BIG_C_SMALL);
 };
 constexpr int kBigMinLog2L = 6, kBigMaxLog2L = 10;
 

@@ -62,6 +62,7 @@ struct R2CParams {
   // compile-time constants - two 16-byte loads per frame instead of one per complex point.  Null: use `window`.
   const void* winphase;
   double win_a0, win_a1, win_a2;
+  int l2_prefetch;  // 1: one lane per frame bulk-prefetches the next frame of its slot into L2
 };
 
 struct C2CParams {
@@ -342,6 +343,13 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       } else {
         const double* s = static_cast<const double*>(p.samples) + base;
         static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
+      }
+      if (p.l2_prefetch && tl == 0 && g + 1 < g_end && f + SLOTS < p.batch) {
+        // the next frame of this slot: its samples are in L2 by the time the loads above come round again
+        const size_t ses = p.sample_dtype == DT_F32 ? 4 : 8;
+        const char* nxt = static_cast<const char*>(p.samples) + (size_t)((f + SLOTS) * p.hop) * ses;
+        const unsigned nbytes = (unsigned)(N * ses);
+        if (((reinterpret_cast<uintptr_t>(nxt) | nbytes) & 15u) == 0) simt::prefetch_l2_bulk(nxt, nbytes);
       }
       if constexpr (sizeof(T) == 8) {
         if (p.winphase != nullptr) {

@@ -234,6 +234,7 @@ struct BigPlan {
   void* work_re = nullptr;  // intermediate planes, work_frames * N elements each
   void* work_im = nullptr;
   long long work_frames = 0;
+  bool work_interleaved = false;  // work_re alone holds cx<T> elements (PDSP_BIG_INTERLEAVE=1)
 };
 
 struct pdsp_plan {
@@ -500,6 +501,10 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     p.scale_mid = 2.0 / (double)n;   // (2 * mag) / size, identical bits for power-of-two size
   }
   p.bin_hz = d->sample_rate / (double)n;  // binFrequencies: quotient first (fourier.ts:160)
+  {
+    const char* pf = getenv("PDSP_L2_PREFETCH");
+    p.l2_prefetch = (pf && pf[0] == '1') ? 1 : 0;
+  }
   LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   cudaError_t e;
   if (n == 1) {
@@ -639,6 +644,13 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
   return 0;
 }
 
+// Intermediate passes exchange interleaved (re, im) elements unless PDSP_BIG_INTERLEAVE=0: 512-byte instead of
+// 2 x 256-byte tile rows (2^24: 0.375 -> 0.353 ms, profiles/r1/README.md)
+static bool big_interleave() {
+  const char* e = getenv("PDSP_BIG_INTERLEAVE");
+  return !(e && e[0] == '0');
+}
+
 static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
                       void* d_oim, int inverse, cudaStream_t st) {
   pdsp_ctx* c = pl->ctx;
@@ -654,13 +666,18 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   if (chunk > batch) chunk = batch;
   {
     std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
-    if (bp->work_frames < chunk) {
+    const bool want_il = big_interleave();
+    if (bp->work_frames < chunk || bp->work_interleaved != want_il) {
       CU(cudaStreamSynchronize(st));
       CU(cudaFree(bp->work_re));
       CU(cudaFree(bp->work_im));
       bp->work_re = bp->work_im = nullptr;
-      CU(cudaMalloc(&bp->work_re, es * (size_t)N * (size_t)chunk));
-      CU(cudaMalloc(&bp->work_im, es * (size_t)N * (size_t)chunk));
+      // work_re alone, twice the size, when the passes exchange interleaved cx<T> elements (default); two planar
+      // work planes with PDSP_BIG_INTERLEAVE=0
+      const bool il = want_il;
+      CU(cudaMalloc(&bp->work_re, (il ? 2 : 1) * es * (size_t)N * (size_t)chunk));
+      if (!il) CU(cudaMalloc(&bp->work_im, es * (size_t)N * (size_t)chunk));
+      bp->work_interleaved = il;
       bp->work_frames = chunk;
     }
   }
@@ -678,15 +695,22 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       const bool last = j == np - 1;
       BigPassParams p;
       memset(&p, 0, sizeof p);
+      const bool interleave = big_interleave();
       p.in_re = j == 0 ? (const void*)fre : bp->work_re;
-      p.in_im = j == 0 ? (const void*)fim : bp->work_im;
+      p.in_im = j == 0 ? (const void*)fim : (interleave ? nullptr : bp->work_im);
       p.out_re = last ? (void*)gre : bp->work_re;
-      p.out_im = last ? (void*)gim : bp->work_im;
+      p.out_im = last ? (void*)gim : (interleave ? nullptr : bp->work_im);
+      p.in_cplx = (interleave && j != 0) ? 1 : 0;
+      p.out_cplx = (interleave && !last) ? 1 : 0;
       p.n_frames = nf;
       p.in_frame = p.out_frame = N;
       p.swap_in = (j == 0 && inverse) ? 1 : 0;
       p.swap_out = (last && inverse) ? 1 : 0;
       p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
+      {
+        const char* pf = getenv("PDSP_BIG_PREFETCH");
+        p.l2_prefetch = (pf && pf[0] == '0') ? 0 : 1;  // default on: 2^24 0.43 -> 0.37 ms (profiles/r1/README.md)
+      }
       if (!last) {
         // view [O][L][I]: C adjacent inner indices per CTA, transform along the stride-I axis in place
         p.n_lo = I / C;
@@ -725,15 +749,24 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
         p.stage_in = 1;
       }
       cudaError_t e;
+      // TMA tile loads for the strided passes while one chunk's planes fit the L2 (2^20: 0.158 vs 0.169 ms per 8
+      // transforms); per-thread loads beyond that (2^24: 0.353 vs 0.373 ms).  PDSP_BIG_TMA=0/1 forces either.
       const char* tma_env = getenv("PDSP_BIG_TMA");
-      if (!last && !(tma_env && tma_env[0] == '0')) {
+      const bool tma = tma_env ? tma_env[0] != '0' : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
+      if (!last && tma) {
         // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
         simt::TensorMap2D tm_re, tm_im;
         int bc = 0, br = 0;
         big_pass_tma_box(bp->lg[j], &bc, &br);
         const bool f64p = pl->precision == PDSP_F64;
-        if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
-        if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+        if (p.in_cplx) {
+          // interleaved work buffer viewed as [rows][2*I] scalars; {2*C, rows/2} boxes keep a box at 64 KB
+          if (make_tensor_map(&tm_re, p.in_re, f64p, 2 * I, nf * O * L, 2 * bc, br / 2)) return 1;
+          tm_im = tm_re;
+        } else {
+          if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+          if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+        }
         e = launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
       } else {
         e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);

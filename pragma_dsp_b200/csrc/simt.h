@@ -61,6 +61,10 @@ PDSP_DEVICE void tma_load_2d(void* smem_dst, const TensorMap2D* map, int x, int 
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of the same box (no shared-memory destination, no barrier)
+PDSP_DEVICE void tma_prefetch_2d(const TensorMap2D* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 PDSP_DEVICE void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -76,6 +80,10 @@ PDSP_DEVICE void mbar_wait(unsigned long long* bar, unsigned parity) {
 }
 // order generic-proxy accesses to shared memory before later async-proxy (TMA) accesses to the same bytes
 PDSP_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bulk prefetch of [p, p + bytes) into L2 (one instruction; p and bytes multiples of 16)
+PDSP_DEVICE void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 PDSP_DEVICE unsigned char* smem() {
   extern __shared__ __align__(16) unsigned char pdsp_smem_[];
   return pdsp_smem_;
@@ -165,8 +173,10 @@ inline void tma_load_2d(void* smem_dst, const TensorMap2D* m, int x, int y, unsi
   }
   emu_mbar_complete_tx(bar, (unsigned)(m->box0 * m->box1 * m->esize));
 }
+inline void tma_prefetch_2d(const TensorMap2D*, int, int) {}
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu_mbar_wait(bar, parity); }
 inline void fence_proxy_async() {}
+inline void prefetch_l2_bulk(const void*, unsigned) {}
 inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over the warp's lanes
   int acc = pred ? 1 : 0;
   for (int m = 16; m >= 1; m >>= 1) acc |= shfl_xor(acc, m, 32);

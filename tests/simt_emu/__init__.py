@@ -24,7 +24,8 @@ class R2CParams(C.Structure):
                 ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int),
                 ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double),
                 ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong),
-                ("winphase", C.c_void_p), ("win_a0", C.c_double), ("win_a1", C.c_double), ("win_a2", C.c_double)]
+                ("winphase", C.c_void_p), ("win_a0", C.c_double), ("win_a1", C.c_double), ("win_a2", C.c_double),
+                ("l2_prefetch", C.c_int)]
 
 
 class C2CParams(C.Structure):

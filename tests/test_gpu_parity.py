@@ -298,12 +298,16 @@ def test_fused_peer_scatter_single_gpu(ctx):
         assert (rec[:offset]["index"] == 0).all() and (rec[offset + batch:]["index"] == 0).all()
 
 
-@pytest.mark.parametrize("tma", ["1", "0"])
-def test_large_fft_tma_and_plain_paths_agree(ctx, monkeypatch, tma):
-    """K2's strided passes have two implementations: TMA tile loads (cp.async.bulk.tensor + mbarrier,
-    the default) and per-thread coalesced loads (PDSP_BIG_TMA=0).  Both must give the same transform."""
+@pytest.mark.parametrize("tma,interleave,prefetch", [("1", "1", "1"), ("0", "1", "1"), ("1", "0", "1"), ("0", "0", "0"),
+                                                     ("1", "1", "0")])
+def test_large_fft_tma_and_plain_paths_agree(ctx, monkeypatch, tma, interleave, prefetch):
+    """K2's strided passes have two implementations: TMA tile loads (cp.async.bulk.tensor + mbarrier) and
+    per-thread coalesced loads (PDSP_BIG_TMA=0), an interleaved or planar work buffer between the passes
+    (PDSP_BIG_INTERLEAVE) and an optional L2 prefetch of the next tile.  All must give the same transform."""
     from pragma_dsp_b200.core import ComplexArray, Radix2Fft
     monkeypatch.setenv("PDSP_BIG_TMA", tma)
+    monkeypatch.setenv("PDSP_BIG_INTERLEAVE", interleave)
+    monkeypatch.setenv("PDSP_BIG_PREFETCH", prefetch)
     for log2n in (14, 18, 22):
         n = 1 << log2n
         rng = np.random.default_rng(log2n)

@@ -157,11 +157,20 @@ def test_launch_and_plan_accounting(emu_api):
     assert L.pdsp_plan_get(ctx.h, 12, 1, C.byref(h)) != 0 and b"power of two" in L.pdsp_last_error()
 
 
-@pytest.mark.parametrize("factors,n", [("6,6", 4096), ("7,6", 8192), ("6,6,6", 1 << 18), ("7,7", 1 << 14)])
-def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n):
+@pytest.mark.parametrize("factors,n,env", [("6,6", 4096, {}), ("7,6", 8192, {}), ("6,6,6", 1 << 18, {}),
+                                           ("7,7", 1 << 14, {}),
+                                           # switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
+                                           ("7,6", 8192, {"PDSP_BIG_TMA": "0"}),
+                                           ("7,6", 8192, {"PDSP_BIG_TMA": "1"}),
+                                           ("6,6,6", 1 << 18, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "1"}),
+                                           ("7,6", 8192, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "0",
+                                                          "PDSP_BIG_PREFETCH": "0"})])
+def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n, env):
     """K2: the multi-pass (four-step / six-step) path, forced onto small sizes with PDSP_BIG_FACTORS so the
     emulator can run it: forward, inverse, real-input forward, batch of 2."""
     from pragma_dsp_b200.core import Radix2Fft
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     if n > 8192:
         monkeypatch.delenv("PDSP_BIG_FACTORS", raising=False) if factors == "7,7" else monkeypatch.setenv("PDSP_BIG_FACTORS", factors)
     else:
