@@ -324,7 +324,10 @@ struct BigTmaSmem {
 // Pass configuration for a sub-transform length 2^LOG2L.
 template <typename T, int LOG2L>
 struct BigCfg {
-  static constexpr int LOG2P = LOG2L >= 8 ? 4 : 3;
+#ifndef PDSP_BIG_P16_FROM
+#define PDSP_BIG_P16_FROM 8  // smallest log2(L) whose threads hold 16 points (8 below)
+#endif
+  static constexpr int LOG2P = LOG2L >= PDSP_BIG_P16_FROM ? 4 : 3;
   static constexpr int MAXRB = LOG2P == 4 ? 4 : 3;
   static constexpr int TF = (1 << LOG2L) >> LOG2P;
   // sequences per CTA = contiguous elements per row of the strided tile: as many as 512 threads and
