@@ -280,6 +280,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- b200 arm
+def _traffic_of(workload):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu capture (None if not captured)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp)).get(workload)
+    except Exception:
+        return None
+
+
 def run_b200(args, w):
     import torch
     import torch.distributed as dist
@@ -513,13 +522,7 @@ def run_b200(args, w):
         bpf = algorithmic_bytes_per_frame(w)
         peak, peak_src = measured_hbm_peak()
         achieved = bpf * frames / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(args.workload)
-            except Exception:
-                traffic = None
+        traffic = _traffic_of(args.workload)
         line = {
             "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -662,7 +665,7 @@ def run_b200_c2c(args, w):
                        "parallelism": f"replicas x{world}"},
             "hbm_gbs": fps * bpf / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": _traffic_of(args.workload), "peak_source": peak_src,
                          "kernel": "r2c_kernel (MD_CPLX)" if real_in else "bigfft_pass(_tma)_kernel (all passes of a transform)",
                          "algorithmic_bytes_per_frame": bpf, "kernel_ms": step_ms},
             "cpu_baseline": cpu_baseline,
