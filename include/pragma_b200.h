@@ -107,12 +107,15 @@ int pdsp_fft_shift(pdsp_ctx* ctx, const double* input, int64_t n, double* out);
  * (src/public/spectrum.ts:107-142, src/effect/index.ts:143-194).  Outputs are in the plan's
  * precision (float for PDSP_F32, double for PDSP_F64), dense rows of `bins` = N/2+1 (one) or N
  * (two) per frame; amplitude / phase / peaks may each be NULL. peaks points to pdsp_peak_f32[batch]
- * or pdsp_peak_f64[batch]. */
+ * or pdsp_peak_f64[batch].  FFT sizes up to 16384 run as one fused kernel; larger sizes (up to 2^28) run as
+ * frame-build + multi-pass transform + epilogue kernels with the same results. */
 int pdsp_spectrum(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* samples, void* amplitude,
                   void* phase, void* peaks);
 
 /* ---- device-resident variants: pointers are device memory, work is enqueued on `stream`
- *      (a cudaStream_t passed as void*; NULL = the context's stream) ------------------------- */
+ *      (a cudaStream_t passed as void*; NULL = the context's stream).  Scratch planes of the large
+ *      transforms are kept per (plan, stream): calls on different streams may overlap, calls on one
+ *      stream are ordered by it. ------------------------------------------------------------- */
 int pdsp_spectrum_dev(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* d_samples, void* d_amplitude,
                       void* d_phase, void* d_peaks, void* stream);
 /* Frame-sharded multi-GPU form (BASELINE config C5; no reference counterpart - the reference is

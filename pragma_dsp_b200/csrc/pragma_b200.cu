@@ -166,6 +166,87 @@ PDSP_GLOBAL void k_r2c_n1(const R2CParams p) {
     }
   }
 }
+
+// ---- spectrum() for FFT sizes beyond one CTA (N > 16384): buildFrame + applyWindow into a dense plane, the
+// multi-pass transform, then this epilogue over the full complex spectrum (src/public/spectrum.ts:107-142).
+template <typename T, typename S>
+PDSP_GLOBAL void k_build_frames(const S* PDSP_RESTRICT s, long long hop, int frame_len, const T* PDSP_RESTRICT win, int n,
+                                long long batch, T* PDSP_RESTRICT out) {
+  const long long stride = (long long)simt::nblocks() * simt::nthreads();
+  const long long total = batch * (long long)n;
+  for (long long i = simt::bid() * (long long)simt::nthreads() + simt::tid(); i < total; i += stride) {
+    const long long f = i / n;
+    const int e = (int)(i - f * n);
+    T x = e < frame_len ? (T)s[f * hop + e] : (T)0;  // buildFrame: truncate / zero-pad (spectrum.ts:36-43)
+    if (win != nullptr) x *= win[e];                 // applyWindow (fourier.ts:54-67)
+    out[i] = x;
+  }
+}
+
+// One CTA per frame: amplitude scaling (spectrum.ts:45-72), phase, findPeak (:74-105) with its first-of-equals rule.
+template <typename T>
+PDSP_GLOBAL void k_big_epilogue(const T* PDSP_RESTRICT re, const T* PDSP_RESTRICT im, int n, int bins, T s_edge, T s_mid,
+                                int one_sided, double bin_hz, long long batch, T* PDSP_RESTRICT amp, T* PDSP_RESTRICT phase,
+                                PeakRec<T>* PDSP_RESTRICT peaks) {
+  T* sv = reinterpret_cast<T*>(simt::smem());                         // per-warp best value
+  int* sk = reinterpret_cast<int*>(simt::smem() + 32 * sizeof(T));    // per-warp best bin
+  const int tid = simt::tid(), nth = simt::nthreads();
+  const int half = n / 2;
+  for (long long f = simt::bid(); f < batch; f += simt::nblocks()) {
+    const T* fre = re + f * (long long)n;
+    const T* fim = im + f * (long long)n;
+    T bv = (T)0;
+    int bk = 0;
+    for (int k = tid; k < bins; k += nth) {
+      const T xr = fre[k];
+      // DC and Nyquist of a real frame are real; the reference's imaginary parts there are sums of +0
+      const T xi = (k == 0 || k == half) ? (T)0 : fim[k];
+      const T scale = (one_sided && (k == 0 || k == half)) ? s_edge : s_mid;
+      const T a = (T)hypot((double)xr, (double)xi) * scale;
+      if (amp != nullptr) amp[f * (long long)bins + k] = a;
+      if (phase != nullptr) phase[f * (long long)bins + k] = fast_atan2(xi, xr);
+      if (k >= 1 && a > bv) {  // k ascends within a thread: strict '>' keeps the first of equal values
+        bv = a;
+        bk = k;
+      }
+    }
+    if (peaks != nullptr) {
+      for (int m = 16; m >= 1; m >>= 1) {
+        const T ov = simt::shfl_xor(bv, m, 32);
+        const int ok = simt::shfl_xor(bk, m, 32);
+        if (ok != 0 && (bk == 0 || peak_better(ov, ok, bv, bk))) {
+          bv = ov;
+          bk = ok;
+        }
+      }
+      if ((tid & 31) == 0) {
+        sv[tid >> 5] = bv;
+        sk[tid >> 5] = bk;
+      }
+      simt::sync_block();
+      if (tid == 0) {
+        for (int w = 1; w < (nth + 31) / 32; ++w) {
+          if (sk[w] != 0 && (bk == 0 || peak_better(sv[w], sk[w], bv, bk))) {
+            bv = sv[w];
+            bk = sk[w];
+          }
+        }
+        // no non-DC bin above zero: findPeak falls back to the DC bin
+        const T xr = fre[bk];
+        const T xi = (bk == 0 || bk == half) ? (T)0 : fim[bk];
+        const T scale = (one_sided && (bk == 0 || bk == half)) ? s_edge : s_mid;
+        PeakRec<T> r;
+        memset(&r, 0, sizeof(r));
+        r.index = bk;
+        r.frequency = (T)((double)bk * bin_hz);
+        r.amplitude = (T)hypot((double)xr, (double)xi) * scale;
+        r.phase = fast_atan2(xi, xr);
+        peaks[f] = r;
+      }
+      simt::sync_block();
+    }
+  }
+}
 }  // namespace pdsp
 
 using namespace pdsp;
@@ -231,10 +312,20 @@ struct BigPlan {
   void* tw_hi[2] = {nullptr, nullptr};               // two-level inter-pass twiddles of passes 0 and 1
   void* tw_lo[2] = {nullptr, nullptr};
   int log_b[2] = {0, 0};
-  void* work_re = nullptr;  // intermediate planes, work_frames * N elements each
-  void* work_im = nullptr;
-  long long work_frames = 0;
-  bool work_interleaved = false;  // work_re alone holds cx<T> elements (PDSP_BIG_INTERLEAVE=1)
+  // Intermediate planes between the passes, ONE SET PER STREAM: the host pipeline runs neighbouring chunks
+  // on different streams, and passes of two transforms sharing a work buffer would overwrite each other.
+  struct Work {
+    void* re = nullptr;  // frames * N elements (2x when interleaved: cx<T> elements, `im` unused)
+    void* im = nullptr;
+    long long frames = 0;
+    bool interleaved = false;
+    // large-N spectrum(): windowed frames and their full complex spectra (spec_frames transforms each)
+    void* spec_x = nullptr;
+    void* spec_re = nullptr;
+    void* spec_im = nullptr;
+    long long spec_frames = 0;
+  };
+  std::map<cudaStream_t, Work> work;
 };
 
 struct pdsp_plan {
@@ -462,6 +553,12 @@ struct PeerSpec {
   long long offset;
 };
 
+struct BigPlan;
+static int big_plan(pdsp_plan* pl, BigPlan** out);
+static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
+                      int inverse, cudaStream_t st);
+static int launch_spectrum_big(pdsp_plan* pl, const R2CParams& p, long long batch, cudaStream_t st);
+
 static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, long long batch,
                            void* d_amp, void* d_phase, void* d_peaks, void* d_cre, void* d_cim, int cfull,
                            cudaStream_t st, const PeerSpec* peers = nullptr) {
@@ -504,6 +601,20 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
   {
     const char* pf = getenv("PDSP_L2_PREFETCH");
     p.l2_prefetch = (pf && pf[0] == '1') ? 1 : 0;
+  }
+  {
+    // beyond one CTA (or forced by the PDSP_BIG_FACTORS test hook): window -> multi-pass transform -> epilogue
+    bool big = pl->log2n - 1 > kMaxLog2M;
+    if (!big && n > 1 && getenv("PDSP_BIG_FACTORS")) {
+      BigPlan* bp = nullptr;
+      if (big_plan(pl, &bp)) return 1;
+      big = bp != nullptr;
+    }
+    if (big) {
+      if (d_cre) return fail("internal: complex output of a large real transform goes through launch_c2c");
+      if (peers && peers->n > 0) return fail("pdsp_spectrum_dev_gather is limited to FFT sizes up to %d", 2 << kMaxLog2M);
+      return launch_spectrum_big(pl, p, batch, st);
+    }
   }
   LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   cudaError_t e;
@@ -664,21 +775,22 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
+  BigPlan::Work* wk = nullptr;
   {
     std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
     const bool want_il = big_interleave();
-    if (bp->work_frames < chunk || bp->work_interleaved != want_il) {
+    wk = &bp->work[st];  // std::map nodes are stable: the pointer outlives the lock
+    if (wk->frames < chunk || wk->interleaved != want_il) {
       CU(cudaStreamSynchronize(st));
-      CU(cudaFree(bp->work_re));
-      CU(cudaFree(bp->work_im));
-      bp->work_re = bp->work_im = nullptr;
-      // work_re alone, twice the size, when the passes exchange interleaved cx<T> elements (default); two planar
+      CU(cudaFree(wk->re));
+      CU(cudaFree(wk->im));
+      wk->re = wk->im = nullptr;
+      // `re` alone, twice the size, when the passes exchange interleaved cx<T> elements (default); two planar
       // work planes with PDSP_BIG_INTERLEAVE=0
-      const bool il = want_il;
-      CU(cudaMalloc(&bp->work_re, (il ? 2 : 1) * es * (size_t)N * (size_t)chunk));
-      if (!il) CU(cudaMalloc(&bp->work_im, es * (size_t)N * (size_t)chunk));
-      bp->work_interleaved = il;
-      bp->work_frames = chunk;
+      CU(cudaMalloc(&wk->re, (want_il ? 2 : 1) * es * (size_t)N * (size_t)chunk));
+      if (!want_il) CU(cudaMalloc(&wk->im, es * (size_t)N * (size_t)chunk));
+      wk->interleaved = want_il;
+      wk->frames = chunk;
     }
   }
   for (long long f0 = 0; f0 < batch; f0 += chunk) {
@@ -695,11 +807,11 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       const bool last = j == np - 1;
       BigPassParams p;
       memset(&p, 0, sizeof p);
-      const bool interleave = big_interleave();
-      p.in_re = j == 0 ? (const void*)fre : bp->work_re;
-      p.in_im = j == 0 ? (const void*)fim : (interleave ? nullptr : bp->work_im);
-      p.out_re = last ? (void*)gre : bp->work_re;
-      p.out_im = last ? (void*)gim : (interleave ? nullptr : bp->work_im);
+      const bool interleave = wk->interleaved;
+      p.in_re = j == 0 ? (const void*)fre : wk->re;
+      p.in_im = j == 0 ? (const void*)fim : (interleave ? nullptr : wk->im);
+      p.out_re = last ? (void*)gre : wk->re;
+      p.out_im = last ? (void*)gim : (interleave ? nullptr : wk->im);
       p.in_cplx = (interleave && j != 0) ? 1 : 0;
       p.out_cplx = (interleave && !last) ? 1 : 0;
       p.n_frames = nf;
@@ -799,6 +911,82 @@ static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long lo
   cudaError_t e = dispatch_c2c(pl->precision == PDSP_F64, pl->log2n, p, lc);
   if (e != cudaSuccess) return fail("c2c launch (n=%d): %s", pl->n, cudaGetErrorString(e));
   c->launches++;
+  return 0;
+}
+
+// spectrum() of frames longer than one CTA can hold.  Frames are processed in sub-batches through per-stream
+// scratch planes (windowed frames, full complex spectra).
+static int launch_spectrum_big(pdsp_plan* pl, const R2CParams& p, long long batch, cudaStream_t st) {
+  pdsp_ctx* c = pl->ctx;
+  BigPlan* bp = nullptr;
+  if (big_plan(pl, &bp)) return 1;
+  if (!bp) return fail("internal: no multi-pass plan for n=%d", pl->n);
+  const int n = pl->n;
+  const size_t es = esize(pl->precision);
+  long long sub = (1LL << 24) / n;  // <= 2^24 elements per scratch plane
+  if (sub < 1) sub = 1;
+  if (sub > batch) sub = batch;
+  BigPlan::Work* wk = nullptr;
+  {
+    std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
+    wk = &bp->work[st];
+    if (wk->spec_frames < sub) {
+      CU(cudaStreamSynchronize(st));
+      CU(cudaFree(wk->spec_x));
+      CU(cudaFree(wk->spec_re));
+      CU(cudaFree(wk->spec_im));
+      wk->spec_x = wk->spec_re = wk->spec_im = nullptr;
+      wk->spec_frames = 0;
+      CU(cudaMalloc(&wk->spec_x, es * (size_t)n * (size_t)sub));
+      CU(cudaMalloc(&wk->spec_re, es * (size_t)n * (size_t)sub));
+      CU(cudaMalloc(&wk->spec_im, es * (size_t)n * (size_t)sub));
+      wk->spec_frames = sub;
+    }
+  }
+  const int bins = p.two_sided ? n : n / 2 + 1;
+  const size_t ses = p.sample_dtype == DT_F64 ? 8 : 4;
+  const size_t pk = pl->precision == PDSP_F64 ? sizeof(PeakRec<double>) : sizeof(PeakRec<float>);
+  const int threads = 256;
+  for (long long f0 = 0; f0 < batch; f0 += sub) {
+    const long long nf = batch - f0 < sub ? batch - f0 : sub;
+    const char* src = static_cast<const char*>(p.samples) + (size_t)f0 * (size_t)p.hop * ses;
+    long long blocks = (nf * (long long)n + threads - 1) / threads;
+    if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+    if (pl->precision == PDSP_F64) {
+      if (p.sample_dtype == DT_F64)
+        PDSP_LAUNCH((k_build_frames<double, double>), (int)blocks, threads, 0, st, reinterpret_cast<const double*>(src), p.hop,
+                    p.frame_len, static_cast<const double*>(p.window), n, nf, static_cast<double*>(wk->spec_x));
+      else
+        PDSP_LAUNCH((k_build_frames<double, float>), (int)blocks, threads, 0, st, reinterpret_cast<const float*>(src), p.hop,
+                    p.frame_len, static_cast<const double*>(p.window), n, nf, static_cast<double*>(wk->spec_x));
+    } else {
+      if (p.sample_dtype == DT_F64)
+        PDSP_LAUNCH((k_build_frames<float, double>), (int)blocks, threads, 0, st, reinterpret_cast<const double*>(src), p.hop,
+                    p.frame_len, static_cast<const float*>(p.window), n, nf, static_cast<float*>(wk->spec_x));
+      else
+        PDSP_LAUNCH((k_build_frames<float, float>), (int)blocks, threads, 0, st, reinterpret_cast<const float*>(src), p.hop,
+                    p.frame_len, static_cast<const float*>(p.window), n, nf, static_cast<float*>(wk->spec_x));
+    }
+    CU(cudaGetLastError());
+    c->launches++;
+    if (launch_c2c(pl, wk->spec_x, nullptr, nf, wk->spec_re, wk->spec_im, 0, st)) return 1;
+    long long eb = nf < (long long)c->sm_count * 8 ? nf : (long long)c->sm_count * 8;
+    const size_t smem = 32 * 8 + 32 * sizeof(int);
+    char* amp = p.amp ? static_cast<char*>(p.amp) + (size_t)f0 * bins * es : nullptr;
+    char* ph = p.phase ? static_cast<char*>(p.phase) + (size_t)f0 * bins * es : nullptr;
+    char* pkp = p.peaks ? static_cast<char*>(p.peaks) + (size_t)f0 * pk : nullptr;
+    if (pl->precision == PDSP_F64)
+      PDSP_LAUNCH(k_big_epilogue<double>, (int)eb, threads, smem, st, static_cast<const double*>(wk->spec_re),
+                  static_cast<const double*>(wk->spec_im), n, bins, p.scale_edge, p.scale_mid, p.two_sided ? 0 : 1, p.bin_hz, nf,
+                  reinterpret_cast<double*>(amp), reinterpret_cast<double*>(ph), reinterpret_cast<PeakRec<double>*>(pkp));
+    else
+      PDSP_LAUNCH(k_big_epilogue<float>, (int)eb, threads, smem, st, static_cast<const float*>(wk->spec_re),
+                  static_cast<const float*>(wk->spec_im), n, bins, (float)p.scale_edge, (float)p.scale_mid,
+                  p.two_sided ? 0 : 1, p.bin_hz, nf, reinterpret_cast<float*>(amp), reinterpret_cast<float*>(ph),
+                  reinterpret_cast<PeakRec<float>*>(pkp));
+    CU(cudaGetLastError());
+    c->launches++;
+  }
   return 0;
 }
 
@@ -931,8 +1119,13 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
         cudaFree(pl->big->tw_hi[i]);
         cudaFree(pl->big->tw_lo[i]);
       }
-      cudaFree(pl->big->work_re);
-      cudaFree(pl->big->work_im);
+      for (auto& kv : pl->big->work) {
+        cudaFree(kv.second.re);
+        cudaFree(kv.second.im);
+        cudaFree(kv.second.spec_x);
+        cudaFree(kv.second.spec_re);
+        cudaFree(kv.second.spec_im);
+      }
       delete pl->big;
     }
     delete pl;
@@ -1023,8 +1216,6 @@ PDSP_EXPORT int pdsp_plan_precision(const pdsp_plan* p) { return p ? p->precisio
 
 static int check_desc(const pdsp_plan* pl, const pdsp_spectrum_desc* d) {
   if (!pl || !d) return fail("null argument");
-  if (pl->log2n - 1 > kMaxLog2M)
-    return fail("spectrum() is fused for FFT sizes up to %d; use the transform entry points for larger sizes", 2 << kMaxLog2M);
   if (d->batch < 0) return fail("negative batch");
   if (d->frame_len < 0) return fail("negative frame length");
   if (d->hop < 0) return fail("negative hop");

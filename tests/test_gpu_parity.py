@@ -370,3 +370,29 @@ def test_device_resident_fft_convolution(ctx):
     st.synchronize()
     refp = 0.5 * np.fft.fft(a.cpu().numpy(), axis=1) * np.conj(np.fft.fft(b.cpu().numpy(), axis=1))
     assert np.abs(pre.cpu().numpy() - refp.real).max() <= 1e-9 and np.abs(pim.cpu().numpy() - refp.imag).max() <= 1e-9
+
+
+@pytest.mark.parametrize("log2n,precision", [(15, "f64"), (17, "f64"), (20, "f64"), (16, "f32")])
+def test_large_spectrum_matches_oracle(ctx, log2n, precision):
+    """spectrum() for FFT sizes beyond the fused single-CTA kernel (N > 16384): buildFrame + window kernel,
+    multi-pass transform, epilogue kernel with findPeak.  Amplitude, phase and the peak record against the oracle,
+    including a zero-padded frame length and a silent frame."""
+    from pragma_dsp_b200 import spectrum_batch
+    n = 1 << log2n
+    batch = 3 if log2n <= 17 else 2
+    rng = np.random.default_rng(log2n)
+    flen = n - 1234
+    dt = np.float64 if precision == "f64" else np.float32
+    x = multitone(rng, batch, flen).astype(dt)
+    x[batch - 1] = 0.0
+    got = spectrum_batch(x, sampleRate=96000.0, fftSize=n, window="blackman", precision=precision)
+    ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=96000.0, window="blackman", threads=8)
+    atol = 1e-12 if precision == "f64" else 3e-6
+    assert got["amplitude"].shape == (batch, n // 2 + 1)
+    assert np.abs(got["amplitude"] - ref["amplitude"]).max() <= atol
+    assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+    assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= atol
+    assert np.abs(got["peaks"]["frequency"] - ref["peaks"]["frequency"]).max() <= (1e-9 if precision == "f64" else 1e-2)
+    strong = ref["amplitude"] > (1e-6 if precision == "f64" else 1e-3)
+    d = np.abs(got["phase"] - ref["phase"])
+    assert np.minimum(d, np.abs(d - 2 * np.pi))[strong].max() <= (1e-7 if precision == "f64" else 2e-2)

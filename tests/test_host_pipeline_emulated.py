@@ -197,6 +197,38 @@ def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n, env):
             assert np.linalg.norm((out.real + 1j * out.imag) - refr) / np.linalg.norm(refr) <= tol
 
 
+@pytest.mark.parametrize("sides,frame_len", [("one", 4096), ("two", 4096), ("one", 3000)])
+def test_large_spectrum_path_emulated(emu_api, monkeypatch, sides, frame_len):
+    """spectrum() beyond one CTA (N > 16384 on the device): window -> multi-pass transform -> epilogue kernel with
+    findPeak.  Forced onto N=4096 with PDSP_BIG_FACTORS so the emulator can run it; compared with the oracle."""
+    from pragma_dsp_b200 import spectrum_batch
+    monkeypatch.setenv("PDSP_BIG_FACTORS", "6,6")
+    rng = np.random.default_rng(11)
+    n, batch = 4096, 3
+    x = multitone(rng, batch, frame_len)
+    x[2] = 0.0  # a silent frame: findPeak falls back to the DC bin
+    for window in ("hann", "rect"):
+        got = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window=window, sides=sides)
+        ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window=window, sides=sides)
+        assert got["amplitude"].shape == ref["amplitude"].shape
+        assert np.abs(got["amplitude"] - ref["amplitude"]).max() <= 1e-12
+        if sides == "one":  # two-sided mirrored bins tie to the last bit: the index may be k or N-k
+            assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+        else:
+            gi, ri = got["peaks"]["index"], ref["peaks"]["index"]
+            assert ((gi == ri) | (gi == n - ri)).all()
+        assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= 1e-12
+        d = np.abs(got["phase"] - ref["phase"])
+        assert np.minimum(d, np.abs(d - 2 * np.pi))[ref["amplitude"] > 1e-6].max() <= 1e-8
+    # peaks only, fp32 plan
+    got = spectrum_batch(x.astype(np.float32), sampleRate=48000.0, fftSize=n, window="hann", sides=sides, precision="f32",
+                         outputs=("peak",))
+    ref = oracle.spectrum_batch(x.astype(np.float32), fftSize=n, sampleRate=48000.0, window="hann", sides=sides)
+    if sides == "one":
+        assert (got["peaks"]["index"] == ref["peaks"]["index"]).all()
+    assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= 2e-6
+
+
 def test_fused_peer_scatter_emulated(emu_api):
     """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
     from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
