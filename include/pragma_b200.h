@@ -53,7 +53,8 @@ typedef struct {
   int32_t sides;         /* pdsp_sides */
   double sample_rate;    /* > 0 */
   int32_t raw_magnitude; /* 1: amplitude output is the unscaled |X| (magnitude(), xform/fourier.ts:98-109) */
-  int32_t _reserved;
+  int32_t fft_shift;     /* 1 (two-sided only): rows are stored fftShift-ed, bin k at (k + N/2) mod N - fftShift
+                            (src/xform/fourier.ts:122-134) fused into the store; peak.index stays the unshifted bin */
 } pdsp_spectrum_desc;
 
 /* ---- library / context ------------------------------------------------------------------ */

@@ -187,6 +187,7 @@ napi_value Spectrum(napi_env env, napi_callback_info info) {
   d.sides = get_i32(env, argv[2], "sides", PDSP_SIDES_ONE);
   d.sample_rate = get_f64(env, argv[2], "sampleRate", 1.0);
   d.raw_magnitude = get_i32(env, argv[2], "rawMagnitude", 0);
+  d.fft_shift = get_i32(env, argv[2], "shift", 0);
   if (d.batch > 0 && d.frame_len > 0 && (size_t)((d.batch - 1) * d.hop + d.frame_len) > s.length)
     return fail(env, "pragma-dsp/b200: frames exceed the samples buffer");
   pdsp_plan* plan = static_cast<pdsp_plan*>(p);

@@ -24,7 +24,7 @@ PEAK_F32 = np.dtype([("index", "<i4"), ("frequency", "<f4"), ("amplitude", "<f4"
 class SpectrumDesc(C.Structure):
     _fields_ = [("sample_dtype", C.c_int32), ("frame_len", C.c_int32), ("hop", C.c_int64), ("batch", C.c_int64),
                 ("window", C.c_int32), ("sides", C.c_int32), ("sample_rate", C.c_double),
-                ("raw_magnitude", C.c_int32), ("_reserved", C.c_int32)]
+                ("raw_magnitude", C.c_int32), ("fft_shift", C.c_int32)]
 
 
 class PragmaB200Error(RuntimeError):

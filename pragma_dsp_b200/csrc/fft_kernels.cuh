@@ -49,6 +49,7 @@ struct R2CParams {
   void* phase;   // atan2(im, re); pitch = bins
   void* peaks;   // PeakRec<T>[batch]
   int two_sided;      // bins = N (mirror bins written) else N/2+1
+  int shift;          // two-sided rows are stored fftShift-ed: bin k lands at (k + N/2) mod N (fourier.ts:122-134)
   double scale_edge;  // amplitude scale of DC and Nyquist
   double scale_mid;   // amplitude scale of every other bin
   double bin_hz;      // sampleRate / N
@@ -312,6 +313,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const bool two_sided = GEN ? p.two_sided != 0 : false;
   const bool cfull = GEN ? p.cfull != 0 : true;
   const int bins = two_sided ? N : M + 1;
+  const int sh = (two_sided && p.shift) ? M : 0;  // fftShift fused into the two-sided stores (row rotation by N/2)
   const int cbins = cfull ? N : M + 1;
   const T s_edge = (T)p.scale_edge, s_mid = (T)p.scale_mid;
   [[maybe_unused]] const T edge_key = (T)((p.scale_edge / p.scale_mid) * (p.scale_edge / p.scale_mid));
@@ -488,8 +490,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
             a = mag * scale;
           }
           if (want_amp && o_amp != nullptr) {
-            (o_amp + b0)[OFF] = a;
-            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_amp + m0)[-OFF] = a;
+            (o_amp + b0 + ((EDGE && k == M) ? -sh : sh))[OFF] = a;  // shifted: k < M -> k + M, the Nyquist bin M -> 0
+            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_amp + m0 - sh)[-OFF] = a;
           }
           if (want_peak) {
             bool is_dc = false;
@@ -506,8 +508,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         }
         if constexpr (PHASE) {
           if (want_phase && o_ph != nullptr) {
-            (o_ph + b0)[OFF] = ph;
-            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_ph + m0)[-OFF] = -ph;
+            (o_ph + b0 + ((EDGE && k == M) ? -sh : sh))[OFF] = ph;
+            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_ph + m0 - sh)[-OFF] = -ph;
           }
         }
       };

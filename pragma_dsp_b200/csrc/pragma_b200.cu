@@ -186,8 +186,8 @@ PDSP_GLOBAL void k_build_frames(const S* PDSP_RESTRICT s, long long hop, int fra
 // One CTA per frame: amplitude scaling (spectrum.ts:45-72), phase, findPeak (:74-105) with its first-of-equals rule.
 template <typename T>
 PDSP_GLOBAL void k_big_epilogue(const T* PDSP_RESTRICT re, const T* PDSP_RESTRICT im, int n, int bins, T s_edge, T s_mid,
-                                int one_sided, double bin_hz, long long batch, T* PDSP_RESTRICT amp, T* PDSP_RESTRICT phase,
-                                PeakRec<T>* PDSP_RESTRICT peaks) {
+                                int one_sided, int shift, double bin_hz, long long batch, T* PDSP_RESTRICT amp,
+                                T* PDSP_RESTRICT phase, PeakRec<T>* PDSP_RESTRICT peaks) {
   T* sv = reinterpret_cast<T*>(simt::smem());                         // per-warp best value
   int* sk = reinterpret_cast<int*>(simt::smem() + 32 * sizeof(T));    // per-warp best bin
   const int tid = simt::tid(), nth = simt::nthreads();
@@ -203,8 +203,9 @@ PDSP_GLOBAL void k_big_epilogue(const T* PDSP_RESTRICT re, const T* PDSP_RESTRIC
       const T xi = (k == 0 || k == half) ? (T)0 : fim[k];
       const T scale = (one_sided && (k == 0 || k == half)) ? s_edge : s_mid;
       const T a = (T)hypot((double)xr, (double)xi) * scale;
-      if (amp != nullptr) amp[f * (long long)bins + k] = a;
-      if (phase != nullptr) phase[f * (long long)bins + k] = fast_atan2(xi, xr);
+      const int ks = shift ? ((k + half) & (n - 1)) : k;  // fftShift fused into the store (two-sided rows)
+      if (amp != nullptr) amp[f * (long long)bins + ks] = a;
+      if (phase != nullptr) phase[f * (long long)bins + ks] = fast_atan2(xi, xr);
       if (k >= 1 && a > bv) {  // k ascends within a thread: strict '>' keeps the first of equal values
         bv = a;
         bk = k;
@@ -589,6 +590,7 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     p.peer_offset = peers->offset;
   }
   p.two_sided = d->sides == PDSP_SIDES_TWO;
+  p.shift = (p.two_sided && d->fft_shift) ? 1 : 0;
   if (d->raw_magnitude) {
     p.scale_edge = p.scale_mid = 1.0;
   } else if (p.two_sided) {
@@ -977,12 +979,12 @@ static int launch_spectrum_big(pdsp_plan* pl, const R2CParams& p, long long batc
     char* pkp = p.peaks ? static_cast<char*>(p.peaks) + (size_t)f0 * pk : nullptr;
     if (pl->precision == PDSP_F64)
       PDSP_LAUNCH(k_big_epilogue<double>, (int)eb, threads, smem, st, static_cast<const double*>(wk->spec_re),
-                  static_cast<const double*>(wk->spec_im), n, bins, p.scale_edge, p.scale_mid, p.two_sided ? 0 : 1, p.bin_hz, nf,
+                  static_cast<const double*>(wk->spec_im), n, bins, p.scale_edge, p.scale_mid, p.two_sided ? 0 : 1, p.shift, p.bin_hz, nf,
                   reinterpret_cast<double*>(amp), reinterpret_cast<double*>(ph), reinterpret_cast<PeakRec<double>*>(pkp));
     else
       PDSP_LAUNCH(k_big_epilogue<float>, (int)eb, threads, smem, st, static_cast<const float*>(wk->spec_re),
                   static_cast<const float*>(wk->spec_im), n, bins, (float)p.scale_edge, (float)p.scale_mid,
-                  p.two_sided ? 0 : 1, p.bin_hz, nf, reinterpret_cast<float*>(amp), reinterpret_cast<float*>(ph),
+                  p.two_sided ? 0 : 1, p.shift, p.bin_hz, nf, reinterpret_cast<float*>(amp), reinterpret_cast<float*>(ph),
                   reinterpret_cast<PeakRec<float>*>(pkp));
     CU(cudaGetLastError());
     c->launches++;
@@ -1223,6 +1225,8 @@ static int check_desc(const pdsp_plan* pl, const pdsp_spectrum_desc* d) {
   if (d->window < 0 || d->window > 3) return fail("Unsupported window type: %d", d->window);
   if (d->sides != PDSP_SIDES_ONE && d->sides != PDSP_SIDES_TWO) return fail("unknown sides %d", d->sides);
   if (d->sample_dtype != PDSP_F32 && d->sample_dtype != PDSP_F64) return fail("unknown sample dtype %d", d->sample_dtype);
+  if (d->fft_shift != 0 && d->fft_shift != 1) return fail("fft_shift must be 0 or 1, got %d", d->fft_shift);
+  if (d->fft_shift && d->sides != PDSP_SIDES_TWO) return fail("fft_shift applies to two-sided spectra only");
   return 0;
 }
 

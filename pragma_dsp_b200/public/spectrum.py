@@ -25,10 +25,13 @@ def _precision(p):
 
 def spectrum_batch(samples, *, sampleRate: float = 1, fftSize: int | None = None, window: str = "rect",
                    sides: str = "one", frameLen: int | None = None, hop: int | None = None, batch: int | None = None,
-                   precision="f64", outputs=("amplitude", "phase", "peak"), raw_magnitude=False, context=None):
+                   precision="f64", outputs=("amplitude", "phase", "peak"), raw_magnitude=False, shift=False,
+                   context=None):
     """Batched spectrum(): `samples` is (batch, frameLen), or 1-D with frameLen/hop/batch (STFT view).
 
-    Returns dict(frequencies, amplitude, phase, peaks) with arrays in the plan precision."""
+    Returns dict(frequencies, amplitude, phase, peaks) with arrays in the plan precision.  shift=True (two-sided
+    only) stores the amplitude / phase rows fftShift-ed - fftShift(amplitude) of src/xform/fourier.ts:122-134 fused
+    into the kernel's stores; `frequencies` is left as binFrequencies() returns it and peak.index is the unshifted bin."""
     ctx = context or _lib.default_context()
     x = _as_samples(samples)
     if x.ndim == 2:
@@ -57,7 +60,7 @@ def spectrum_batch(samples, *, sampleRate: float = 1, fftSize: int | None = None
     peaks = np.zeros(batch, dtype=PEAK_F64 if prec == F64 else PEAK_F32) if "peak" in outputs else None
     d = SpectrumDesc(sample_dtype=F64 if x.dtype == np.float64 else F32, frame_len=int(frameLen), hop=int(hop),
                      batch=int(batch), window=WINDOWS[window], sides=SIDES[sides], sample_rate=float(sampleRate),
-                     raw_magnitude=int(bool(raw_magnitude)))
+                     raw_magnitude=int(bool(raw_magnitude)), fft_shift=int(bool(shift)))
     check(lib().pdsp_spectrum(plan, C.byref(d), ptr(x) if x.size else None, ptr(amp), ptr(ph), ptr(peaks)))
     return {"frequencies": binFrequencies(size, sampleRate, sides), "amplitude": amp, "phase": ph, "peaks": peaks}
 

@@ -21,7 +21,7 @@ class R2CParams(C.Structure):
     _fields_ = [("samples", C.c_void_p), ("sample_dtype", C.c_int), ("vec_ok", C.c_int), ("frame_len", C.c_int),
                 ("hop", C.c_longlong), ("batch", C.c_longlong), ("window", C.c_void_p), ("tw", C.c_void_p),
                 ("post", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p), ("cfull", C.c_int),
-                ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int),
+                ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int), ("shift", C.c_int),
                 ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double),
                 ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong),
                 ("winphase", C.c_void_p), ("win_a0", C.c_double), ("win_a1", C.c_double), ("win_a2", C.c_double),

@@ -396,3 +396,18 @@ def test_large_spectrum_matches_oracle(ctx, log2n, precision):
     strong = ref["amplitude"] > (1e-6 if precision == "f64" else 1e-3)
     d = np.abs(got["phase"] - ref["phase"])
     assert np.minimum(d, np.abs(d - 2 * np.pi))[strong].max() <= (1e-7 if precision == "f64" else 2e-2)
+
+
+@pytest.mark.parametrize("n", [2, 4, 64, 1024, 8192, 1 << 15])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_fused_fftshift_equals_shift_after(ctx, n, precision):
+    """SURVEY 8f-3: desc.fft_shift stores two-sided amplitude / phase rows already fftShift-ed (fourier.ts:122-134);
+    bit-identical to shifting the unshifted rows afterwards; the peak record is unaffected."""
+    from pragma_dsp_b200 import spectrum_batch
+    rng = np.random.default_rng(n)
+    x = (multitone(rng, 5, n) if n >= 64 else rng.standard_normal((5, n))).astype(np.float64 if precision == "f64" else np.float32)
+    plain = spectrum_batch(x, sampleRate=8000.0, fftSize=n, window="hamming", sides="two", precision=precision)
+    fused = spectrum_batch(x, sampleRate=8000.0, fftSize=n, window="hamming", sides="two", precision=precision, shift=True)
+    assert np.array_equal(fused["amplitude"], np.fft.fftshift(plain["amplitude"], axes=1))
+    assert np.array_equal(fused["phase"], np.fft.fftshift(plain["phase"], axes=1))
+    assert (fused["peaks"] == plain["peaks"]).all()

@@ -229,6 +229,30 @@ def test_large_spectrum_path_emulated(emu_api, monkeypatch, sides, frame_len):
     assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= 2e-6
 
 
+def test_fused_fftshift_two_sided_emulated(emu_api, monkeypatch):
+    """fftShift fused into the two-sided stores (desc.fft_shift) equals fftShift() applied afterwards,
+    in the fused single-CTA kernel and in the large-N epilogue; one-sided + shift is rejected."""
+    from pragma_dsp_b200 import spectrum_batch
+    from pragma_dsp_b200.xform import fftShift
+    rng = np.random.default_rng(12)
+    for n in (2, 8, 64, 1024):  # log2(N/2) = 0, 2, 5, 9: sizes the emulated library instantiates
+        x = multitone(rng, 3, n) if n >= 64 else rng.standard_normal((3, n))
+        plain = spectrum_batch(x, sampleRate=8000.0, fftSize=n, window="hann", sides="two")
+        fused = spectrum_batch(x, sampleRate=8000.0, fftSize=n, window="hann", sides="two", shift=True)
+        for f in range(3):
+            assert np.array_equal(fused["amplitude"][f], fftShift(plain["amplitude"][f])), n
+            assert np.array_equal(fused["phase"][f], fftShift(plain["phase"][f])), n
+        assert (fused["peaks"] == plain["peaks"]).all()
+    with pytest.raises(Exception, match="two-sided"):
+        spectrum_batch(multitone(rng, 1, 64), fftSize=64, sides="one", shift=True)
+    monkeypatch.setenv("PDSP_BIG_FACTORS", "6,6")
+    x = multitone(rng, 2, 4096)
+    plain = spectrum_batch(x, sampleRate=8000.0, fftSize=4096, sides="two")
+    fused = spectrum_batch(x, sampleRate=8000.0, fftSize=4096, sides="two", shift=True)
+    assert np.array_equal(fused["amplitude"], np.fft.fftshift(plain["amplitude"], axes=1))
+    assert np.array_equal(fused["phase"], np.fft.fftshift(plain["phase"], axes=1))
+
+
 def test_fused_peer_scatter_emulated(emu_api):
     """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
     from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
