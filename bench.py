@@ -485,6 +485,33 @@ def run_b200(args, w):
         e2e_s = float(tt[0])
     e2e_fps = frames * world * e2e_steps / e2e_s
 
+    # ---- ingestion ring: the same frames pushed in blocks of 256 from pageable memory, results
+    # popped in order - what a frame-at-a-time source (spectrumStream) sees; one host thread does the copies
+    ingest = None
+    if rank == 0 and world == 1 and not args.quick and hop == n:
+        from pragma_dsp_b200 import IngestRing
+        src = np.array(hx_np, copy=True)  # pageable, like a JS typed array
+        ring = IngestRing(n, sampleRate=48000.0, fftSize=n, window=w["window"], precision=w["prec"],
+                          sample_dtype=src.dtype, outputs=outs, framesPerChunk=4096, depth=3, context=ctx)
+
+        def ingest_pass():
+            pushed = popped = 0
+            while pushed < frames:
+                k = ring.push(src[pushed:pushed + 256])
+                pushed += k
+                if k == 0:
+                    popped += ring.pop(4096)["count"]
+            ring.flush()
+            while popped < frames:
+                popped += ring.pop(4096)["count"]
+        ingest_pass()
+        t0 = time.perf_counter()
+        ingest_pass()
+        ingest_s = time.perf_counter() - t0
+        ring.close()
+        ingest = {"value": frames / ingest_s, "unit": "frames/s", "api": "pdsp_ingest_push/pop, 256-frame pushes, pageable source",
+                  "frames_per_chunk": 4096, "depth": 3}
+
     # ---- parity spot check (outside every timed region): first 256 frames vs the oracle
     parity = None
     cpu_baseline = None
@@ -535,6 +562,7 @@ def run_b200(args, w):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "pdsp_spectrum (host pinned buffers)"},
+            "ingest": ingest,
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
             "parity": parity,

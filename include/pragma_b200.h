@@ -156,6 +156,23 @@ int pdsp_host_free(pdsp_ctx* ctx, void* h_ptr);
 int pdsp_memcpy_h2d(pdsp_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, void* stream);
 int pdsp_memcpy_d2h(pdsp_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, void* stream);
 
+/* ---- ingestion ring: spectrumStream (src/effect/index.ts:190-194) maps a stream of frames
+ *      1:1 and in order.  The ring batches them without the caller assembling batches: frames are copied
+ *      into a pinned chunk as they arrive, a full chunk goes out on its own stream (H2D, fused kernel, D2H)
+ *      while the next one fills, and results come back in arrival order.  desc->hop and desc->batch are
+ *      ignored (frames are frame_len samples, packed by the ring). ------------------------------------- */
+typedef struct pdsp_ingest pdsp_ingest;
+int pdsp_ingest_open(pdsp_plan* plan, const pdsp_spectrum_desc* desc, int want_amplitude, int want_phase, int want_peaks,
+                     int64_t frames_per_chunk, int depth, pdsp_ingest** ring);
+/* copies `count` frames, `stride` samples apart (0 = frame_len); *accepted < count means the ring is full */
+int pdsp_ingest_push(pdsp_ingest* ring, const void* frames, int64_t count, int64_t stride, int64_t* accepted);
+/* sends the partially filled chunk (end of stream / latency bound) */
+int pdsp_ingest_flush(pdsp_ingest* ring);
+/* up to max_frames finished frames, in arrival order, appended densely to the caller's arrays (NULL = skip);
+ * waits for chunks already sent, never for a partially filled one; *got may be 0 */
+int pdsp_ingest_pop(pdsp_ingest* ring, void* amplitude, void* phase, void* peaks, int64_t max_frames, int64_t* got);
+int pdsp_ingest_close(pdsp_ingest* ring);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,11 @@ SYMBOLS = {
     "pdsp_host_free": (C.c_int, [_vp, _vp]),
     "pdsp_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "pdsp_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "pdsp_ingest_open": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, C.c_int, C.POINTER(C.c_void_p)]),
+    "pdsp_ingest_push": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_i64)]),
+    "pdsp_ingest_flush": (C.c_int, [_vp]),
+    "pdsp_ingest_pop": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "pdsp_ingest_close": (C.c_int, [_vp]),
 }
 
 _lib = None

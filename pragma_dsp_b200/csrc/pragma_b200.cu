@@ -1566,3 +1566,201 @@ PDSP_EXPORT int pdsp_memcpy_d2h(pdsp_ctx* c, void* h, const void* d, size_t byte
   CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
   return 0;
 }
+
+// ------------------------------------------------------------------------------ ingestion ring
+// spectrumStream (src/effect/index.ts:190-194) maps a stream of frames 1:1, in order.  The ring turns that into
+// batched launches without the caller assembling batches: frames are copied into a pinned chunk as they arrive;
+// a full chunk is sent on its own stream (H2D -> fused kernel -> D2H into pinned memory) while the next chunk
+// fills; results are handed back in arrival order.
+struct IngestChunk {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  void* h_in = nullptr;   // pinned, cap frames
+  void* d_in = nullptr;
+  void* d_out = nullptr;  // [amplitude rows | phase rows | peak records], 256-byte aligned sections
+  void* h_out = nullptr;  // pinned mirror of d_out
+  long long frames = 0;   // frames copied in so far
+  long long popped = 0;   // frames already handed back
+  bool in_flight = false;
+};
+struct pdsp_ingest {
+  pdsp_plan* plan = nullptr;
+  pdsp_spectrum_desc desc;
+  long long cap = 0;
+  int want_amp = 0, want_phase = 0, want_peaks = 0;
+  size_t in_frame = 0, row = 0, pk = 0;        // bytes per frame: samples, one output row, one peak record
+  size_t a_off = 0, p_off = 0, k_off = 0, out_bytes = 0;
+  std::vector<IngestChunk> chunks;
+  int fill = 0;  // chunk receiving frames
+  int head = 0;  // oldest chunk with results not yet handed back
+  std::mutex mu;
+};
+
+static int ingest_submit(pdsp_ingest* g, IngestChunk& ch) {
+  if (ch.frames == 0 || ch.in_flight) return 0;
+  CU(cudaMemcpyAsync(ch.d_in, ch.h_in, (size_t)ch.frames * g->in_frame, cudaMemcpyHostToDevice, ch.stream));
+  pdsp_spectrum_desc d = g->desc;
+  d.batch = ch.frames;
+  char* dout = static_cast<char*>(ch.d_out);
+  if (launch_spectrum(g->plan, &d, ch.d_in, ch.frames, g->want_amp ? dout + g->a_off : nullptr,
+                      g->want_phase ? dout + g->p_off : nullptr, g->want_peaks ? dout + g->k_off : nullptr, nullptr, nullptr, 0,
+                      ch.stream))
+    return 1;
+  char* hout = static_cast<char*>(ch.h_out);
+  if (g->want_amp)
+    CU(cudaMemcpyAsync(hout + g->a_off, dout + g->a_off, (size_t)ch.frames * g->row, cudaMemcpyDeviceToHost, ch.stream));
+  if (g->want_phase)
+    CU(cudaMemcpyAsync(hout + g->p_off, dout + g->p_off, (size_t)ch.frames * g->row, cudaMemcpyDeviceToHost, ch.stream));
+  if (g->want_peaks)
+    CU(cudaMemcpyAsync(hout + g->k_off, dout + g->k_off, (size_t)ch.frames * g->pk, cudaMemcpyDeviceToHost, ch.stream));
+  CU(cudaEventRecord(ch.done, ch.stream));
+  ch.in_flight = true;
+  ch.popped = 0;
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_ingest_open(pdsp_plan* pl, const pdsp_spectrum_desc* d, int want_amplitude, int want_phase,
+                                 int want_peaks, int64_t frames_per_chunk, int depth, pdsp_ingest** out) {
+  if (!out) return fail("null argument");
+  *out = nullptr;
+  if (check_desc(pl, d)) return 1;
+  if (frames_per_chunk <= 0) return fail("frames_per_chunk must be positive");
+  if (depth < 2 || depth > 16) return fail("ring depth must be 2..16, got %d", depth);
+  if (d->frame_len <= 0) return fail("the ingestion ring needs a positive frame length");
+  if (!want_amplitude && !want_phase && !want_peaks) return fail("no output requested");
+  if (set_device(pl->ctx)) return 1;
+  pdsp_ingest* g = new pdsp_ingest();
+  g->plan = pl;
+  g->desc = *d;
+  g->desc.hop = d->frame_len;  // frames are packed back to back inside a chunk
+  g->cap = frames_per_chunk;
+  g->want_amp = want_amplitude != 0, g->want_phase = want_phase != 0, g->want_peaks = want_peaks != 0;
+  const int n = pl->n;
+  const size_t bins = d->sides == PDSP_SIDES_TWO ? (size_t)n : (size_t)n / 2 + 1;
+  g->in_frame = (size_t)d->frame_len * esize(d->sample_dtype);
+  g->row = bins * esize(pl->precision);
+  g->pk = pl->precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
+  g->a_off = 0;
+  g->p_off = g->a_off + align256(g->want_amp ? (size_t)g->cap * g->row : 0);
+  g->k_off = g->p_off + align256(g->want_phase ? (size_t)g->cap * g->row : 0);
+  g->out_bytes = g->k_off + align256(g->want_peaks ? (size_t)g->cap * g->pk : 0) + 256;
+  g->chunks.resize((size_t)depth);
+  int rc = 0;
+  for (auto& ch : g->chunks) {
+    cudaError_t e = cudaStreamCreateWithFlags(&ch.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ch.h_in, (size_t)g->cap * g->in_frame, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&ch.d_in, (size_t)g->cap * g->in_frame + 256);
+    if (e == cudaSuccess) e = cudaMalloc(&ch.d_out, g->out_bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ch.h_out, g->out_bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      rc = fail("ingestion ring allocation: %s", cudaGetErrorString(e));
+      break;
+    }
+  }
+  if (rc) {
+    pdsp_ingest_close(g);
+    return 1;
+  }
+  *out = g;
+  return 0;
+}
+
+PDSP_EXPORT int pdsp_ingest_close(pdsp_ingest* g) {
+  if (!g) return 0;
+  if (g->plan && set_device(g->plan->ctx)) return 1;
+  for (auto& ch : g->chunks) {
+    if (ch.stream) cudaStreamSynchronize(ch.stream);
+    cudaFreeHost(ch.h_in);
+    cudaFree(ch.d_in);
+    cudaFree(ch.d_out);
+    cudaFreeHost(ch.h_out);
+    if (ch.done) cudaEventDestroy(ch.done);
+    if (ch.stream) cudaStreamDestroy(ch.stream);
+  }
+  delete g;
+  return 0;
+}
+
+// Copies `count` frames (frame_len samples each, `stride` samples apart; 0 = frame_len) into the ring, sending
+// every chunk that fills up.  *accepted is how many were taken: fewer than `count` means the ring is full -
+// the next chunk still holds results the caller has not collected with pdsp_ingest_pop.
+PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t count, int64_t stride, int64_t* accepted) {
+  if (!g || (!frames && count > 0)) return fail("null argument");
+  if (count < 0 || stride < 0) return fail("negative count or stride");
+  if (accepted) *accepted = 0;
+  if (set_device(g->plan->ctx)) return 1;
+  std::lock_guard<std::mutex> lk(g->mu);
+  const size_t es = esize(g->desc.sample_dtype);
+  const size_t step = (size_t)(stride ? stride : g->desc.frame_len) * es;
+  const char* src = static_cast<const char*>(frames);
+  int64_t done = 0;
+  while (done < count) {
+    IngestChunk& ch = g->chunks[(size_t)g->fill];
+    if (ch.in_flight) break;  // ring full
+    long long take = g->cap - ch.frames;
+    if (take > count - done) take = count - done;
+    char* dst = static_cast<char*>(ch.h_in) + (size_t)ch.frames * g->in_frame;
+    if (step == g->in_frame) {
+      memcpy(dst, src, (size_t)take * g->in_frame);
+    } else {
+      for (long long i = 0; i < take; ++i) memcpy(dst + (size_t)i * g->in_frame, src + (size_t)i * step, g->in_frame);
+    }
+    ch.frames += take;
+    done += take;
+    src += (size_t)take * step;
+    if (ch.frames == g->cap) {
+      if (ingest_submit(g, ch)) return 1;
+      g->fill = (g->fill + 1) % (int)g->chunks.size();
+    }
+  }
+  if (accepted) *accepted = done;
+  return 0;
+}
+
+// Sends the partially filled chunk (end of stream, or a latency bound on the caller's side).
+PDSP_EXPORT int pdsp_ingest_flush(pdsp_ingest* g) {
+  if (!g) return fail("null argument");
+  if (set_device(g->plan->ctx)) return 1;
+  std::lock_guard<std::mutex> lk(g->mu);
+  IngestChunk& ch = g->chunks[(size_t)g->fill];
+  if (ch.in_flight || ch.frames == 0) return 0;
+  if (ingest_submit(g, ch)) return 1;
+  g->fill = (g->fill + 1) % (int)g->chunks.size();
+  return 0;
+}
+
+// Hands back up to max_frames finished frames in arrival order (rows appended densely to the caller's arrays,
+// which may be NULL for outputs not requested at open).  Blocks on chunks already sent; frames still sitting in
+// a partially filled chunk are not waited for.  *got may be 0.
+PDSP_EXPORT int pdsp_ingest_pop(pdsp_ingest* g, void* amplitude, void* phase, void* peaks, int64_t max_frames, int64_t* got) {
+  if (!g || !got) return fail("null argument");
+  *got = 0;
+  if (max_frames < 0) return fail("negative max_frames");
+  if (set_device(g->plan->ctx)) return 1;
+  std::lock_guard<std::mutex> lk(g->mu);
+  int64_t n = 0;
+  while (n < max_frames) {
+    IngestChunk& ch = g->chunks[(size_t)g->head];
+    if (!ch.in_flight) break;
+    CU(cudaEventSynchronize(ch.done));
+    long long take = ch.frames - ch.popped;
+    if (take > max_frames - n) take = max_frames - n;
+    const char* hout = static_cast<const char*>(ch.h_out);
+    if (amplitude && g->want_amp)
+      memcpy(static_cast<char*>(amplitude) + (size_t)n * g->row, hout + g->a_off + (size_t)ch.popped * g->row, (size_t)take * g->row);
+    if (phase && g->want_phase)
+      memcpy(static_cast<char*>(phase) + (size_t)n * g->row, hout + g->p_off + (size_t)ch.popped * g->row, (size_t)take * g->row);
+    if (peaks && g->want_peaks)
+      memcpy(static_cast<char*>(peaks) + (size_t)n * g->pk, hout + g->k_off + (size_t)ch.popped * g->pk, (size_t)take * g->pk);
+    ch.popped += take;
+    n += take;
+    if (ch.popped == ch.frames) {
+      ch.in_flight = false;
+      ch.frames = ch.popped = 0;
+      g->head = (g->head + 1) % (int)g->chunks.size();
+    }
+  }
+  *got = n;
+  return 0;
+}

@@ -91,35 +91,57 @@ def spectrumStream(frames: Iterable, options: dict | None = None, *, service: Fo
                    chunk: int = 4096) -> Iterator[dict]:
     """src/effect/index.ts:190-194 - ordered 1:1 map over a stream of (Float32Array) frames.
 
-    Frames of equal length are stacked `chunk` at a time into one batched launch; a frame of a
-    different length flushes the pending chunk first so order is preserved."""
+    Frames go through the ingestion ring (pdsp_ingest_*): each is copied into a pinned chunk as it arrives, a
+    full chunk of `chunk` frames is transformed on its own stream while the next one fills, and results are
+    yielded in arrival order.  A frame of a different length or dtype drains the ring and opens a new one."""
+    from ..public.ingest import IngestRing
     opts = dict(options or {})
     svc = service or FourierService()
-    pending: list[np.ndarray] = []
+    ring = None
+    key = None
+    pending = 0  # frames pushed and not yet yielded
 
-    def flush():
-        if not pending:
-            return
-        block = np.stack(pending)
-        size = opts.get("fftSize")
-        size = nextPowerOfTwo(block.shape[1]) if size is None else size
-        svc.fft(size)
-        r = spectrum_batch(block, sampleRate=opts.get("sampleRate", 1), fftSize=size, window=opts.get("window", "rect"),
-                           sides=opts.get("sides", "one"), precision=opts.get("precision", "f64"), context=svc._ctx)
-        for i in range(block.shape[0]):
-            yield _result(r, i)
-        pending.clear()
+    def drain(r, n_wait):
+        """Yield finished frames; n_wait > 0 insists on at least that many (the ring is full or the stream ended)."""
+        nonlocal pending
+        while n_wait > 0 and pending > 0:
+            out = r.pop(min(pending, chunk))
+            if out["count"] == 0:
+                break
+            for i in range(out["count"]):
+                yield _result(out, i)
+            pending -= out["count"]
+            n_wait -= out["count"]
 
     for frame in frames:
         f = np.asarray(frame)
         if f.dtype != np.float32 and f.dtype != np.float64:
             f = f.astype(np.float64)
-        if pending and (f.shape != pending[0].shape or f.dtype != pending[0].dtype):
-            yield from flush()
-        pending.append(f)
-        if len(pending) >= chunk:
-            yield from flush()
-    yield from flush()
+        k = (f.shape, f.dtype)
+        if ring is not None and k != key:
+            ring.flush()
+            yield from drain(ring, pending)
+            ring.close()
+            ring = None
+        if f.size == 0:  # spectrum([]) is a one-bin result; not worth a ring
+            yield _one(svc, f, opts)
+            continue
+        if ring is None:
+            size = opts.get("fftSize")
+            size = nextPowerOfTwo(f.shape[0]) if size is None else size
+            svc.fft(size)
+            ring = IngestRing(f.shape[0], sampleRate=opts.get("sampleRate", 1), fftSize=size,
+                              window=opts.get("window", "rect"), sides=opts.get("sides", "one"),
+                              precision=opts.get("precision", "f64"), sample_dtype=f.dtype, framesPerChunk=chunk,
+                              depth=3, context=svc._ctx)
+            key = k
+        while ring.push(f) == 0:  # ring full: hand back the oldest chunk, then retry
+            yield from drain(ring, 1)
+        pending += 1
+    if ring is not None:
+        ring.flush()
+        yield from drain(ring, pending)
+        ring.close()
 
 
 __all__ = ["FourierService", "Fourier", "FourierLive", "spectrumFx", "spectrumStream"]

@@ -253,6 +253,48 @@ def test_fused_fftshift_two_sided_emulated(emu_api, monkeypatch):
     assert np.array_equal(fused["phase"], np.fft.fftshift(plain["phase"], axes=1))
 
 
+def test_ingestion_ring_emulated(emu_api):
+    """SURVEY 8f-4: frames pushed one at a time / in blocks come back in order, bit-identical to spectrum_batch;
+    ring-full back-pressure, partial-chunk flush, pop smaller than a chunk, and spectrumStream on top of the ring."""
+    from pragma_dsp_b200 import IngestRing, spectrum_batch
+    from pragma_dsp_b200.effect import FourierLive, spectrumStream
+    rng = np.random.default_rng(21)
+    n, total = 1024, 23
+    x = multitone(rng, total, n, np.float32)
+    ref = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann")
+    with IngestRing(n, sampleRate=48000.0, window="hann", sample_dtype=np.float32, framesPerChunk=4, depth=3) as ring:
+        amp, ph, pk = [], [], []
+        pushed = 0
+        while pushed < total:
+            k = ring.push(x[pushed:pushed + 5])  # blocks of 5 against chunks of 4: chunks fill across pushes
+            pushed += k
+            if k == 0:  # ring full (3 chunks of 4 in flight): collect 3 frames - less than a chunk - and go on
+                out = ring.pop(3)
+                assert out["count"] == 3
+                amp.append(out["amplitude"]), ph.append(out["phase"]), pk.append(out["peaks"])
+        ring.flush()
+        while True:
+            out = ring.pop(7)
+            if out["count"] == 0:
+                break
+            amp.append(out["amplitude"]), ph.append(out["phase"]), pk.append(out["peaks"])
+        amp, ph, pk = np.concatenate(amp), np.concatenate(ph), np.concatenate(pk)
+    assert amp.shape == ref["amplitude"].shape
+    assert np.array_equal(amp, ref["amplitude"]) and np.array_equal(ph, ref["phase"]) and (pk == ref["peaks"]).all()
+    # the stream operator: ordered, 1:1, frames of another length in the middle, an empty stream
+    svc = FourierLive()
+    frames = [x[i] for i in range(9)] + [x[9][:64]] + [x[i] for i in range(10, 14)]
+    outs = list(spectrumStream(frames, {"sampleRate": 48000.0, "window": "hann"}, service=svc, chunk=4))
+    assert len(outs) == len(frames)
+    for i, o in enumerate(outs):
+        r = oracle.spectrum(frames[i], sampleRate=48000.0, window="hann")
+        assert o["peak"]["index"] == r["peak"]["index"], i
+        assert np.abs(o["amplitude"] - r["amplitude"]).max() <= 1e-12
+    assert list(spectrumStream([], {}, service=svc)) == []
+    with pytest.raises(Exception, match="depth"):
+        IngestRing(n, depth=1)
+
+
 def test_fused_peer_scatter_emulated(emu_api):
     """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
     from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
