@@ -261,6 +261,71 @@ napi_value HostAlloc(napi_env env, napi_callback_info info) {
   return ab;
 }
 
+// ---- ingestion ring (pdsp_ingest_*): what ts/effect/index.ts spectrumStream pushes Stream<Float32Array> frames into
+void ingest_finalize(napi_env, void* data, void*) { pdsp_ingest_close(static_cast<pdsp_ingest*>(data)); }
+// ingestOpen(plan, {frameLen, window, sides, sampleRate, sampleDtype}, wantAmp, wantPhase, wantPeaks, framesPerChunk, depth)
+napi_value IngestOpen(napi_env env, napi_callback_info info) {
+  ARGS(7)
+  void* p = nullptr;
+  napi_get_value_external(env, argv[0], &p);
+  pdsp_spectrum_desc d;
+  memset(&d, 0, sizeof d);
+  d.sample_dtype = get_i32(env, argv[1], "sampleDtype", PDSP_F32);
+  d.frame_len = get_i32(env, argv[1], "frameLen", 0);
+  d.hop = d.frame_len;
+  d.window = get_i32(env, argv[1], "window", PDSP_WIN_RECT);
+  d.sides = get_i32(env, argv[1], "sides", PDSP_SIDES_ONE);
+  d.sample_rate = get_f64(env, argv[1], "sampleRate", 1.0);
+  int32_t wa = 0, wp = 0, wk = 0, depth = 3;
+  int64_t per_chunk = 0;
+  napi_get_value_int32(env, argv[2], &wa);
+  napi_get_value_int32(env, argv[3], &wp);
+  napi_get_value_int32(env, argv[4], &wk);
+  napi_get_value_int64(env, argv[5], &per_chunk);
+  napi_get_value_int32(env, argv[6], &depth);
+  pdsp_ingest* ring = nullptr;
+  if (pdsp_ingest_open(static_cast<pdsp_plan*>(p), &d, wa, wp, wk, per_chunk, depth, &ring)) return fail_last(env);
+  napi_value ext;
+  napi_create_external(env, ring, ingest_finalize, nullptr, &ext);
+  return ext;
+}
+// ingestPush(ring, frames: Float32Array|Float64Array holding whole frames, count) -> frames accepted
+napi_value IngestPush(napi_env env, napi_callback_info info) {
+  ARGS(3)
+  void* r = nullptr;
+  napi_get_value_external(env, argv[0], &r);
+  TA s;
+  int64_t count = 0, accepted = 0;
+  napi_get_value_int64(env, argv[2], &count);
+  if (!get_ta(env, argv[1], &s) || !s.present || !is_float(s)) return fail(env, "pragma-dsp/b200: expected (ring, frames, count)");
+  if (pdsp_ingest_push(static_cast<pdsp_ingest*>(r), s.data, count, 0, &accepted)) return fail_last(env);
+  napi_value v;
+  napi_create_double(env, (double)accepted, &v);
+  return v;
+}
+napi_value IngestFlush(napi_env env, napi_callback_info info) {
+  ARGS(1)
+  void* r = nullptr;
+  napi_get_value_external(env, argv[0], &r);
+  if (pdsp_ingest_flush(static_cast<pdsp_ingest*>(r))) return fail_last(env);
+  return undefined(env);
+}
+// ingestPop(ring, amplitude|null, phase|null, peaks: Uint8Array|null, maxFrames) -> frames returned
+napi_value IngestPop(napi_env env, napi_callback_info info) {
+  ARGS(5)
+  void* r = nullptr;
+  napi_get_value_external(env, argv[0], &r);
+  TA amp, ph, pk;
+  int64_t max_frames = 0, got = 0;
+  napi_get_value_int64(env, argv[4], &max_frames);
+  if (!get_ta(env, argv[1], &amp) || !get_ta(env, argv[2], &ph) || !get_ta(env, argv[3], &pk))
+    return fail(env, "pragma-dsp/b200: expected (ring, amplitude|null, phase|null, peaks|null, maxFrames)");
+  if (pdsp_ingest_pop(static_cast<pdsp_ingest*>(r), amp.data, ph.data, pk.data, max_frames, &got)) return fail_last(env);
+  napi_value v;
+  napi_create_double(env, (double)got, &v);
+  return v;
+}
+
 napi_value AbiVersion(napi_env env, napi_callback_info) {
   napi_value v;
   napi_create_int32(env, pdsp_abi_version(), &v);
@@ -288,5 +353,9 @@ extern "C" __attribute__((visibility("default"))) napi_value napi_register_modul
   def(env, exports, "createWindow", CreateWindow);
   def(env, exports, "binFrequencies", BinFrequencies);
   def(env, exports, "hostAlloc", HostAlloc);
+  def(env, exports, "ingestOpen", IngestOpen);
+  def(env, exports, "ingestPush", IngestPush);
+  def(env, exports, "ingestFlush", IngestFlush);
+  def(env, exports, "ingestPop", IngestPop);
   return exports;
 }

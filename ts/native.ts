@@ -19,6 +19,14 @@ export interface Native {
   createWindow(type: number, size: number, out: Float64Array): void;
   binFrequencies(size: number, sampleRate: number, sides: number, out: Float64Array): void;
   hostAlloc(ctx: Handle, bytes: number): ArrayBuffer;
+  // ingestion ring (pdsp_ingest_*): frames in as they arrive, results out in arrival order; a long-lived source
+  // (microphone, websocket) pushes each frame and pops whatever is finished instead of assembling batches
+  ingestOpen(plan: Handle, desc: { frameLen: number; window: number; sides: number; sampleRate: number; sampleDtype: number },
+             wantAmplitude: number, wantPhase: number, wantPeaks: number, framesPerChunk: number, depth: number): Handle;
+  ingestPush(ring: Handle, frames: Float32Array | Float64Array, count: number): number;
+  ingestFlush(ring: Handle): void;
+  ingestPop(ring: Handle, amplitude: Float64Array | Float32Array | null, phase: Float64Array | Float32Array | null,
+            peaks: Uint8Array | null, maxFrames: number): number;
 }
 
 export const F32 = 0, F64 = 1;
