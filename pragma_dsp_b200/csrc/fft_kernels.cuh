@@ -390,13 +390,15 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     } else {
       const long long base = valid ? f * p.hop : 0;
       const int lim_f = valid ? lim : 0;
-      static_for<0, P>([&](auto qi) {
-        constexpr int q = decltype(qi)::value;
-        const int i0 = 2 * (t + TF * q);
-        T x0 = (T)0, x1 = (T)0;
-        if (p.sample_dtype == DT_F32) {
-          const float* s = static_cast<const float*>(p.samples) + base;
-          if (p.vec_ok && i0 + 1 < lim_f) {
+      // sample type and alignment are decided once per frame, outside the unrolled loop (a warp-uniform test
+      // inside it keeps the loads from being issued as one batch)
+      auto load_gen = [&](auto* s, auto vec_c) {
+        constexpr bool VEC = decltype(vec_c)::value;
+        static_for<0, P>([&](auto qi) {
+          constexpr int q = decltype(qi)::value;
+          const int i0 = 2 * (t + TF * q);
+          T x0 = (T)0, x1 = (T)0;
+          if (VEC && i0 + 1 < lim_f) {
             const cx<T> pr = load_pair<T>(s, i0);
             x0 = pr.x;
             x1 = pr.y;
@@ -404,24 +406,30 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
             if (i0 < lim_f) x0 = (T)s[i0];
             if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
           }
-        } else {
-          const double* s = static_cast<const double*>(p.samples) + base;
-          if (p.vec_ok && i0 + 1 < lim_f) {
-            const cx<T> pr = load_pair<T>(s, i0);
-            x0 = pr.x;
-            x1 = pr.y;
-          } else {
-            if (i0 < lim_f) x0 = (T)s[i0];
-            if (i0 + 1 < lim_f) x1 = (T)s[i0 + 1];
-          }
-        }
-        if (win != nullptr) {
-          const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win + i0));
-          x0 *= w.x;
-          x1 *= w.y;
-        }
-        v[q] = cx<T>{x0, x1};
-      });
+          v[q] = cx<T>{x0, x1};
+        });
+      };
+      if (p.sample_dtype == DT_F32) {
+        const float* s = static_cast<const float*>(p.samples) + base;
+        if (p.vec_ok)
+          load_gen(s, std::true_type{});
+        else
+          load_gen(s, std::false_type{});
+      } else {
+        const double* s = static_cast<const double*>(p.samples) + base;
+        if (p.vec_ok)
+          load_gen(s, std::true_type{});
+        else
+          load_gen(s, std::false_type{});
+      }
+      if (win != nullptr) {
+        static_for<0, P>([&](auto qi) {
+          constexpr int q = decltype(qi)::value;
+          const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
+          v[q].x *= w.x;
+          v[q].y *= w.y;
+        });
+      }
     }
 
     // ---- M-point complex FFT of the packed frame
