@@ -2,7 +2,7 @@
 """Fraction of the HBM roofline across FFT sizes (amplitude + peak, Hann) for both precisions.
 
     python scripts/sweep_sizes.py > gpurun_out/sweep_sizes.jsonl
-    SWEEP_MODE=amp|amp_peak|peak|cplx SWEEP_LOG2N=10,11,12 python scripts/sweep_sizes.py
+    SWEEP_MODE=amp|amp_peak|peak|cplx|amp_phase_peak SWEEP_SIDES=one|two SWEEP_LOG2N=10,11,12 python scripts/sweep_sizes.py
 """
 import ctypes as C
 import json
@@ -40,6 +40,7 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         if MODE == "cplx":  # Radix2Fft.forward: all N bins, two planes
             amp = torch.empty((frames, n), dtype=tdt, device=dev)
         im = torch.empty((frames, n), dtype=tdt, device=dev) if MODE == "cplx" else None
+        ph = torch.empty((frames, bins), dtype=tdt, device=dev) if "phase" in MODE else None
 
         def go():
             if MODE == "cplx":
@@ -47,7 +48,8 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
                                                   C.c_void_p(im.data_ptr()), 1, C.c_void_p(st.cuda_stream)))
                 return
             check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()),
-                                      C.c_void_p(amp.data_ptr()) if "amp" in MODE else None, None,
+                                      C.c_void_p(amp.data_ptr()) if "amp" in MODE else None,
+                                      C.c_void_p(ph.data_ptr()) if ph is not None else None,
                                       C.c_void_p(pk.data_ptr()) if "peak" in MODE else None, C.c_void_p(st.cuda_stream)))
         for _ in range(3):
             go()
@@ -60,9 +62,9 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         es = 8 if prec == F64 else 4
-        bpf = n * es + (2 * n * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0)
+        bpf = n * es + (2 * n * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0) + (bins * es if "phase" in MODE else 0)
                         + ((32 if prec == F64 else 16) if "peak" in MODE else 0))
         gbs = frames * bpf / (ms * 1e-3) / 1e9
         print(json.dumps({"mode": MODE, "sides": SIDES_, "precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
                           "gbs": gbs, "frac_of_measured_hbm": gbs / peak}), flush=True)
-        del x, amp, pk, im
+        del x, amp, pk, im, ph
