@@ -25,8 +25,23 @@ struct KCfg {
 #ifndef PDSP_F32_SMALL_LOG2P
 #define PDSP_F32_SMALL_LOG2P 4  // fp32, M = 128 / 256: 16 points per thread (N = 512: 0.55 -> 0.70 of roofline)
 #endif
+// fp32, small frames: log2(points per thread) for M = 128 (N = 256), 64, 32, 16.  A frame's lanes read 8 bytes each, so
+// fewer points per thread = more lanes per frame = longer contiguous segments per load (TF = 16 lanes -> 128 bytes).
+#ifndef PDSP_F32_LOG2P_M7
+#define PDSP_F32_LOG2P_M7 3  // N = 256: 8 points, 16 lanes per frame (amp 0.60 -> 0.65, all-bins forward 0.55 -> 0.77)
+#endif
+#ifndef PDSP_F32_LOG2P_M6
+#define PDSP_F32_LOG2P_M6 3  // N = 128: 4 points (16 lanes) helps the all-bins forward (0.53 -> 0.83) but costs amplitude modes 10 %
+#endif
+#ifndef PDSP_F32_LOG2P_M5
+#define PDSP_F32_LOG2P_M5 3
+#endif
+#ifndef PDSP_F32_LOG2P_M4
+#define PDSP_F32_LOG2P_M4 3
+#endif
   static constexpr int LOG2P = LOG2M < 3 ? LOG2M
-                               : sizeof(T) == 4 ? (LOG2M >= PDSP_F32_P32_FROM ? 5 : (LOG2M >= 7 ? PDSP_F32_SMALL_LOG2P : 3))
+                               : sizeof(T) == 4 ? (LOG2M >= PDSP_F32_P32_FROM ? 5 : LOG2M == 8 ? PDSP_F32_SMALL_LOG2P : LOG2M == 7 ? PDSP_F32_LOG2P_M7
+                                  : LOG2M == 6 ? PDSP_F32_LOG2P_M6 : LOG2M == 5 ? PDSP_F32_LOG2P_M5 : LOG2M == 4 ? PDSP_F32_LOG2P_M4 : 3)
                                                 : (LOG2M == PDSP_F64_P32_AT ? 5 : (LOG2M >= 9 ? 4 : 3));
   static constexpr int MAXRB = LOG2P >= 4 ? LOG2P : 3;
   static constexpr int TF = (1 << LOG2M) >> LOG2P;
