@@ -208,6 +208,10 @@ PDSP_DEVICE void frame_sync(int slot, int slots_per_cta) {
   }
 }
 
+#ifndef PDSP_SHUFFLE_EXCHANGE
+#define PDSP_SHUFFLE_EXCHANGE 1
+#endif
+
 template <typename T, int LOG2M, int LOG2P, int MAXRB>
 struct FftEngine {
   static_assert(LOG2P <= LOG2M, "points per thread cannot exceed the frame");
@@ -263,6 +267,14 @@ struct FftEngine {
       // (doubles only: the fp64 kernels are L1-bound with DP slack, the fp32 kernels are issue-bound with
       // L1 slack - there a load is cheaper than the four FP instructions of the derivation)
       constexpr bool DERIVE = sizeof(T) == 8 && last && NSL > 0 && BPT > 1 && (32 % P) == 0;
+      // Exchange by shuffle (fp64, M = 512 = 16 x 16 x 2, one warp per frame): the radix-2 last pass pairs element
+      // j with j + 256, and after this radix-16 pass thread (h, l) = (t >> 4, t & 15) holds the 16 outputs
+      // k = 0..15 of position 256h + l + 16k.  The natural layout t' + 32q the last pass reads wants, in thread
+      // (h', l), the outputs of parity h' of both (0, l) and (1, l): each thread keeps 8 of its outputs and swaps
+      // the other 8 with lane t ^ 16.  32 SHFLs replace 16 STS.128 + 16 LDS.128 (128 L1 wavefronts) and two
+      // warp barriers; the kernel is L1-bound.
+      constexpr bool SHUF = PDSP_SHUFFLE_EXCHANGE && !BLOCKSYNC && sizeof(T) == 8 && LOG2M == 9 && LOG2P == 4 && RB == 4 &&
+                            pass == NPASS - 2 && NPASS == 3;
       [[maybe_unused]] cx<T> w0[R];
       static_for<0, BPT>([&](auto ui) {
         constexpr int u = decltype(ui)::value;
@@ -288,13 +300,26 @@ struct FftEngine {
         dif_butterfly<T, R>(a);
         if constexpr (last) {
           static_for<0, R>([&](auto k) { v[u + decltype(k)::value * BPT] = a[bitrev(decltype(k)::value, b)]; });
+        } else if constexpr (SHUF) {
+          static_assert(BPT == 1 && R == 16 && P == 16 && TF == 32, "shuffle exchange layout");
+          const bool h = ((t >> 4) & 1) != 0;
+          static_for<0, 8>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const cx<T> e = a[bitrev(2 * i, b)], o = a[bitrev(2 * i + 1, b)];
+            const cx<T> send = h ? e : o;
+            cx<T> got;
+            got.x = simt::shfl_xor(send.x, 16, 32);
+            got.y = simt::shfl_xor(send.y, 16, 32);
+            v[i] = h ? got : e;
+            v[8 + i] = h ? o : got;
+          });
         } else {
           const int base = ((j >> NSL) << (NSL + b)) + (j & (NS - 1));
           static_for<0, R>(
               [&](auto k) { sm[pad(base + (decltype(k)::value << NSL))] = a[bitrev(decltype(k)::value, b)]; });
         }
       });
-      if constexpr (!last) {
+      if constexpr (!last && !SHUF) {
         sync();
         static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
         sync();
