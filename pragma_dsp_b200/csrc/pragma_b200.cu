@@ -1063,7 +1063,11 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static long long pick_chunk(long long batch, size_t bytes_per_frame) {
   // ~24 MB of traffic per chunk keeps three chunks in flight without hoarding HBM or pinned memory
-  const size_t target = 24u << 20;
+  size_t target = 24u << 20;
+  if (const char* e = getenv("PDSP_CHUNK_BYTES")) {  // test hook: small jobs still exercise the multi-chunk pipeline
+    const long long v = atoll(e);
+    if (v > 0) target = (size_t)v;
+  }
   long long c = (long long)(target / (bytes_per_frame ? bytes_per_frame : 1));
   if (c < 1) c = 1;
   if (c > batch) c = batch;

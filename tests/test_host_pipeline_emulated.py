@@ -62,9 +62,9 @@ def test_chunked_pipeline_many_chunks(emu_api, monkeypatch):
     from pragma_dsp_b200 import spectrum_batch
     L = emu_api.lib()
     rng = np.random.default_rng(2)
-    n, batch = 64, 20000  # 256 B in + 140 B out per frame -> 24 MB / 396 B: force small chunks via big batch? no:
-    # pick_chunk targets ~24 MB, so use N=4096 frames to get several chunks with a modest batch
-    n, batch = 4096, 1300  # 16 KB + 8 KB per frame -> ~1000 frames per chunk -> 2 chunks
+    # pick_chunk targets ~24 MB per chunk; the PDSP_CHUNK_BYTES hook shrinks it so a small job is cut into ~10 chunks
+    monkeypatch.setenv("PDSP_CHUNK_BYTES", str(256 << 10))
+    n, batch = 1024, 300  # 4 KB + 4 KB per frame -> 31 frames per chunk
     x = multitone(rng, batch, n, np.float32)
     got = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann", precision="f64", outputs=("amplitude", "peak"))
     ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window="hann", want_phase=False, threads=8)
