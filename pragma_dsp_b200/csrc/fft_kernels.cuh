@@ -212,7 +212,7 @@ PDSP_DEVICE_NOINLINE float t_hypot_slow(float x, float y) { return hypotf(x, y);
 PDSP_DEVICE_NOINLINE double t_hypot_slow(double x, double y) { return hypot(x, y); }
 
 // sqrt without the IEEE slow path.  fp32: MUFU.SQRT (sqrt.approx, <= 1 ulp-ish, 2^-23 relative).
-// fp64: MUFU.RSQ64H seed + two Newton steps, branch-free; exact 0 for +0; inf/NaN and sums outside
+// fp64: MUFU.RSQ64H seed + two Newton steps (the second on the residual, with the unrefined 1/(2 sqrt)), branch-free; exact 0 for +0; inf/NaN and sums outside
 // the normal range are caught by the caller's exponent tracker and redone with hypot().
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
 PDSP_DEVICE float fast_sqrt(float s) {
@@ -224,10 +224,9 @@ PDSP_DEVICE double fast_sqrt(double s) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
   double g = s * y;          // ~ sqrt(s), 22 bits
-  double h = 0.5 * y;        // ~ 1 / (2 sqrt(s))
+  const double h = 0.5 * y;  // ~ 1 / (2 sqrt(s)), 22 bits: enough for the last correction (error 2^-44 * 2^-22)
   double r = fma(-h, g, 0.5);
   g = fma(g, r, g);          // 44 bits
-  h = fma(h, r, h);
   r = fma(-g, g, s);         // residual s - g^2
   g = fma(r, h, g);          // full precision
   return __double2hiint(s) == 0 ? 0.0 : g;  // +0 (and sub-2^-1042 dust): rsqrt gave inf
