@@ -329,10 +329,10 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const long long groups_per_cta = (n_groups + simt::nblocks() - 1) / simt::nblocks();
   const long long g_begin = (long long)simt::bid() * groups_per_cta;
   const long long g_end = g_begin + groups_per_cta < n_groups ? g_begin + groups_per_cta : n_groups;
-  // fp64 kernels: 32-bit trip count and a running frame index - the 64-bit (g, g_end) pair was spilled and re-read
+  // fp64 kernels with one warp per frame: 32-bit trip count and a running frame index - the 64-bit (g, g_end) pair was spilled and re-read
   // every iteration and the loop test waited on that local-memory load (8 % of the north-star kernel's stall
   // samples; 0.715 -> 0.727).  The fp32 kernels keep the 64-bit form, which allocates better there (-1.4 % otherwise).
-  constexpr bool IT32 = sizeof(T) == 8;
+  constexpr bool IT32 = sizeof(T) == 8 && TF <= 32;  // wider fp64 frames measured 1-4 % slower with it (N=2048 all-bins forward)
   using Cnt = typename std::conditional<IT32, int, long long>::type;
   const Cnt it_begin = IT32 ? (Cnt)0 : (Cnt)g_begin;
   const Cnt n_iter = IT32 ? (Cnt)(g_end > g_begin ? g_end - g_begin : 0) : (Cnt)g_end;
