@@ -441,3 +441,50 @@ def test_ingestion_ring_matches_batched_call(ctx):
     amp, pk = np.concatenate(amp), np.concatenate(pk)
     assert amp.shape == ref["amplitude"].shape
     assert np.array_equal(amp, ref["amplitude"]) and (pk == ref["peaks"]).all()
+
+
+def test_randomised_shapes_against_oracle_gpu(ctx):
+    """Seeded random walk over the spectrum() parameter space on the device (every size class, both plan precisions,
+    zero-padding / truncation, overlapping and odd hops, both sides, all windows, output subsets, fused shift)."""
+    from pragma_dsp_b200 import spectrum_batch
+    rng = np.random.default_rng(77)
+    sizes = [1, 2, 4, 8, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768]
+    for case in range(120):
+        n = int(rng.choice(sizes))
+        batch = int(rng.integers(1, 40 if n <= 4096 else 4))
+        frame_len = int(rng.choice([n, max(1, n - 1), max(1, n // 2 + 1), n + 3, 1]))
+        hop = int(rng.choice([frame_len, max(1, frame_len // 2), frame_len + 5, max(1, frame_len - 1)]))
+        window = str(rng.choice(["rect", "hann", "hamming", "blackman"]))
+        sides = str(rng.choice(["one", "two"]))
+        sdt = np.float64 if rng.integers(0, 2) else np.float32
+        precision = "f64" if rng.integers(0, 3) else "f32"
+        outputs = [("amplitude", "phase", "peak"), ("amplitude",), ("peak",), ("amplitude", "peak"), ("phase",)][int(rng.integers(0, 5))]
+        shift = bool(sides == "two" and rng.integers(0, 2))
+        total = (batch - 1) * hop + frame_len
+        x = rng.standard_normal(total).astype(sdt)
+        if n >= 16:
+            k0 = int(rng.integers(1, n // 2))
+            x += (3.0 * np.sin(2 * np.pi * k0 * np.arange(total) / n)).astype(sdt)
+        tag = (case, n, batch, frame_len, hop, window, sides, sdt.__name__, precision, outputs, shift)
+        got = spectrum_batch(x, sampleRate=8000.0, fftSize=n, window=window, sides=sides, frameLen=frame_len, hop=hop,
+                             batch=batch, outputs=outputs, shift=shift, precision=precision)
+        ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=8000.0, window=window, sides=sides, frameLen=frame_len,
+                                    hop=hop, batch=batch, threads=8)
+        ramp, rph = ref["amplitude"], ref["phase"]
+        if shift:
+            ramp, rph = np.fft.fftshift(ramp, axes=1), np.fft.fftshift(rph, axes=1)
+        scale = max(1.0, float(np.abs(ramp).max()))
+        atol = (1e-12 if precision == "f64" else 2e-6 * np.log2(max(2, n))) * scale
+        if "amplitude" in outputs:
+            assert np.abs(got["amplitude"] - ramp).max() <= atol, tag
+        if "phase" in outputs:
+            strong = ramp > (1e-6 if precision == "f64" else 1e-2) * scale
+            d = np.abs(got["phase"].astype(np.float64) - rph)
+            if strong.any():
+                assert np.minimum(d, np.abs(d - 2 * np.pi))[strong].max() <= (1e-8 if precision == "f64" else 5e-3), tag
+        if "peak" in outputs:
+            gi, ri = got["peaks"]["index"], ref["peaks"]["index"]
+            for f in np.nonzero(gi != ri)[0]:  # only last-bit ties (noise bins, mirror bins) may differ
+                a = ref["amplitude"][f]
+                assert abs(a[gi[f]] - a[ri[f]]) <= (1e-12 if precision == "f64" else 1e-5) * max(a[ri[f]], 1e-30), tag
+            assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= atol, tag
