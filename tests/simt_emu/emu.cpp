@@ -48,17 +48,56 @@ static int run_c2c(const C2CParams& p, int nblocks) {
   return 0;
 }
 
+// The instantiations are split over several translation units (-DEMU_PART=k, built in parallel by
+// tests/simt_emu/__init__.py): parts 0-4 hold the r2c kernels of a group of sizes, 5 / 6 the fp64 / fp32 tuning
+// variants, 7 the c2c kernels, the configuration query and the dispatchers.
+#ifndef EMU_PART
+#error "compile with -DEMU_PART=0..7"
+#endif
 #define EMU_SIZES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11)
+#if EMU_PART == 0
+#define EMU_PART_SIZES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6)
+#define EMU_PART_NAME emu_r2c_part0
+#elif EMU_PART == 1
+#define EMU_PART_SIZES(X) X(7) X(8)
+#define EMU_PART_NAME emu_r2c_part1
+#elif EMU_PART == 2
+#define EMU_PART_SIZES(X) X(9)
+#define EMU_PART_NAME emu_r2c_part2
+#elif EMU_PART == 3
+#define EMU_PART_SIZES(X) X(10)
+#define EMU_PART_NAME emu_r2c_part3
+#elif EMU_PART == 4
+#define EMU_PART_SIZES(X) X(11)
+#define EMU_PART_NAME emu_r2c_part4
+#endif
 
-extern "C" int emu_r2c(int f64, int log2m, const R2CParams* p, int nblocks, int mode) {
+#if EMU_PART <= 4
+extern "C" int EMU_PART_NAME(int f64, int log2m, const R2CParams* p, int nblocks, int mode) {
   switch (log2m) {
 #define X(L) \
   case L:    \
     return f64 ? run_r2c<double, L>(*p, nblocks, mode) : run_r2c<float, L>(*p, nblocks, mode);
-    EMU_SIZES(X)
+    EMU_PART_SIZES(X)
 #undef X
   }
   return -1;
+}
+#endif
+
+#if EMU_PART == 7
+extern "C" int emu_r2c_part0(int, int, const R2CParams*, int, int);
+extern "C" int emu_r2c_part1(int, int, const R2CParams*, int, int);
+extern "C" int emu_r2c_part2(int, int, const R2CParams*, int, int);
+extern "C" int emu_r2c_part3(int, int, const R2CParams*, int, int);
+extern "C" int emu_r2c_part4(int, int, const R2CParams*, int, int);
+extern "C" int emu_r2c(int f64, int log2m, const R2CParams* p, int nblocks, int mode) {
+  if (log2m < 0 || log2m > 11) return -1;
+  if (log2m <= 6) return emu_r2c_part0(f64, log2m, p, nblocks, mode);
+  if (log2m <= 8) return emu_r2c_part1(f64, log2m, p, nblocks, mode);
+  if (log2m == 9) return emu_r2c_part2(f64, log2m, p, nblocks, mode);
+  if (log2m == 10) return emu_r2c_part3(f64, log2m, p, nblocks, mode);
+  return emu_r2c_part4(f64, log2m, p, nblocks, mode);
 }
 extern "C" int emu_c2c(int f64, int log2m, const C2CParams* p, int nblocks) {
   switch (log2m) {
@@ -70,6 +109,9 @@ extern "C" int emu_c2c(int f64, int log2m, const C2CParams* p, int nblocks) {
   }
   return -1;
 }
+#endif
+
+#if EMU_PART == 5 || EMU_PART == 6
 template <typename T, int VAR>
 static int run_var(const R2CParams& p, int nblocks, int mode) {
   switch (mode) {
@@ -79,15 +121,29 @@ static int run_var(const R2CParams& p, int nblocks, int mode) {
   }
   return -2;
 }
-extern "C" int emu_r2c_var(int f64, int var, const R2CParams* p, int nblocks, int mode) {
+#if EMU_PART == 5
+extern "C" int emu_r2c_var_f64(int var, const R2CParams* p, int nblocks, int mode) {
+  using VT = double;
+#else
+extern "C" int emu_r2c_var_f32(int var, const R2CParams* p, int nblocks, int mode) {
+  using VT = float;
+#endif
   switch (var) {
 #define X(V) \
   case V:    \
-    return f64 ? run_var<double, V>(*p, nblocks, mode) : run_var<float, V>(*p, nblocks, mode);
+    return run_var<VT, V>(*p, nblocks, mode);
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
 #undef X
   }
   return -1;
+}
+#endif
+
+#if EMU_PART == 7
+extern "C" int emu_r2c_var_f64(int, const R2CParams*, int, int);
+extern "C" int emu_r2c_var_f32(int, const R2CParams*, int, int);
+extern "C" int emu_r2c_var(int f64, int var, const R2CParams* p, int nblocks, int mode) {
+  return f64 ? emu_r2c_var_f64(var, p, nblocks, mode) : emu_r2c_var_f32(var, p, nblocks, mode);
 }
 // kernel configuration of (type, size, variant): lets the harness build the per-pass twiddle table
 template <typename T, int LOG2M, int VAR>
@@ -122,3 +178,4 @@ extern "C" int emu_cfg(int f64, int log2m, int var, int* out) {
   return -1;
 }
 extern "C" int emu_params_size(int which) { return which == 0 ? (int)sizeof(R2CParams) : (int)sizeof(C2CParams); }
+#endif  // EMU_PART == 7
