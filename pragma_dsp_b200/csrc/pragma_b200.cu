@@ -775,6 +775,10 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
   // transforms are processed `chunk` at a time (all passes of a chunk share the work planes)
   long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
+  if (const char* e = getenv("PDSP_BIG_CHUNK")) {  // experiment / test hook: transforms per group of passes
+    const long long v = atoll(e);
+    if (v > 0) chunk = v;
+  }
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   BigPlan::Work* wk = nullptr;
