@@ -267,6 +267,7 @@ enum : int {
   MD_PHASE = 2,   // phase rows
   MD_PEAK = 4,    // per-frame findPeak record
   MD_CPLX = 8,    // complex spectrum, all N bins (Radix2Fft.forward)
+  MD_TWO = 16,    // two-sided amplitude / phase rows (N bins, mirror bins written); one-sided (N/2+1) otherwise
 };
 
 template <typename T, typename S>
@@ -306,7 +307,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const cx<T>* PDSP_RESTRICT post = static_cast<const cx<T>*>(p.post);
   const T* PDSP_RESTRICT win = static_cast<const T*>(p.window);
   const int lim = p.frame_len < N ? p.frame_len : N;
-  const bool two_sided = GEN ? p.two_sided != 0 : false;
+  const bool two_sided = GEN ? p.two_sided != 0 : (MODE & MD_TWO) != 0;
   const bool cfull = GEN ? p.cfull != 0 : true;
   const int bins = two_sided ? N : M + 1;
   const int sh = (two_sided && p.shift) ? M : 0;  // fftShift fused into the two-sided stores (row rotation by N/2)

@@ -91,7 +91,8 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
 // The output combinations that get a compile-time specialised kernel (everything else, and every
 // ragged/unaligned call, runs the generic kernel).
 #define PDSP_SPEC_MODES(X)                                                                          \
-  X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)
+  X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)                    \
+  X(MD_AMP | MD_TWO) X(MD_AMP | MD_PHASE | MD_PEAK | MD_TWO)
 
 inline bool mode_is_specialised(int mode) {
   switch (mode) {
@@ -107,7 +108,7 @@ inline bool mode_is_specialised(int mode) {
 
 // One translation unit instantiates a contiguous range [LO, HI] of sizes (see inst.cu).
 // `mode` = 0 (generic) or one of PDSP_SPEC_MODES; the caller guarantees the specialised
-// kernels' preconditions (whole vector-aligned frames, one-sided rows).
+// kernels' preconditions (whole vector-aligned frames).
 template <typename T, int L, int LO, int HI>
 cudaError_t r2c_case(int mode, const R2CParams& p, const LaunchCtx& lc) {
   if constexpr (L >= LO && L <= HI) {

@@ -233,3 +233,20 @@ def test_window_by_rotation_matches_table(n, window, coef):
     assert (a["peaks"]["index"] == b["peaks"]["index"]).all()
     ref = oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window=window)
     assert np.abs(b["amp"] - ref["amplitude"]).max() <= 1e-13
+
+
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("want", [("amp",), ("amp", "phase", "peak")])
+def test_two_sided_specialised_equals_generic(n, dtype, want):
+    """MD_TWO: the two-sided rows (mirror bins, optional fused fftShift) of the specialised kernels carry the generic
+    kernel's bits."""
+    rng = np.random.default_rng(n + 7)
+    batch = 5
+    x = multitone(rng, batch, n).astype(dtype)
+    w = oracle.createWindow("hamming", n)
+    kw = dict(dtype=dtype, batch=batch, window=w, sample_rate=8000.0, want=want, nblocks=2, sides="two")
+    a = E.r2c(x.reshape(-1), n, **kw)
+    b = E.r2c(x.reshape(-1), n, specialised=True, **kw)
+    for key in a:
+        assert (a[key] == b[key]).all(), key
