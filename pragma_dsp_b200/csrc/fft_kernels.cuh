@@ -268,6 +268,7 @@ enum : int {
   MD_PEAK = 4,    // per-frame findPeak record
   MD_CPLX = 8,    // complex spectrum, all N bins (Radix2Fft.forward)
   MD_TWO = 16,    // two-sided amplitude / phase rows (N bins, mirror bins written); one-sided (N/2+1) otherwise
+  MD_PAD = 32,    // frames shorter than N, zero-padded (spectrum()'s default for lengths that are not a power of two)
 };
 
 template <typename T, typename S>
@@ -344,13 +345,29 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     if constexpr (!GEN) {
       // whole aligned frames: one vector load per complex point; a tail slot re-reads the last frame
       const long long base = (valid ? f : p.batch - 1) * p.hop;
-      if (p.sample_dtype == DT_F32) {
-        const float* s = static_cast<const float*>(p.samples) + base;
-        static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
-      } else {
-        const double* s = static_cast<const double*>(p.samples) + base;
-        static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
-      }
+      auto load_frame = [&](auto* s) {
+        if constexpr ((MODE & MD_PAD) != 0) {
+          // buildFrame's zero padding (spectrum.ts:36-43): pairs at or beyond frame_len read as 0, the pair that
+          // straddles an odd frame_len keeps its first sample.  A separate compile-time mode: the same test as a
+          // run-time branch around these loads cost the whole-frame kernels 2-5 %.
+          // (keeping the vector loads unconditional and zeroing by selects measured far worse: 0.68 -> 0.38)
+          static_for<0, P>([&](auto qi) {
+            const int i0 = 2 * (t + TF * decltype(qi)::value);
+            cx<T> pr{(T)0, (T)0};
+            if (i0 + 1 < lim)
+              pr = load_pair<T>(s, i0);
+            else if (i0 < lim)
+              pr.x = (T)s[i0];
+            v[decltype(qi)::value] = pr;
+          });
+        } else {
+          static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
+        }
+      };
+      if (p.sample_dtype == DT_F32)
+        load_frame(static_cast<const float*>(p.samples) + base);
+      else
+        load_frame(static_cast<const double*>(p.samples) + base);
       if (p.l2_prefetch && tl == 0 && it + 1 < n_iter && f + SLOTS < p.batch) {
         // the next frame of this slot: its samples are in L2 by the time the loads above come round again
         const size_t ses = p.sample_dtype == DT_F32 ? 4 : 8;

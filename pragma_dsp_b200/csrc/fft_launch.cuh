@@ -92,7 +92,8 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
 // ragged/unaligned call, runs the generic kernel).
 #define PDSP_SPEC_MODES(X)                                                                          \
   X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)                    \
-  X(MD_AMP | MD_TWO) X(MD_AMP | MD_PHASE | MD_PEAK | MD_TWO)
+  X(MD_AMP | MD_TWO) X(MD_AMP | MD_PHASE | MD_PEAK | MD_TWO)                                                               \
+  X(MD_AMP | MD_PAD) X(MD_AMP | MD_PEAK | MD_PAD) X(MD_AMP | MD_PHASE | MD_PEAK | MD_PAD)
 
 inline bool mode_is_specialised(int mode) {
   switch (mode) {

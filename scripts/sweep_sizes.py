@@ -21,7 +21,8 @@ ctx = _lib.Context(0)
 L = lib()
 peak, _ = bench.measured_hbm_peak()
 MODE = os.environ.get("SWEEP_MODE", "amp_peak")
-SIDES_ = os.environ.get("SWEEP_SIDES", "one")  # "two" exercises the generic kernel
+SIDES_ = os.environ.get("SWEEP_SIDES", "one")
+PAD = int(os.environ.get("SWEEP_PAD", "0"))  # frames are PAD samples shorter than N (zero-padded by the kernel)
 SIZES = [int(v) for v in os.environ.get("SWEEP_LOG2N", ",".join(str(i) for i in range(5, 15))).split(",")]
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev)
@@ -29,12 +30,13 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
     for log2n in SIZES:
         n = 1 << log2n
         frames = max(64, (1 << 26) // n)  # ~64M samples per launch: far beyond L2
-        x = torch.randn((frames, n), device=dev, dtype=tdt)
+        flen = max(2, n - PAD) & ~1
+        x = torch.randn((frames, flen), device=dev, dtype=tdt)
         bins = n // 2 + 1 if SIDES_ == "one" else n
         amp = torch.empty((frames, bins), dtype=tdt, device=dev)
         pk = torch.zeros((frames, 32), dtype=torch.uint8, device=dev)
         plan = ctx.plan(n, prec)
-        d = SpectrumDesc(sample_dtype=prec, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES[SIDES_],
+        d = SpectrumDesc(sample_dtype=prec, frame_len=flen, hop=flen, batch=frames, window=WINDOWS["hann"], sides=SIDES[SIDES_],
                          sample_rate=48000.0, raw_magnitude=0)
 
         if MODE == "cplx":  # Radix2Fft.forward: all N bins, two planes
@@ -62,9 +64,9 @@ for prec_name, prec, tdt in (("f64", F64, torch.float64), ("f32", F32, torch.flo
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         es = 8 if prec == F64 else 4
-        bpf = n * es + (2 * n * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0) + (bins * es if "phase" in MODE else 0)
+        bpf = flen * es + (2 * n * es if MODE == "cplx" else (bins * es if "amp" in MODE else 0) + (bins * es if "phase" in MODE else 0)
                         + ((32 if prec == F64 else 16) if "peak" in MODE else 0))
         gbs = frames * bpf / (ms * 1e-3) / 1e9
-        print(json.dumps({"mode": MODE, "sides": SIDES_, "precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+        print(json.dumps({"mode": MODE, "sides": SIDES_, "pad": PAD, "precision": prec_name, "n": n, "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
                           "gbs": gbs, "frac_of_measured_hbm": gbs / peak}), flush=True)
         del x, amp, pk, im, ph

@@ -214,9 +214,9 @@ def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, w
         p.win_a0, p.win_a1, p.win_a2 = winrot
     mode = 0
     if specialised:  # compile-time specialised kernel (MD_* bits); preconditions are the caller's job
-        assert p.vec_ok and frame_len >= n and cfull
+        assert p.vec_ok and cfull
         mode = (1 if "amp" in want else 0) | (2 if "phase" in want else 0) | (4 if "peak" in want else 0) | \
-               (8 if "complex" in want else 0) | (16 if sides == "two" else 0)
+               (8 if "complex" in want else 0) | (16 if sides == "two" else 0) | (32 if frame_len < n else 0)
     if variant:
         assert mode in (1, 5, 4) and n == 1024
         rc = lib().emu_r2c_var(int(dtype == np.float64), variant, C.byref(p), nblocks, mode)

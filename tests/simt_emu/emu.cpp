@@ -33,6 +33,9 @@ static int run_r2c(const R2CParams& p, int nblocks, int mode) {
       case MD_CPLX: return run_r2c_m<T, LOG2M, MD_CPLX>(p, nblocks);
       case MD_AMP | MD_PHASE | MD_PEAK: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK>(p, nblocks);
       case MD_AMP | MD_TWO: return run_r2c_m<T, LOG2M, MD_AMP | MD_TWO>(p, nblocks);
+      case MD_AMP | MD_PAD: return run_r2c_m<T, LOG2M, MD_AMP | MD_PAD>(p, nblocks);
+      case MD_AMP | MD_PEAK | MD_PAD: return run_r2c_m<T, LOG2M, MD_AMP | MD_PEAK | MD_PAD>(p, nblocks);
+      case MD_AMP | MD_PHASE | MD_PEAK | MD_PAD: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK | MD_PAD>(p, nblocks);
       case MD_AMP | MD_PHASE | MD_PEAK | MD_TWO: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK | MD_TWO>(p, nblocks);
       default: break;
     }

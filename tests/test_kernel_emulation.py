@@ -250,3 +250,22 @@ def test_two_sided_specialised_equals_generic(n, dtype, want):
     b = E.r2c(x.reshape(-1), n, specialised=True, **kw)
     for key in a:
         assert (a[key] == b[key]).all(), key
+
+
+@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("want", [("amp",), ("amp", "peak"), ("amp", "phase", "peak")])
+def test_zero_padded_specialised_equals_generic(n, dtype, want):
+    """MD_PAD: frames shorter than N (odd and even lengths, a single sample) through the specialised kernels'
+    predicated loads carry the generic kernel's bits."""
+    rng = np.random.default_rng(n + 11)
+    batch = 5
+    w = oracle.createWindow("hann", n)
+    for flen in (n - 3, n // 2 + 2, 1):
+        hop = (flen + 1) & ~1  # even hop keeps the vector alignment the specialised path needs
+        buf = rng.standard_normal((batch - 1) * hop + flen).astype(dtype)
+        kw = dict(dtype=dtype, batch=batch, window=w, sample_rate=8000.0, want=want, nblocks=2, frame_len=flen, hop=hop)
+        a = E.r2c(buf, n, **kw)
+        b = E.r2c(buf, n, specialised=True, **kw)
+        for key in a:
+            assert (a[key] == b[key]).all(), (flen, key)
