@@ -162,7 +162,7 @@ def test_launch_and_plan_accounting(emu_api):
                                            # switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
                                            ("7,6", 8192, {"PDSP_BIG_TMA": "0"}),
                                            ("7,6", 8192, {"PDSP_BIG_TMA": "1"}),
-                                           ("6,6,6", 1 << 18, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "1"}),
+                                           ("6,6", 4096, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "1"}),
                                            ("7,6", 8192, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "0",
                                                           "PDSP_BIG_PREFETCH": "0"})])
 def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n, env):
