@@ -348,16 +348,14 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       auto load_frame = [&](auto* s) {
         if constexpr ((MODE & MD_PAD) != 0) {
           // buildFrame's zero padding (spectrum.ts:36-43): pairs at or beyond frame_len read as 0, the pair that
-          // straddles an odd frame_len keeps its first sample.  A separate compile-time mode: the same test as a
+          // straddles an odd frame_len would keep its first sample (generic kernel only).  A separate compile-time mode: the same test as a
           // run-time branch around these loads cost the whole-frame kernels 2-5 %.
-          // (keeping the vector loads unconditional and zeroing by selects measured far worse: 0.68 -> 0.38)
+          // (keeping the vector loads unconditional and zeroing by selects measured far worse: 0.68 -> 0.38.  The host
+          // sends odd frame lengths - one pair would straddle the end - to the generic kernel.)
           static_for<0, P>([&](auto qi) {
             const int i0 = 2 * (t + TF * decltype(qi)::value);
             cx<T> pr{(T)0, (T)0};
-            if (i0 + 1 < lim)
-              pr = load_pair<T>(s, i0);
-            else if (i0 < lim)
-              pr.x = (T)s[i0];
+            if (i0 < lim) pr = load_pair<T>(s, i0);
             v[decltype(qi)::value] = pr;
           });
         } else {

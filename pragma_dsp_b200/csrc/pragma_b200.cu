@@ -633,6 +633,7 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     // compile-time specialised kernel when the call is the regular batched shape, generic otherwise
     int mode = (d_amp ? MD_AMP : 0) | (d_phase ? MD_PHASE : 0) | (d_peaks ? MD_PEAK : 0) | (d_cre ? MD_CPLX : 0) |
                (p.two_sided ? MD_TWO : 0) | (d->frame_len < n ? MD_PAD : 0);
+    if ((mode & MD_PAD) && (d->frame_len & 1)) mode = -1;  // MD_PAD loads whole sample pairs: even frame lengths only
     const bool regular = p.vec_ok && (d_cre == nullptr || (cfull && !p.two_sided)) &&
                          mode_is_specialised(mode);
     if (regular && pl->precision == PDSP_F64 && d->window != PDSP_WIN_RECT && n >= 4) {
