@@ -362,7 +362,10 @@ def run_b200(args, w):
         with torch.cuda.stream(compute):
             if comm is not None and i >= 2:
                 compute.wait_event(gather_done[i & 1])  # the gather that last read this peaks buffer
-            if timed:
+            # per-launch duration (roofline.achieved): CUDA events around every 4th launch of the timed region - an
+            # event pair around every launch adds ~4 us of stream bubbles per step to the step time itself
+            probe = timed and (i % 4 == 0)
+            if probe:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(compute)
@@ -371,7 +374,7 @@ def run_b200(args, w):
                                                  rank * frames, C.c_void_p(compute.cuda_stream)))
             else:
                 check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), C.c_void_p(compute.cuda_stream)))
-            if timed:
+            if probe:
                 e1.record(compute)
                 kernel_events.append((e0, e1))
             if comm is not None:
