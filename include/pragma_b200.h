@@ -65,6 +65,11 @@ int pdsp_ctx_create(int device, pdsp_ctx** ctx);
 int pdsp_ctx_destroy(pdsp_ctx* ctx);
 int pdsp_ctx_sync(pdsp_ctx* ctx);
 int pdsp_ctx_device(const pdsp_ctx* ctx);
+/* Tuning / test hook: sets one tunable of the context ("staged", "chunk_bytes", "big_tma", "big_interleave",
+ * "big_prefetch", "big_chunk", "big_factors", "big_resident", "variant"); value NULL or "" restores the default.  The same
+ * tunables are read ONCE from the environment (PDSP_<KEY>) when the context is created; nothing on the launch
+ * path reads the environment.  Results do not depend on them (parity tests run every setting). */
+int pdsp_ctx_tune(pdsp_ctx* ctx, const char* key, const char* value);
 int pdsp_ctx_sm_count(const pdsp_ctx* ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 int64_t pdsp_ctx_launch_count(const pdsp_ctx* ctx);
@@ -82,6 +87,10 @@ int pdsp_bin_frequencies(int32_t size, double sample_rate, int sides, double* ou
  *      cached per context like FourierLive's Map (src/effect/index.ts:30-40) ------------------ */
 int pdsp_plan_get(pdsp_ctx* ctx, int32_t size, int precision, pdsp_plan** plan);
 int32_t pdsp_plan_size(const pdsp_plan* plan);
+/* Frees the scratch planes the large-transform path keeps per (plan, stream); call it before destroying a stream that
+ * was passed to a *_dev entry point with an FFT size above 16384 (NULL = the context's stream).  The ingestion ring
+ * does this for its own streams in pdsp_ingest_close. */
+int pdsp_plan_release_stream(pdsp_plan* plan, void* stream);
 int pdsp_plan_precision(const pdsp_plan* plan);
 
 /* ---- Radix2Fft / FFT methods, host buffers ------------------------------------------------- */

@@ -41,6 +41,8 @@ SYMBOLS = {
     "pdsp_ctx_destroy": (C.c_int, [_vp]),
     "pdsp_ctx_sync": (C.c_int, [_vp]),
     "pdsp_ctx_device": (C.c_int, [_vp]),
+    "pdsp_ctx_tune": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "pdsp_plan_release_stream": (C.c_int, [_vp, _vp]),
     "pdsp_ctx_sm_count": (C.c_int, [_vp]),
     "pdsp_ctx_launch_count": (_i64, [_vp]),
     "pdsp_is_power_of_two": (C.c_int, [_i32]),
@@ -123,6 +125,10 @@ class Context:
 
     def sync(self) -> None:
         check(lib().pdsp_ctx_sync(self.h))
+
+    def tune(self, key: str, value=None) -> None:
+        """pdsp_ctx_tune: set one tunable (tests and sweeps); None restores the default."""
+        check(lib().pdsp_ctx_tune(self.h, key.encode(), None if value is None else str(value).encode()))
 
     @property
     def launch_count(self) -> int:

@@ -22,7 +22,12 @@ LIB = os.path.join(HERE, "libpragma_b200.so")
 NVCC = os.environ.get("PDSP_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 EXTRA = os.environ.get("PDSP_EXTRA_NVCC_FLAGS", "").split()  # experiments only (e.g. -DPDSP_F32_P32_FROM=7)
-FLAGS = ARCH + EXTRA + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+# --tuning / PDSP_TUNING=1: also build the 17 alternative N=1024 mappings (fft_config.h PDSP_VARIANT, selected with
+# pdsp_ctx_tune("variant") / PDSP_VARIANT).  The shipped library carries the default mapping only.
+TUNING = os.environ.get("PDSP_TUNING", "0") == "1"
+LIB = os.environ.get("PDSP_LIB_OUT", LIB)  # experiment builds go to another file (and object directory)
+OBJ = os.environ.get("PDSP_OBJ_DIR", OBJ)
+FLAGS = ARCH + EXTRA + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "--compress-mode=size", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                 "-ccbin", "/usr/bin/g++"]
 
 
@@ -47,8 +52,8 @@ def _digest(paths, extra):
 
 
 def _compile(args):
-    src, obj, defs, stamp = args
-    cmd = [NVCC] + FLAGS + defs + ["-c", src, "-o", obj]
+    src, obj, flags, stamp = args
+    cmd = [NVCC] + flags + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         return obj, r.returncode, r.stdout + r.stderr
@@ -56,7 +61,8 @@ def _compile(args):
     return obj, 0, r.stderr
 
 
-def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
+def build(force: bool = False, jobs: int | None = None, verbose: bool = True, tuning: bool | None = None) -> str:
+    tuning = TUNING if tuning is None else tuning
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "pragma_b200.h"))
@@ -69,17 +75,18 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
                 f"-DPDSP_INST_NAME={name}"]
         units.append((os.path.join(CSRC, "inst.cu"), os.path.join(OBJ, name + ".o"), defs))
     nvar = int(re.search(r"kNumVariants = (\d+)", open(os.path.join(CSRC, "fft_config.h")).read()).group(1))
-    for v in range(1, nvar):
+    flags = FLAGS + (["-DPDSP_TUNING=1"] if tuning else [])
+    for v in range(1, nvar if tuning else 1):
         for tag, ctype in (("f64", "double"), ("f32", "float")):
             name = f"launch_r2c_var_{tag}_{v}"
             units.append((os.path.join(CSRC, "inst_var.cu"), os.path.join(OBJ, name + ".o"),
                           [f"-DPDSP_VAR_T={ctype}", f"-DPDSP_VAR={v}", f"-DPDSP_INST_NAME={name}"]))
     for src, obj, defs in units:
-        stamp = _digest(headers + [src], " ".join(FLAGS + defs))
+        stamp = _digest(headers + [src], " ".join(flags + defs))
         objs.append(obj)
         old = open(obj + ".stamp").read() if os.path.exists(obj + ".stamp") and os.path.exists(obj) else ""
         if force or old != stamp:
-            tasks.append((src, obj, defs, stamp))
+            tasks.append((src, obj, flags + defs, stamp))
     if tasks:
         if verbose:
             print(f"[pragma_dsp_b200.build] compiling {len(tasks)} unit(s) for sm_100a ...", flush=True)
@@ -90,7 +97,10 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
                     raise RuntimeError(f"nvcc failed for {obj}")
                 if verbose and log.strip():
                     print(log.strip())
-    if tasks or not os.path.exists(LIB):
+    stale = [o for o in os.listdir(OBJ) if o.endswith(".o") and os.path.join(OBJ, o) not in objs]
+    for o in stale:  # objects of units no longer built (e.g. tuning variants after a default build)
+        os.remove(os.path.join(OBJ, o))
+    if tasks or stale or not os.path.exists(LIB):
         cmd = [NVCC] + ARCH + ["-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -105,5 +115,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--tuning", action="store_true", help="also build the N=1024 tuning variants (-DPDSP_TUNING)")
     a = ap.parse_args()
-    build(force=a.force, jobs=a.jobs)
+    build(force=a.force, jobs=a.jobs, tuning=a.tuning or None)

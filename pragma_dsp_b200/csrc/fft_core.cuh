@@ -240,13 +240,34 @@ struct FftEngine {
   static constexpr int TW_ELEMS = tw_offset(NPASS);
   PDSP_DEVICE static int pad(int i) { return i + (i >> PAD_SHIFT); }
 
+  // Exchange by shuffle instead of shared memory (see fft()): fp64, M = 512 = 16 x 16 x 2, one warp per frame, pass 1.
+  template <bool BLOCKSYNC>
+  static constexpr bool shuffle_pass(int pass) {
+    return PDSP_SHUFFLE_EXCHANGE && !BLOCKSYNC && sizeof(T) == 8 && LOG2M == 9 && LOG2P == 4 && RB == 4 && NPASS == 3 &&
+           pass == NPASS - 2;
+  }
+  // the last pass whose output goes through the shared-memory buffer (-1: none)
+  template <bool BLOCKSYNC>
+  static constexpr int last_smem_pass() {
+    int r = -1;
+    for (int i = 0; i + 1 < NPASS; ++i)
+      if (!shuffle_pass<BLOCKSYNC>(i)) r = i;
+    return r;
+  }
+  struct NoHook {
+    PDSP_DEVICE void operator()() const {}
+  };
+
   // v[q] holds element t + TF*q (natural order) on entry and the transform on exit.
   // tw: the per-schedule table described at tw_offset() (TW_ELEMS entries).
   // BLOCKSYNC: the frame's threads are spread over the CTA's warps (column-tiled passes of the
   // large-N path), so every exchange is a __syncthreads.
-  template <bool BLOCKSYNC = false>
+  // after_smem(): called once, as soon as the frame's threads are done with the shared-memory buffer (after the last
+  // exchange that goes through it, or straight away when there is none) - the staged kernels refill it from there.
+  template <bool BLOCKSYNC = false, class Hook = NoHook>
   PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int slot,
-                              int slots_per_cta) {
+                              int slots_per_cta, Hook after_smem = Hook{}) {
+    if constexpr (last_smem_pass<BLOCKSYNC>() < 0) after_smem();
     auto sync = [&]() {
       if constexpr (BLOCKSYNC)
         simt::sync_block();
@@ -273,8 +294,7 @@ struct FftEngine {
       // (h', l), the outputs of parity h' of both (0, l) and (1, l): each thread keeps 8 of its outputs and swaps
       // the other 8 with lane t ^ 16.  32 SHFLs replace 16 STS.128 + 16 LDS.128 (128 L1 wavefronts) and two
       // warp barriers; the kernel is L1-bound.
-      constexpr bool SHUF = PDSP_SHUFFLE_EXCHANGE && !BLOCKSYNC && sizeof(T) == 8 && LOG2M == 9 && LOG2P == 4 && RB == 4 &&
-                            pass == NPASS - 2 && NPASS == 3;
+      constexpr bool SHUF = shuffle_pass<BLOCKSYNC>(pass);
       [[maybe_unused]] cx<T> w0[R];
       static_for<0, BPT>([&](auto ui) {
         constexpr int u = decltype(ui)::value;
@@ -323,6 +343,7 @@ struct FftEngine {
         sync();
         static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
         sync();
+        if constexpr (pass == last_smem_pass<BLOCKSYNC>()) after_smem();
       }
     });
   }

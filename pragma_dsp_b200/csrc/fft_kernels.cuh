@@ -58,12 +58,6 @@ struct R2CParams {
   void* peer[8];
   int n_peers;
   long long peer_offset;
-  // window by rotation (fp64 specialised kernels): w[i] = a0 - a1*cos(th_i) + a2*cos(2*th_i), th_i = 2*pi*i/(N-1).
-  // winphase[i] = (cos th_i, sin th_i) for i < N; each thread loads its two base phases and rotates them by
-  // compile-time constants - two 16-byte loads per frame instead of one per complex point.  Null: use `window`.
-  const void* winphase;
-  double win_a0, win_a1, win_a2;
-  int l2_prefetch;  // 1: one lane per frame bulk-prefetches the next frame of its slot into L2
 };
 
 struct C2CParams {
@@ -209,7 +203,7 @@ PDSP_DEVICE_NOINLINE float t_hypot_slow(float x, float y) { return hypotf(x, y);
 PDSP_DEVICE_NOINLINE double t_hypot_slow(double x, double y) { return hypot(x, y); }
 
 // sqrt without the IEEE slow path.  fp32: MUFU.SQRT (sqrt.approx, <= 1 ulp-ish, 2^-23 relative).
-// fp64: MUFU.RSQ64H seed + two Newton steps (the second on the residual, with the unrefined 1/(2 sqrt)), branch-free; exact 0 for +0; inf/NaN and sums outside
+// fp64: MUFU.RSQ64H seed + one third-order (Halley) step, 5 DP instructions, branch- and select-free; exact 0 for +0; inf/NaN and sums outside
 // the normal range are caught by the caller's exponent tracker and redone with hypot().
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
 PDSP_DEVICE float fast_sqrt(float s) {
@@ -218,15 +212,15 @@ PDSP_DEVICE float fast_sqrt(float s) {
   return r;
 }
 PDSP_DEVICE double fast_sqrt(double s) {
+  // MUFU.RSQ64H reads the high word only: clamping it (one integer max, ALU pipe) to the smallest normal keeps the seed
+  // finite for s = +0, so that g = s * y is an exact 0 there without a select; relative error of y about 2^-20
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-  double g = s * y;          // ~ sqrt(s), 22 bits
-  const double h = 0.5 * y;  // ~ 1 / (2 sqrt(s)), 22 bits: enough for the last correction (error 2^-44 * 2^-22)
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g);          // 44 bits
-  r = fma(-g, g, s);         // residual s - g^2
-  g = fma(r, h, g);          // full precision
-  return __double2hiint(s) == 0 ? 0.0 : g;  // +0 (and sub-2^-1042 dust): rsqrt gave inf
+  const double sc = __hiloint2double(max(__double2hiint(s), 0x00100000), 0);
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(sc));
+  const double g = s * y;              // ~ sqrt(s)
+  const double e = fma(-g, y, 1.0);    // 1 - s*y^2
+  const double q = fma(0.375, e, 0.5);
+  return fma(g * e, q, g);             // g * (1 + e/2 + 3e^2/8): third-order step, error ~ e^3 < 2^-58
 }
 #else
 PDSP_DEVICE float fast_sqrt(float s) { return sqrtf(s); }
@@ -242,12 +236,24 @@ PDSP_DEVICE double t_mag_checked(double re, double im) {
 }
 PDSP_DEVICE float t_mag_checked(float re, float im) { return fast_sqrt(re * re + im * im); }
 
-template <typename T>
-struct PeakCand {
-  T v;     // scaled amplitude of the best non-DC bin so far (0 = none)
-  int k;   // its bin (0 = none)
-  T re, im;
-};
+// a[i] for a run-time i over a register array (a switch: only the owning lane of one frame takes one arm)
+template <typename T, int NQ>
+PDSP_DEVICE cx<T> pick_reg(const cx<T> (&a)[NQ], int i) {
+  static_assert(NQ <= 16, "at most 32 points per thread");
+  cx<T> r = a[0];
+  switch (i) {
+#define PDSP_PICK(J) \
+  case J:            \
+    if constexpr (NQ > J) r = a[J]; \
+    break;
+    PDSP_PICK(1) PDSP_PICK(2) PDSP_PICK(3) PDSP_PICK(4) PDSP_PICK(5) PDSP_PICK(6) PDSP_PICK(7) PDSP_PICK(8)
+    PDSP_PICK(9) PDSP_PICK(10) PDSP_PICK(11) PDSP_PICK(12) PDSP_PICK(13) PDSP_PICK(14) PDSP_PICK(15)
+#undef PDSP_PICK
+    default:
+      break;
+  }
+  return r;
+}
 
 // findPeak ordering (/root/reference/src/public/spectrum.ts:74-105): strict '>' scanning upward,
 // so among equal values the lowest index wins; a candidate needs v > 0; NaN never wins.
@@ -269,7 +275,27 @@ enum : int {
   MD_CPLX = 8,    // complex spectrum, all N bins (Radix2Fft.forward)
   MD_TWO = 16,    // two-sided amplitude / phase rows (N bins, mirror bins written); one-sided (N/2+1) otherwise
   MD_PAD = 32,    // frames shorter than N, zero-padded (spectrum()'s default for lengths that are not a power of two)
+  MD_STAGED = 64, // software-pipelined sample loads: one lane per frame fetches the NEXT frame of its slot with a bulk
+                  // asynchronous copy (cp.async.bulk + mbarrier) into the slot's shared-memory buffer while the current
+                  // frame is transformed; needs 16-byte aligned frames (base and hop) and sample type no wider than T
 };
+
+// Shared-memory plan of r2c_kernel: per frame slot the exchange buffer of the engine, which in staged mode doubles as the
+// landing zone of the next frame's raw samples (N samples of at most sizeof(T) bytes = M complex elements) and is kept
+// 16-byte aligned; staged mode appends one mbarrier per slot.
+template <typename T, typename E, int MODE>
+constexpr int r2c_slot_elems() {
+  int e = E::NEEDS_SMEM ? E::SMEM_ELEMS : 0;
+  if ((MODE & MD_STAGED) != 0) {
+    if (e < E::M) e = E::M;
+    while ((e * (int)sizeof(cx<T>)) % 16 != 0) ++e;
+  }
+  return e;
+}
+template <typename T, typename E, int MODE, int SLOTS>
+constexpr size_t r2c_smem_bytes() {
+  return sizeof(cx<T>) * (size_t)r2c_slot_elems<T, E, MODE>() * SLOTS + ((MODE & MD_STAGED) != 0 ? 8 * SLOTS + 8 : 0);
+}
 
 template <typename T, typename S>
 PDSP_DEVICE cx<T> load_pair(const S* PDSP_RESTRICT s, int i0) {
@@ -290,7 +316,13 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   // through shared memory.  Warp w of the frame holds logical threads 16w..16w+15 on lanes 0-15 and their
   // partners TF-16w..TF-16w-15 on lanes 16-31; t = 0 and t = TF/2 pair with themselves (warp 0, lanes 0 and 16).
   constexpr bool PAIRED = TF > 32;
-  constexpr int SLOT_ELEMS = E::NEEDS_SMEM ? E::SMEM_ELEMS : 0;
+  constexpr bool STAGED = !GEN && (MODE & MD_STAGED) != 0;
+  static_assert(!STAGED || (MODE & MD_PAD) == 0, "staged loads fetch whole frames");
+  constexpr int SLOT_ELEMS = r2c_slot_elems<T, E, MODE>();
+  // The amplitude scale is a power of two (1, 1/N or 2/N): in the specialised kernels without a complex output it is
+  // folded into the Hermitian post-pass constants, so X arrives scaled (bit-identical to scaling |X| afterwards, short
+  // of subnormal results) and the per-bin multiply disappears; DC / Nyquist take one extra factor s_edge / s_mid.
+  constexpr bool FOLD = !GEN && (MODE & MD_CPLX) == 0;
   // peak-only kernels rank bins by |X|^2 (no square root per bin); the winner's amplitude is computed
   // once, in the finishing loop.  Frames spanning several warps keep the linear key.
   constexpr bool KEYSQ = MODE == MD_PEAK && TF <= 32;
@@ -314,7 +346,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const int sh = (two_sided && p.shift) ? M : 0;  // fftShift fused into the two-sided stores (row rotation by N/2)
   const int cbins = cfull ? N : M + 1;
   const T s_edge = (T)p.scale_edge, s_mid = (T)p.scale_mid;
-  [[maybe_unused]] const T edge_key = (T)((p.scale_edge / p.scale_mid) * (p.scale_edge / p.scale_mid));
+  [[maybe_unused]] const T edge_ratio = (T)(p.scale_edge / p.scale_mid);  // 1/2 (one-sided) or 1
+  [[maybe_unused]] const T edge_key = edge_ratio * edge_ratio;
   const bool want_cplx = GEN ? p.out_re != nullptr : (MODE & MD_CPLX) != 0;
   const bool want_amp = GEN ? p.amp != nullptr : (MODE & MD_AMP) != 0;
   const bool want_phase = GEN ? p.phase != nullptr : (MODE & MD_PHASE) != 0;
@@ -336,6 +369,28 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   const Cnt it_begin = IT32 ? (Cnt)0 : (Cnt)g_begin;
   const Cnt n_iter = IT32 ? (Cnt)(g_end > g_begin ? g_end - g_begin : 0) : (Cnt)g_end;
   long long f_run = g_begin * SLOTS + slot;
+
+  // ---- staged mode: the slot's buffer receives frame i+1 (one bulk asynchronous copy, issued by the frame's first lane
+  // as soon as frame i's last shared-memory exchange is over) while frame i goes through the remaining passes, the
+  // post-pass and the stores; an mbarrier per slot counts the bytes in.  The global-load latency that the direct form
+  // exposes at the top of every iteration (a quarter of the fp64 kernel's stall cycles, profiles/r1) is off the path.
+  [[maybe_unused]] unsigned long long* bar = nullptr;
+  [[maybe_unused]] unsigned stage_phase = 0u;
+  [[maybe_unused]] const unsigned stage_bytes = (unsigned)N * (p.sample_dtype == DT_F32 ? 4u : 8u);
+  [[maybe_unused]] auto stage_issue = [&](long long fi) {  // first lane of the frame only
+    const long long ff = fi < p.batch ? fi : p.batch - 1;   // a tail slot re-reads the last frame
+    const char* src = static_cast<const char*>(p.samples) + (size_t)(ff * p.hop) * (p.sample_dtype == DT_F32 ? 4 : 8);
+    simt::fence_proxy_async();  // the lanes' generic-proxy accesses to the buffer (ordered by the sync before this call)
+    simt::mbar_expect_tx(bar, stage_bytes);
+    simt::bulk_load_1d(sm, src, stage_bytes, bar);
+  };
+  if constexpr (STAGED) {
+    bar = reinterpret_cast<unsigned long long*>(simt::smem() + ((sizeof(cx<T>) * (size_t)SLOT_ELEMS * SLOTS + 7) & ~(size_t)7)) + slot;
+    if (tl == 0) simt::mbar_init(bar, 1);
+    simt::sync_block();
+    if (tl == 0 && it_begin < n_iter) stage_issue(IT32 ? f_run : (long long)it_begin * SLOTS + slot);
+  }
+
   for (Cnt it = it_begin; it < n_iter; ++it, f_run += SLOTS) {
     const long long f = IT32 ? f_run : (long long)it * SLOTS + slot;
     const bool valid = f < p.batch;
@@ -344,7 +399,6 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     cx<T> v[P];
     if constexpr (!GEN) {
       // whole aligned frames: one vector load per complex point; a tail slot re-reads the last frame
-      const long long base = (valid ? f : p.batch - 1) * p.hop;
       auto load_frame = [&](auto* s) {
         if constexpr ((MODE & MD_PAD) != 0) {
           // buildFrame's zero padding (spectrum.ts:36-43): pairs at or beyond frame_len read as 0, the pair that
@@ -362,45 +416,23 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
         }
       };
-      if (p.sample_dtype == DT_F32)
-        load_frame(static_cast<const float*>(p.samples) + base);
-      else
-        load_frame(static_cast<const double*>(p.samples) + base);
-      if (p.l2_prefetch && tl == 0 && it + 1 < n_iter && f + SLOTS < p.batch) {
-        // the next frame of this slot: its samples are in L2 by the time the loads above come round again
-        const size_t ses = p.sample_dtype == DT_F32 ? 4 : 8;
-        const char* nxt = static_cast<const char*>(p.samples) + (size_t)((f + SLOTS) * p.hop) * ses;
-        const unsigned nbytes = (unsigned)(N * ses);
-        if (((reinterpret_cast<uintptr_t>(nxt) | nbytes) & 15u) == 0) simt::prefetch_l2_bulk(nxt, nbytes);
+      if constexpr (STAGED) {
+        // the frame was fetched into the slot's buffer during the previous iteration (or by the prologue)
+        simt::mbar_wait(bar, stage_phase);
+        stage_phase ^= 1u;
+        if (p.sample_dtype == DT_F32)
+          load_frame(reinterpret_cast<const float*>(sm));
+        else
+          load_frame(reinterpret_cast<const double*>(sm));
+        frame_sync<TF>(slot, SLOTS);  // every lane holds its samples: the exchanges may overwrite the buffer
+      } else {
+        const long long base = (valid ? f : p.batch - 1) * p.hop;
+        if (p.sample_dtype == DT_F32)
+          load_frame(static_cast<const float*>(p.samples) + base);
+        else
+          load_frame(static_cast<const double*>(p.samples) + base);
       }
-      if constexpr (sizeof(T) == 8) {
-        if (p.winphase != nullptr) {
-          const cx<T>* PDSP_RESTRICT wph = static_cast<const cx<T>*>(p.winphase);
-          const cx<T> e0 = ldg_cx(wph + 2 * t), e1 = ldg_cx(wph + 2 * t + 1);  // phases of samples 2t, 2t+1
-          const T a0 = (T)p.win_a0, a1 = (T)p.win_a1, a2 = (T)p.win_a2;
-          static_for<0, P>([&](auto qi) {
-            constexpr int q = decltype(qi)::value;
-            // samples 2(t + TF*q) (+1): phase advanced by q * 2*pi*(2*TF)/(N-1)
-            constexpr long double ang = 2 * kPiL * (long double)(2 * TF * q) / (long double)(N - 1);
-            constexpr T CQ = (T)cx_cos(ang), SQ = (T)cx_sin(ang);
-            const T c0 = e0.x * CQ - e0.y * SQ, c1 = e1.x * CQ - e1.y * SQ;
-            T w0 = a0 - a1 * c0, w1 = a0 - a1 * c1;
-            if (a2 != (T)0) {  // Blackman: cos(2 th) = 2 cos^2(th) - 1
-              w0 += a2 * ((T)2 * c0 * c0 - (T)1);
-              w1 += a2 * ((T)2 * c1 * c1 - (T)1);
-            }
-            v[q].x *= w0;
-            v[q].y *= w1;
-          });
-        } else if (win != nullptr) {
-          static_for<0, P>([&](auto qi) {
-            constexpr int q = decltype(qi)::value;
-            const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
-            v[q].x *= w.x;
-            v[q].y *= w.y;
-          });
-        }
-      } else if (win != nullptr) {
+      if (win != nullptr) {
         static_for<0, P>([&](auto qi) {
           constexpr int q = decltype(qi)::value;
           const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
@@ -453,25 +485,99 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     }
 
     // ---- M-point complex FFT of the packed frame
-    E::fft(v, t, sm, tw, slot, SLOTS);
+    if constexpr (STAGED) {
+      // after the last exchange through the buffer: send for the next frame of this slot
+      E::fft(v, t, sm, tw, slot, SLOTS, [&]() {
+        if (tl == 0 && it + 1 < n_iter) stage_issue(f + SLOTS);
+      });
+    } else {
+      E::fft(v, t, sm, tw, slot, SLOTS);
+    }
 
-    // ---- Hermitian split + fused epilogue
+    // ---- Hermitian split: X[k], X[M-k] for the thread's pairs (and X[M/2] in thread 0), kept in registers
+    // The bins of one thread form two streams: stream 0 walks k = t + TF*q upward (XA[q]), stream 1 walks M - k
+    // downward (XB[q]).  The transform's registers die here; everything below - outputs, the hypot() rerun, the
+    // peak record - works from XA / XB / XH.
+    constexpr int NQ = M == 1 ? 1 : P / 2;
+    cx<T> XA[NQ], XB[NQ], XH{(T)0, (T)0};
+    if constexpr (M == 1) {
+      // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
+      const T fs = FOLD ? s_mid : (T)1;
+      XA[0] = cx<T>{(v[0].x + v[0].y) * fs, (T)0};
+      XB[0] = cx<T>{(v[0].x - v[0].y) * fs, (T)0};
+    } else {
+      // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
+      // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
+      constexpr bool DERIVE = sizeof(T) == 8 && (16 % P) == 0 && P >= 2;  // see FftEngine::fft
+      const T hs = FOLD ? (T)0.5 * s_mid : (T)0.5;                         // folded amplitude scale (a power of two)
+      cx<T> post0{(T)0, (T)0};
+      if constexpr (DERIVE) {
+        post0 = ldg_cx(post + t);
+        if constexpr (FOLD) post0 = ew_mul(post0, cx<T>{s_mid, s_mid});
+      }
+      static_for<0, P / 2>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        cx<T> zp;  // Z[(M - k) % M], k = t + TF*q < M/2
+        if constexpr (PAIRED) {
+          const cx<T> mine = v[P - 1 - q];
+          cx<T> got;
+          got.x = simt::shfl_xor(mine.x, 16, 32);
+          got.y = simt::shfl_xor(mine.y, 16, 32);
+          zp = (t == 0) ? v[(P - q) % P] : (t == TF / 2 ? mine : got);
+        } else if constexpr (TF == 1) {
+          zp = v[(P - q) % P];
+        } else {
+          const cx<T> mine = v[P - 1 - q];
+          cx<T> got;
+          got.x = simt::shfl(mine.x, (TF - t) & (TF - 1), TF);
+          got.y = simt::shfl(mine.y, (TF - t) & (TF - 1), TF);
+          zp = (t == 0) ? v[(P - q) % P] : got;
+        }
+        const cx<T> a = v[q];
+        const cx<T> sum = ew_fma(zp, cx<T>{(T)1, (T)-1}, a);  // A + conj(Zp)
+        const cx<T> dif = ew_fma(zp, cx<T>{(T)-1, (T)1}, a);  // A - conj(Zp)
+        cx<T> w;                                               // (wi/2, -wr/2): W_N^k * (-i/2)
+        if constexpr (DERIVE) {
+          w = mul_w32<(q * 16 / P) % 16>(post0);
+        } else {
+          w = ldg_cx(post + t + TF * q);
+          if constexpr (FOLD) w = ew_mul(w, cx<T>{s_mid, s_mid});
+        }
+        const cx<T> tt = cmul(dif, w);
+        cx<T> xa = ew_fma(sum, cx<T>{hs, hs}, tt);                      // X[k]
+        cx<T> xb = ew_fma(sum, cx<T>{hs, -hs}, cx<T>{-tt.x, tt.y});     // X[M-k] = conj(E - W*O)
+        if constexpr (q == 0) {
+          // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
+          // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
+          if (t == 0) {
+            xa.y = (T)0;
+            xb.y = (T)0;
+          }
+        }
+        XA[q] = xa;
+        XB[q] = xb;
+      });
+      // self-paired bin M/2 = conj(Z[M/2]) (thread 0; above every stream-0 bin of that thread)
+      if (t == 0) XH = FOLD ? cx<T>{v[P / 2].x * s_mid, -(v[P / 2].y * s_mid)} : cx<T>{v[P / 2].x, -v[P / 2].y};
+    }
+
+    // ---- fused epilogue.  Every address is a per-thread base plus a compile-time offset.
     T* o_re = valid && want_cplx ? static_cast<T*>(p.out_re) + f * cbins : nullptr;
     T* o_im = valid && want_cplx ? static_cast<T*>(p.out_im) + f * cbins : nullptr;
     T* o_amp = valid && want_amp ? static_cast<T*>(p.amp) + f * bins : nullptr;
     T* o_ph = valid && PHASE && want_phase ? static_cast<T*>(p.phase) + f * bins : nullptr;
-    PeakCand<T> best{(T)0, 0, (T)0, (T)0};
-    T dc_re = (T)0, dc_amp = (T)0;
+    T best_v = (T)0;  // scaled amplitude (squared key in peak-only mode) of the thread's best non-DC bin, 0 = none
+    int best_k = 0;
+    T dc_amp = (T)0;
 
-    // The bins of one thread form two streams: stream 0 walks k = t + TF*q upward, stream 1 walks
-    // M - k downward.  Every address is a per-thread base plus a compile-time offset.
-    auto post_pass = [&](auto careful_c) {
+    auto epilogue = [&](auto careful_c) {
       constexpr bool CAREFUL = decltype(careful_c)::value;  // second run with hypot() for out-of-range sums
       // findPeak keeps the first of equal values (strict '>' scanning upward): stream 0 is visited in
       // ascending k so '>' suffices; stream 1 is visited in descending k so '>=' lets the lower bin
       // win a tie (its threshold starts at the smallest positive number: a candidate needs v > 0).
-      PeakCand<T> c0{(T)0, 0, (T)0, (T)0};
-      PeakCand<T> c1{sizeof(T) == 8 ? (T)4.9406564584124654e-324 : (T)1.401298464324817e-45, 0, (T)0, (T)0};
+      // Only (value, bin) are tracked per bin; the winner's re / im are picked out of XA / XB once per frame.
+      T c0v = (T)0, c1v = sizeof(T) == 8 ? (T)4.9406564584124654e-324 : (T)1.401298464324817e-45;
+      int c0k = 0, c1k = 0;
       unsigned hi_max = 0u, lo_min = 0xffffffffu;  // exponent range of re^2+im^2 seen by this thread (fp64)
 
       auto emit = [&](auto stream_c, auto off_c, auto edge_c, int k, cx<T> X, T ph) {
@@ -513,9 +619,14 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
               }
               mag = fast_sqrt(ss);
             }
-            T scale = s_mid;
-            if constexpr (EDGE) scale = (k == 0 || k == M) ? s_edge : s_mid;
-            a = mag * scale;
+            if constexpr (FOLD) {
+              a = mag;  // X carries s_mid already
+              if constexpr (EDGE) a = (k == 0 || k == M) ? mag * edge_ratio : mag;
+            } else {
+              T scale = s_mid;
+              if constexpr (EDGE) scale = (k == 0 || k == M) ? s_edge : s_mid;
+              a = mag * scale;
+            }
           }
           if (want_amp && o_amp != nullptr) {
             (o_amp + b0 + ((EDGE && k == M) ? -sh : sh))[OFF] = a;  // shifted: k < M -> k + M, the Nyquist bin M -> 0
@@ -525,12 +636,11 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
             bool is_dc = false;
             if constexpr (EDGE) is_dc = k == 0;
             if (is_dc) {
-              dc_re = X.x;
               dc_amp = a;
             } else if constexpr (STREAM == 0) {
-              if (a > c0.v) c0 = PeakCand<T>{a, k, X.x, X.y};
+              if (a > c0v) c0v = a, c0k = k;
             } else {
-              if (a >= c1.v) c1 = PeakCand<T>{a, k, X.x, X.y};
+              if (a >= c1v) c1v = a, c1k = k;
             }
           }
         }
@@ -545,58 +655,17 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       using I1 = std::integral_constant<int, 1>;
 
       if constexpr (M == 1) {
-        // N = 2: X[0] = x0 + x1, X[1] = x0 - x1
-        const cx<T> x0{v[0].x + v[0].y, (T)0}, x1{v[0].x - v[0].y, (T)0};
         Pair2<T> ph{(T)0, (T)0};
         if constexpr (PHASE) {
-          if (want_phase) ph = t_atan2_x2(x0.y, x0.x, x1.y, x1.x);
+          if (want_phase) ph = t_atan2_x2(XA[0].y, XA[0].x, XB[0].y, XB[0].x);
         }
-        emit(I0{}, I0{}, std::true_type{}, 0, x0, ph.a);
-        emit(I1{}, I0{}, std::true_type{}, 1, x1, ph.b);
+        emit(I0{}, I0{}, std::true_type{}, 0, XA[0], ph.a);
+        emit(I1{}, I0{}, std::true_type{}, 1, XB[0], ph.b);
       } else {
-        // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
-        // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
-        constexpr bool DERIVE = sizeof(T) == 8 && (16 % P) == 0 && P >= 2;  // see FftEngine::fft
-        cx<T> post0{(T)0, (T)0};
-        if constexpr (DERIVE) post0 = ldg_cx(post + t);
         static_for<0, P / 2>([&](auto qi) {
           constexpr int q = decltype(qi)::value;
           const int k = t + TF * q;  // 0 <= k < M/2
-          cx<T> zp;                  // Z[(M - k) % M]
-          if constexpr (PAIRED) {
-            const cx<T> mine = v[P - 1 - q];
-            cx<T> got;
-            got.x = simt::shfl_xor(mine.x, 16, 32);
-            got.y = simt::shfl_xor(mine.y, 16, 32);
-            zp = (t == 0) ? v[(P - q) % P] : (t == TF / 2 ? mine : got);
-          } else if constexpr (TF == 1) {
-            zp = v[(P - q) % P];
-          } else {
-            const cx<T> mine = v[P - 1 - q];
-            cx<T> got;
-            got.x = simt::shfl(mine.x, (TF - t) & (TF - 1), TF);
-            got.y = simt::shfl(mine.y, (TF - t) & (TF - 1), TF);
-            zp = (t == 0) ? v[(P - q) % P] : got;
-          }
-          const cx<T> a = v[q];
-          const cx<T> sum = ew_fma(zp, cx<T>{(T)1, (T)-1}, a);  // A + conj(Zp)
-          const cx<T> dif = ew_fma(zp, cx<T>{(T)-1, (T)1}, a);  // A - conj(Zp)
-          cx<T> w;                                               // (wi/2, -wr/2): W_N^k * (-i/2)
-          if constexpr (DERIVE)
-            w = mul_w32<(q * 16 / P) % 16>(post0);
-          else
-            w = ldg_cx(post + k);
-          const cx<T> tt = cmul(dif, w);
-          cx<T> xa = ew_fma(sum, cx<T>{(T)0.5, (T)0.5}, tt);                                     // X[k]
-          cx<T> xb = ew_fma(sum, cx<T>{(T)0.5, (T)-0.5}, cx<T>{-tt.x, tt.y});                    // X[M-k] = conj(E - W*O)
-          if constexpr (q == 0) {
-            // DC and Nyquist of a real frame are real; the reference's imaginary parts there are +0
-            // (sums of +0), so atan2 gives 0 / +pi rather than -0 / -pi.
-            if (t == 0) {
-              xa.y = (T)0;
-              xb.y = (T)0;
-            }
-          }
+          const cx<T> xa = XA[q], xb = XB[q];
           Pair2<T> ph{(T)0, (T)0};
           if constexpr (PHASE) {
             if (want_phase) {
@@ -609,14 +678,12 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           emit(I0{}, std::integral_constant<int, TF * q>{}, std::bool_constant<q == 0>{}, k, xa, ph.a);
           emit(I1{}, std::integral_constant<int, -TF * q>{}, std::bool_constant<q == 0>{}, M - k, xb, ph.b);
         });
-        // self-paired bin M/2 = conj(Z[M/2]) (thread 0; above every stream-0 bin of that thread)
         if (t == 0) {
-          const cx<T> xh{v[P / 2].x, -v[P / 2].y};
           T ph = (T)0;
           if constexpr (PHASE) {
-            if (want_phase) ph = t_atan2(xh.y, xh.x);
+            if (want_phase) ph = t_atan2(XH.y, XH.x);
           }
-          emit(I0{}, std::integral_constant<int, M / 2>{}, std::false_type{}, M / 2, xh, ph);
+          emit(I0{}, std::integral_constant<int, M / 2>{}, std::false_type{}, M / 2, XH, ph);
         }
       }
       int verdict = 0;  // bit 0: a sum of squares left the safe range; bit 1: every sum of this thread was 0
@@ -626,32 +693,34 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         if (need_mag) verdict = ((hi_max >= 0x7fd00000u || lo_min < 0x003fffffu) ? 1 : 0) | (hi_max == 0u ? 2 : 0);
       }
       // merge the two streams: higher value wins, equal values go to the lower bin
-      best = c0;
-      if (c1.k != 0 && (best.k == 0 || peak_better(c1.v, c1.k, best.v, best.k))) best = c1;
+      best_v = c0v, best_k = c0k;
+      if (c1k != 0 && (best_k == 0 || peak_better(c1v, c1k, best_v, best_k))) best_v = c1v, best_k = c1k;
       return verdict;
     };
 
     {
-      int verdict = post_pass(std::false_type{});
+      int verdict = epilogue(std::false_type{});
       if (!valid) verdict = 0;  // tail slots hold no frame
       if constexpr (sizeof(T) == 8) {
-        // rare: some |X|^2 over/underflowed - redo the epilogue with hypot(), like Math.hypot.  Votes span
-        // the warp (the shuffles inside post_pass need converged lanes).
+        // rare: some |X|^2 over/underflowed - redo the epilogue with hypot(), like Math.hypot (a warp-uniform decision)
         bool redo = simt::any((verdict & 1) != 0);
         if (!redo && simt::any((verdict & 2) != 0)) {
           // some thread saw only zeros: genuine silence, or bins below 2^-521 whose squares underflowed?
-          bool nonzero = false;
-          static_for<0, P>([&](auto q) { nonzero = nonzero || v[decltype(q)::value].x != (T)0 || v[decltype(q)::value].y != (T)0; });
+          bool nonzero = XH.x != (T)0 || XH.y != (T)0;
+          static_for<0, NQ>([&](auto q) {
+            nonzero = nonzero || XA[decltype(q)::value].x != (T)0 || XA[decltype(q)::value].y != (T)0 ||
+                      XB[decltype(q)::value].x != (T)0 || XB[decltype(q)::value].y != (T)0;
+          });
           redo = simt::any(nonzero);
         }
-        if (redo) post_pass(std::true_type{});
+        if (redo) epilogue(std::true_type{});
       }
     }
 
     // ---- findPeak: (value desc, index asc) reduction over the frame's threads
     if (want_peak) {
-      T bv = best.v;
-      int bk = best.k;
+      T bv = best_v;
+      int bk = best_k;
       constexpr int W = TF < 32 ? TF : 32;
       PDSP_UNROLL
       for (int m = W / 2; m >= 1; m >>= 1) {
@@ -688,13 +757,22 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       // bin > 0 -> bin 0.  frequency / phase (and the amplitude in peak-only mode) are filled in by the
       // CTA-wide finishing loop below, where every lane has a record - an atan2 issued here would occupy
       // the whole warp for one lane.
-      const bool owner = bk != 0 ? (best.k == bk) : (t == 0);
+      const bool owner = bk != 0 ? (best_k == bk) : (t == 0);
       if (valid && owner) {
+        // which register holds bin bk: stream 0 (k = t + TF*q < M/2), stream 1 (k = M - t - TF*q > M/2), or XH (k = M/2)
+        cx<T> Xw;
+        if (M > 1 && 2 * bk == M)
+          Xw = XH;
+        else if (2 * bk < M || M == 1)
+          Xw = pick_reg(XA, M == 1 ? 0 : (bk - t) / TF);
+        else
+          Xw = pick_reg(XB, (M - bk - t) / TF);
+        if (M == 1 && bk == 1) Xw = XB[0];
         PeakRec<T> rec;
         rec.index = bk;
-        rec.frequency = bk != 0 ? best.re : dc_re;
-        rec.phase = bk != 0 ? best.im : (T)0;
-        rec.amplitude = bk != 0 ? best.v : dc_amp;  // a squared key in peak-only mode; recomputed below
+        rec.frequency = Xw.x;  // bk == 0: XA[0] of thread 0 = (X[0], +0)
+        rec.phase = Xw.y;
+        rec.amplitude = bk != 0 ? bv : dc_amp;  // a squared key in peak-only mode; recomputed below
         if constexpr (sizeof(T) == 8) rec.pad = 0;
         static_cast<PeakRec<T>*>(p.peaks)[f] = rec;
       }
@@ -710,7 +788,9 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     for (long long f = f_first + tid; f < f_last; f += THREADS) {
       PeakRec<T> rec = recs[f];
       const T re = rec.frequency, im = rec.phase;
-      if (KEYSQ) rec.amplitude = t_mag_checked(re, im) * ((rec.index == 0 || rec.index == M) ? s_edge : s_mid);
+      if (KEYSQ)
+        rec.amplitude = t_mag_checked(re, im) * (FOLD ? ((rec.index == 0 || rec.index == M) ? edge_ratio : (T)1)
+                                                      : ((rec.index == 0 || rec.index == M) ? s_edge : s_mid));
       rec.frequency = (T)((double)rec.index * p.bin_hz);
       rec.phase = t_atan2(im, re);
       recs[f] = rec;

@@ -49,7 +49,8 @@ cudaError_t launch_r2c_t(const R2CParams& p, const LaunchCtx& lc) {
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS;
   constexpr int SLOTS = THREADS / E::TF;
-  constexpr size_t SMEM = E::NEEDS_SMEM ? sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS : 0;
+  constexpr size_t SMEM = r2c_smem_bytes<T, E, MODE, SLOTS>();
+  static_assert((MODE & MD_STAGED) == 0 || E::TF <= 32, "staged loads: frames no wider than a warp");
   auto kern = [] {
     if constexpr (C::MAXREG > 0)
       return r2c_kernel_mr<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MAXREG, MODE>;
@@ -95,6 +96,18 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
   X(MD_AMP | MD_TWO) X(MD_AMP | MD_PHASE | MD_PEAK | MD_TWO)                                                               \
   X(MD_AMP | MD_PAD) X(MD_AMP | MD_PEAK | MD_PAD) X(MD_AMP | MD_PHASE | MD_PEAK | MD_PAD)
 
+// ... and those that also exist with bulk-staged sample loads (MD_STAGED), for the sizes staged_supported() names
+#define PDSP_STAGED_MODES(X) \
+  X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)
+
+// staged kernels are built for frames that fit a warp, from N = 512 up (smaller frames gain nothing: several frames
+// share one warp's load instructions already)
+template <typename T, int LOG2M>
+constexpr bool staged_supported() {
+  using C = KCfg<T, LOG2M>;
+  return LOG2M >= 8 && C::TF <= 32;
+}
+
 inline bool mode_is_specialised(int mode) {
   switch (mode) {
 #define X(m) \
@@ -114,7 +127,18 @@ template <typename T, int L, int LO, int HI>
 cudaError_t r2c_case(int mode, const R2CParams& p, const LaunchCtx& lc) {
   if constexpr (L >= LO && L <= HI) {
     if constexpr (L >= kMinSpecLog2M) {
-      switch (mode) {
+      if constexpr (staged_supported<T, L>()) {
+        switch (mode) {
+#define X(m)              \
+  case ((m) | MD_STAGED): \
+    return launch_r2c_t<T, L, ((m) | MD_STAGED)>(p, lc);
+          PDSP_STAGED_MODES(X)
+#undef X
+          default:
+            break;
+        }
+      }
+      switch (mode & ~MD_STAGED) {  // no staged form of this mode / size: the direct-load kernel
 #define X(m) \
   case (m):  \
     return launch_r2c_t<T, L, (m)>(p, lc);

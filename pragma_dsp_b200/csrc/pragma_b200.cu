@@ -46,11 +46,12 @@ cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const L
 cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, const simt::TensorMap2D& tm_re,
                                 const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
 
-// tuning variants (inst_var.cu), one symbol per (type, variant); not built into the emulated test library
-#ifdef PDSP_EMU
-#define PDSP_VARS(X)
-#else
+// tuning variants (inst_var.cu), one symbol per (type, variant): only in -DPDSP_TUNING builds
+// (python -m pragma_dsp_b200.build --tuning); the shipped library carries the default mapping alone
+#if defined(PDSP_TUNING) && !defined(PDSP_EMU)
 #define PDSP_VARS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17)
+#else
+#define PDSP_VARS(X)
 #endif
 #define X(v)                                                                           \
   cudaError_t launch_r2c_var_f64_##v(int, const R2CParams&, const LaunchCtx&);         \
@@ -58,16 +59,65 @@ cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, con
 PDSP_VARS(X)
 #undef X
 
-static int env_variant() {
-  // read on every launch (a getenv is nanoseconds) so one process can sweep the variants
-  const char* e = getenv("PDSP_VARIANT");
-  const int v = e ? atoi(e) : 0;
-  return (v < 0 || v >= kNumVariants) ? 0 : v;
+// Tunables of a context.  Read from the environment ONCE, in pdsp_ctx_create (PDSP_* variables), and changed
+// afterwards only through pdsp_ctx_tune: nothing on the launch path calls getenv.
+struct Tune {
+  int variant = 0;          // PDSP_VARIANT: kernel mapping of N = 1024 (PDSP_TUNING builds only)
+  int big_tma = -1;         // PDSP_BIG_TMA: -1 auto, 0 per-thread tile loads, 1 TMA tile loads (multi-pass path)
+  int big_interleave = 1;   // PDSP_BIG_INTERLEAVE: interleaved (re, im) work buffer between passes
+  int big_prefetch = 1;     // PDSP_BIG_PREFETCH: L2 prefetch of a CTA's next tile
+  long long big_chunk = 0;  // PDSP_BIG_CHUNK: transforms per group of passes (0 = default)
+  int big_factors[3] = {0, 0, 0};  // PDSP_BIG_FACTORS "a,b[,c]": log2 of forced pass lengths (test hook)
+  int n_big_factors = 0;
+  long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
+  int staged = -1;            // PDSP_STAGED: -1 auto, 0 / 1 force the direct / bulk-staged sample loads
+  int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
+};
+static int tune_set(Tune& t, const char* key, const char* val) {
+  if (!key) return 1;
+  const char* v = val ? val : "";
+  const bool unset = v[0] == 0;
+  if (!strcmp(key, "variant")) {
+    const int x = atoi(v);
+    t.variant = (x < 0 || x >= kNumVariants) ? 0 : x;
+  } else if (!strcmp(key, "big_tma")) {
+    t.big_tma = unset ? -1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_interleave")) {
+    t.big_interleave = unset ? 1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_prefetch")) {
+    t.big_prefetch = unset ? 1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_chunk")) {
+    t.big_chunk = atoll(v) > 0 ? atoll(v) : 0;
+  } else if (!strcmp(key, "big_factors")) {
+    int a = 0, b = 0, c3 = 0;
+    const int got = sscanf(v, "%d,%d,%d", &a, &b, &c3);
+    t.n_big_factors = got >= 2 ? got : 0;
+    t.big_factors[0] = a, t.big_factors[1] = b, t.big_factors[2] = got == 3 ? c3 : 0;
+  } else if (!strcmp(key, "chunk_bytes")) {
+    t.chunk_bytes = atoll(v) > 0 ? atoll(v) : 0;
+  } else if (!strcmp(key, "staged")) {
+    t.staged = unset ? -1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_resident")) {
+    t.big_resident = unset ? -1 : (v[0] != '0');
+  } else {
+    return 1;
+  }
+  return 0;
+}
+static void tune_from_env(Tune& t) {
+  static const char* const keys[][2] = {{"variant", "PDSP_VARIANT"},           {"big_tma", "PDSP_BIG_TMA"},
+                                        {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
+                                        {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
+                                        {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}};
+  for (auto& k : keys)
+    if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
 
-static cudaError_t dispatch_r2c(bool f64, int log2m, int mode, const R2CParams& p, const LaunchCtx& lc) {
+static cudaError_t dispatch_r2c(bool f64, int log2m, int mode, int variant, const R2CParams& p, const LaunchCtx& lc) {
+  (void)variant;
   if (log2m == kVariantLog2M && (mode == MD_AMP || mode == (MD_AMP | MD_PEAK) || mode == MD_PEAK)) {
-    switch (env_variant()) {
+    switch (variant) {
 #define X(v) \
   case v:    \
     return f64 ? launch_r2c_var_f64_##v(mode, p, lc) : launch_r2c_var_f32_##v(mode, p, lc);
@@ -304,6 +354,7 @@ struct pdsp_ctx {
   std::map<std::pair<int, int>, pdsp_plan*> plans;
   std::map<std::tuple<int, int, int>, void*> pass_tw;  // (f64, log2m, rb) -> per-pass twiddle table
   std::atomic<long long> launches{0};
+  Tune tune;  // read from the environment at creation, changed by pdsp_ctx_tune
 };
 
 // multi-pass plan of a transform too long for one CTA: N = 2^lg[0] * 2^lg[1] (* 2^lg[2])
@@ -336,7 +387,6 @@ struct pdsp_plan {
   int precision;
   void* d_post = nullptr;  // cx<T>[n/4 + 1]
   void* d_win[4] = {nullptr, nullptr, nullptr, nullptr};
-  void* d_winphase = nullptr;  // cx<double>[n]: (cos, sin)(2*pi*i/(n-1)), fp64 plans (window by rotation)
   BigPlan* big = nullptr;      // built lazily for n > 8192
 };
 
@@ -519,26 +569,6 @@ static int plan_window(pdsp_plan* pl, int window, const void** d_win) {
   return 0;
 }
 
-// window by rotation (fp64 specialised kernels): phase table + the window's cosine-series coefficients
-static int plan_winphase(pdsp_plan* pl, int window, const void** d_tab, double coef[3]) {
-  static const double kCoef[4][3] = {{1, 0, 0}, {0.5, 0.5, 0}, {0.54, 0.46, 0}, {0.42, 0.5, 0.08}};
-  for (int i = 0; i < 3; ++i) coef[i] = kCoef[window][i];
-  std::lock_guard<std::recursive_mutex> lk(pl->ctx->plan_mu);
-  if (!pl->d_winphase) {
-    const int n = pl->n;
-    std::vector<cx<double>> tab((size_t)n);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int i = 0; i < n; ++i) {
-      const long double th = two_pi * (long double)i / (long double)(n - 1);
-      tab[(size_t)i] = cx<double>{(double)cosl(th), (double)sinl(th)};
-    }
-    CU(cudaMalloc(&pl->d_winphase, sizeof(cx<double>) * tab.size()));
-    CU(cudaMemcpy(pl->d_winphase, tab.data(), sizeof(cx<double>) * tab.size(), cudaMemcpyHostToDevice));
-  }
-  *d_tab = pl->d_winphase;
-  return 0;
-}
-
 // ------------------------------------------------------------------------------ kernel launches
 static size_t esize(int dtype) { return dtype == PDSP_F64 ? 8 : 4; }
 
@@ -601,13 +631,9 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
   }
   p.bin_hz = d->sample_rate / (double)n;  // binFrequencies: quotient first (fourier.ts:160)
   {
-    const char* pf = getenv("PDSP_L2_PREFETCH");
-    p.l2_prefetch = (pf && pf[0] == '1') ? 1 : 0;
-  }
-  {
-    // beyond one CTA (or forced by the PDSP_BIG_FACTORS test hook): window -> multi-pass transform -> epilogue
+    // beyond one CTA (or forced by the big_factors test hook): window -> multi-pass transform -> epilogue
     bool big = pl->log2n - 1 > kMaxLog2M;
-    if (!big && n > 1 && getenv("PDSP_BIG_FACTORS")) {
+    if (!big && n > 1 && c->tune.n_big_factors) {
       BigPlan* bp = nullptr;
       if (big_plan(pl, &bp)) return 1;
       big = bp != nullptr;
@@ -636,17 +662,13 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     if ((mode & MD_PAD) && (d->frame_len & 1)) mode = -1;  // MD_PAD loads whole sample pairs: even frame lengths only
     const bool regular = p.vec_ok && (d_cre == nullptr || (cfull && !p.two_sided)) &&
                          mode_is_specialised(mode);
-    if (regular && pl->precision == PDSP_F64 && d->window != PDSP_WIN_RECT && n >= 4) {
-      // Opt-in (PDSP_WINROT=1): measured on B200 it trades 56 L1 wavefronts per frame for 96 DP instructions
-      // and loses ~5% (profiles/r1/README.md), so the window table stays the default.
-      const char* on = getenv("PDSP_WINROT");
-      if (on && on[0] == '1') {
-        double coef[3];
-        if (plan_winphase(pl, d->window, &p.winphase, coef)) return 1;
-        p.win_a0 = coef[0], p.win_a1 = coef[1], p.win_a2 = coef[2];
-      }
+    if (regular && c->tune.staged != 0 && !(mode & (MD_PAD | MD_TWO)) && d->frame_len >= n) {
+      // bulk-staged sample loads (MD_STAGED): 16-byte aligned frames, sample type no wider than the plan's;
+      // dispatch falls back to the direct-load kernel for sizes that have no staged form
+      const bool aligned = (reinterpret_cast<uintptr_t>(d_samples) % 16) == 0 && ((size_t)d->hop * es) % 16 == 0 && ((size_t)n * es) % 16 == 0;
+      if (aligned && es <= esize(pl->precision)) mode |= MD_STAGED;
     }
-    e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, regular ? mode : MD_GENERIC, p, lc);
+    e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, regular ? mode : MD_GENERIC, c->tune.variant, p, lc);
   }
   if (e != cudaSuccess) return fail("r2c launch (n=%d): %s", n, cudaGetErrorString(e));
   c->launches++;
@@ -724,11 +746,11 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
   }
   const int n = pl->log2n;
   int lg[3] = {0, 0, 0}, np = 0;
-  if (const char* e = getenv("PDSP_BIG_FACTORS")) {  // test hook: "a,b[,c]" = log2 of the pass lengths
-    int a = 0, b = 0, c3 = 0;
-    const int got = sscanf(e, "%d,%d,%d", &a, &b, &c3);
-    if (got >= 2 && a + b + (got == 3 ? c3 : 0) == n) {
-      lg[0] = a, lg[1] = b, lg[2] = got == 3 ? c3 : 0;
+  const Tune& tn = pl->ctx->tune;
+  if (tn.n_big_factors) {  // test hook: forced pass lengths (log2)
+    const int got = tn.n_big_factors;
+    if (tn.big_factors[0] + tn.big_factors[1] + (got == 3 ? tn.big_factors[2] : 0) == n) {
+      lg[0] = tn.big_factors[0], lg[1] = tn.big_factors[1], lg[2] = got == 3 ? tn.big_factors[2] : 0;
       np = got;
     } else if (n <= kMaxLog2M) {
       return 0;
@@ -759,12 +781,8 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
   return 0;
 }
 
-// Intermediate passes exchange interleaved (re, im) elements unless PDSP_BIG_INTERLEAVE=0: 512-byte instead of
+// Intermediate passes exchange interleaved (re, im) elements unless tune.big_interleave = 0: 512-byte instead of
 // 2 x 256-byte tile rows (2^24: 0.375 -> 0.353 ms, profiles/r1/README.md)
-static bool big_interleave() {
-  const char* e = getenv("PDSP_BIG_INTERLEAVE");
-  return !(e && e[0] == '0');
-}
 
 static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
                       void* d_oim, int inverse, cudaStream_t st) {
@@ -777,16 +795,13 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
   // transforms are processed `chunk` at a time (all passes of a chunk share the work planes)
   long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
-  if (const char* e = getenv("PDSP_BIG_CHUNK")) {  // experiment / test hook: transforms per group of passes
-    const long long v = atoll(e);
-    if (v > 0) chunk = v;
-  }
+  if (c->tune.big_chunk > 0) chunk = c->tune.big_chunk;  // experiment / test hook: transforms per group of passes
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   BigPlan::Work* wk = nullptr;
   {
     std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
-    const bool want_il = big_interleave();
+    const bool want_il = c->tune.big_interleave != 0;
     wk = &bp->work[st];  // std::map nodes are stable: the pointer outlives the lock
     if (wk->frames < chunk || wk->interleaved != want_il) {
       CU(cudaStreamSynchronize(st));
@@ -827,10 +842,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       p.swap_in = (j == 0 && inverse) ? 1 : 0;
       p.swap_out = (last && inverse) ? 1 : 0;
       p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
-      {
-        const char* pf = getenv("PDSP_BIG_PREFETCH");
-        p.l2_prefetch = (pf && pf[0] == '0') ? 0 : 1;  // default on: 2^24 0.43 -> 0.37 ms (profiles/r1/README.md)
-      }
+      p.l2_prefetch = c->tune.big_prefetch;  // default on: 2^24 0.43 -> 0.37 ms (profiles/r1/README.md)
       if (!last) {
         // view [O][L][I]: C adjacent inner indices per CTA, transform along the stride-I axis in place
         p.n_lo = I / C;
@@ -871,8 +883,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       cudaError_t e;
       // TMA tile loads for the strided passes while one chunk's planes fit the L2 (2^20: 0.158 vs 0.169 ms per 8
       // transforms); per-thread loads beyond that (2^24: 0.353 vs 0.373 ms).  PDSP_BIG_TMA=0/1 forces either.
-      const char* tma_env = getenv("PDSP_BIG_TMA");
-      const bool tma = tma_env ? tma_env[0] != '0' : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
+      const bool tma = c->tune.big_tma >= 0 ? c->tune.big_tma != 0 : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
       if (!last && tma) {
         // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
         simt::TensorMap2D tm_re, tm_im;
@@ -902,7 +913,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
 static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
                       int inverse, cudaStream_t st) {
   pdsp_ctx* c = pl->ctx;
-  if (pl->log2n > kMaxLog2M || getenv("PDSP_BIG_FACTORS")) {
+  if (pl->log2n > kMaxLog2M || c->tune.n_big_factors) {
     BigPlan* bp = nullptr;
     if (big_plan(pl, &bp)) return 1;
     if (bp) return launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st);
@@ -1067,13 +1078,10 @@ static int drain(pdsp_ctx* c) {
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static long long pick_chunk(long long batch, size_t bytes_per_frame) {
+static long long pick_chunk(const pdsp_ctx* ctx, long long batch, size_t bytes_per_frame) {
   // ~24 MB of traffic per chunk keeps three chunks in flight without hoarding HBM or pinned memory
   size_t target = 24u << 20;
-  if (const char* e = getenv("PDSP_CHUNK_BYTES")) {  // test hook: small jobs still exercise the multi-chunk pipeline
-    const long long v = atoll(e);
-    if (v > 0) target = (size_t)v;
-  }
+  if (ctx->tune.chunk_bytes > 0) target = (size_t)ctx->tune.chunk_bytes;  // test hook: small jobs still exercise the multi-chunk pipeline
   long long c = (long long)(target / (bytes_per_frame ? bytes_per_frame : 1));
   if (c < 1) c = 1;
   if (c > batch) c = batch;
@@ -1108,6 +1116,7 @@ PDSP_EXPORT int pdsp_ctx_create(int device, pdsp_ctx** out) {
   pdsp_ctx* c = new pdsp_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  tune_from_env(c->tune);
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int i = 0; i < kSlots; ++i) {
     CU(cudaStreamCreateWithFlags(&c->slots[i].stream, cudaStreamNonBlocking));
@@ -1125,7 +1134,6 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
     pdsp_plan* pl = kv.second;
     cudaFree(pl->d_post);
     for (int i = 0; i < 4; ++i) cudaFree(pl->d_win[i]);
-    cudaFree(pl->d_winphase);
     if (pl->big) {
       for (int i = 0; i < 2; ++i) {
         cudaFree(pl->big->tw_hi[i]);
@@ -1162,6 +1170,12 @@ PDSP_EXPORT int pdsp_ctx_sync(pdsp_ctx* c) {
   if (set_device(c)) return 1;
   if (drain(c)) return 1;
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+PDSP_EXPORT int pdsp_ctx_tune(pdsp_ctx* c, const char* key, const char* value) {
+  if (!c || !key) return fail("null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (tune_set(c->tune, key, value)) return fail("unknown tunable '%s'", key);
   return 0;
 }
 PDSP_EXPORT int pdsp_ctx_device(const pdsp_ctx* c) { return c ? c->device : -1; }
@@ -1222,6 +1236,28 @@ PDSP_EXPORT int pdsp_plan_get(pdsp_ctx* c, int32_t size, int precision, pdsp_pla
   c->plans[key] = pl;
   *out = pl;
   return 0;
+}
+// Frees the scratch planes the multi-pass path keeps for (plan, stream).  The map is keyed by the stream handle, so a
+// stream must be released before it is destroyed (a recycled handle would inherit a stale entry).
+static int release_stream_work(pdsp_plan* pl, cudaStream_t st) {
+  if (!pl || !pl->big) return 0;
+  std::lock_guard<std::recursive_mutex> lk(pl->ctx->plan_mu);
+  auto it = pl->big->work.find(st);
+  if (it == pl->big->work.end()) return 0;
+  CU(cudaStreamSynchronize(st));
+  BigPlan::Work& w = it->second;
+  cudaFree(w.re);
+  cudaFree(w.im);
+  cudaFree(w.spec_x);
+  cudaFree(w.spec_re);
+  cudaFree(w.spec_im);
+  pl->big->work.erase(it);
+  return 0;
+}
+PDSP_EXPORT int pdsp_plan_release_stream(pdsp_plan* pl, void* stream) {
+  if (!pl) return fail("null argument");
+  if (set_device(pl->ctx)) return 1;
+  return release_stream_work(pl, stream ? static_cast<cudaStream_t>(stream) : pl->ctx->stream);
 }
 PDSP_EXPORT int32_t pdsp_plan_size(const pdsp_plan* p) { return p ? p->n : 0; }
 PDSP_EXPORT int pdsp_plan_precision(const pdsp_plan* p) { return p ? p->precision : -1; }
@@ -1350,7 +1386,7 @@ PDSP_EXPORT int pdsp_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const 
   const size_t pk = pl->precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
   const size_t out_per_frame = (amplitude ? bins * os : 0) + (phase ? bins * os : 0) + (peaks ? pk : 0);
   const size_t in_per_frame = (size_t)(d->hop > 0 ? (d->hop < d->frame_len ? d->hop : d->frame_len) : 0) * es;
-  const long long chunk = pick_chunk(d->batch, in_per_frame + out_per_frame);
+  const long long chunk = pick_chunk(c, d->batch, in_per_frame + out_per_frame);
   const bool src_pinned = samples ? is_device_visible(samples) : true;
   const bool pin[3] = {amplitude ? is_device_visible(amplitude) : true, phase ? is_device_visible(phase) : true,
                        peaks ? is_device_visible(peaks) : true};
@@ -1401,7 +1437,7 @@ static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, i
   const size_t n = (size_t)pl->n;
   const size_t es = mode == 0 ? esize(in_dtype) : 8;
   const size_t in_per_frame = n * es * (mode == 0 ? 1 : 2);
-  const long long chunk = pick_chunk(batch, in_per_frame + 16 * n);
+  const long long chunk = pick_chunk(c, batch, in_per_frame + 16 * n);
   const bool pin_re = is_device_visible(in_re), pin_im = in_im ? is_device_visible(in_im) : true;
   const bool pin[2] = {is_device_visible(out_re), is_device_visible(out_im)};
   int si = 0, rc = 0;
@@ -1418,12 +1454,16 @@ static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, i
     if (mode != 0) {
       const char* im_src = static_cast<const char*>(in_im) + (size_t)f0 * n * 8;
       char* d_im = static_cast<char*>(s.d_in) + plane_al;
-      if (pin_im) {
-        CU(cudaMemcpyAsync(d_im, im_src, plane, cudaMemcpyHostToDevice, s.stream));
-      } else {
+      const void* dma_src = im_src;
+      if (!pin_im) {
         char* h = static_cast<char*>(s.h_in) + plane_al;
         memcpy(h, im_src, plane);
-        CU(cudaMemcpyAsync(d_im, h, plane, cudaMemcpyHostToDevice, s.stream));
+        dma_src = h;
+      }
+      const cudaError_t ce = cudaMemcpyAsync(d_im, dma_src, plane, cudaMemcpyHostToDevice, s.stream);
+      if (ce != cudaSuccess) {  // leave through drain(): slots of earlier chunks still point at caller buffers
+        rc = fail("cudaMemcpyAsync (imaginary plane): %s", cudaGetErrorString(ce));
+        break;
       }
     }
     const size_t oplane = (size_t)nb * n * 8, oplane_al = align256(oplane);
@@ -1681,6 +1721,7 @@ PDSP_EXPORT int pdsp_ingest_close(pdsp_ingest* g) {
   if (g->plan && set_device(g->plan->ctx)) return 1;
   for (auto& ch : g->chunks) {
     if (ch.stream) cudaStreamSynchronize(ch.stream);
+    if (ch.stream && g->plan) release_stream_work(g->plan, ch.stream);  // large-N scratch planes keyed by this stream
     cudaFreeHost(ch.h_in);
     cudaFree(ch.d_in);
     cudaFree(ch.d_out);

@@ -61,6 +61,13 @@ PDSP_DEVICE void tma_load_2d(void* smem_dst, const TensorMap2D* map, int x, int 
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// 1-D bulk copy global -> shared (cp.async.bulk, SASS UBLKCP): `bytes` and both addresses multiples of 16; completion
+// is counted on the mbarrier like a tensor load's
+PDSP_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // L2 prefetch of the same box (no shared-memory destination, no barrier)
 PDSP_DEVICE void tma_prefetch_2d(const TensorMap2D* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
@@ -172,6 +179,10 @@ inline void tma_load_2d(void* smem_dst, const TensorMap2D* m, int x, int y, unsi
     }
   }
   emu_mbar_complete_tx(bar, (unsigned)(m->box0 * m->box1 * m->esize));
+}
+inline void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  memcpy(smem_dst, gsrc, bytes);
+  emu_mbar_complete_tx(bar, bytes);
 }
 inline void tma_prefetch_2d(const TensorMap2D*, int, int) {}
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu_mbar_wait(bar, parity); }

@@ -31,7 +31,7 @@ def step():
 
 
 for mb in (4, 8, 16, 24, 32, 48, 64, 96, 128):
-    os.environ["PDSP_CHUNK_BYTES"] = str(mb << 20)
+    ctx.tune("chunk_bytes", mb << 20)
     for _ in range(3):
         step()
     t0 = time.perf_counter()

@@ -52,7 +52,7 @@ def main():
         bpf = bench.algorithmic_bytes_per_frame(w)
         ref_amp = ref_pk = None
         for v in [int(s) for s in a.variants.split(",")]:
-            os.environ["PDSP_VARIANT"] = str(v)
+            ctx.tune("variant", v)
 
             def go():
                 check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()),
@@ -85,7 +85,7 @@ def main():
                    "frac_of_measured_hbm": fps * bpf / 1e9 / peak, "agree_with_v0": agree}
             rows.append(row)
             print(json.dumps(row), flush=True)
-    os.environ.pop("PDSP_VARIANT", None)
+    ctx.tune("variant", None)
 
 
 if __name__ == "__main__":

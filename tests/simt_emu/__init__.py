@@ -23,9 +23,7 @@ class R2CParams(C.Structure):
                 ("post", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p), ("cfull", C.c_int),
                 ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int), ("shift", C.c_int),
                 ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double),
-                ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong),
-                ("winphase", C.c_void_p), ("win_a0", C.c_double), ("win_a1", C.c_double), ("win_a2", C.c_double),
-                ("l2_prefetch", C.c_int)]
+                ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong)]
 
 
 class C2CParams(C.Structure):
@@ -167,7 +165,7 @@ def _p(a):
 
 def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, window=None, sides="one",
         sample_rate=1.0, raw=False, want=("complex", "amp", "phase", "peak"), cfull=True, nblocks=1,
-        specialised=False, variant=0, winrot=None):
+        specialised=False, variant=0, staged=False):
     """Run r2c_kernel under the emulator. samples: 1-D float32/float64 array."""
     samples = np.ascontiguousarray(samples)
     assert samples.dtype in (np.float32, np.float64)
@@ -206,17 +204,14 @@ def r2c(samples, n, *, dtype=np.float64, frame_len=None, hop=None, batch=None, w
     else:
         p.scale_edge, p.scale_mid = 1.0 / n, 2.0 / n
     p.bin_hz = sample_rate / n
-    if winrot is not None:  # window by rotation: (a0, a1, a2) of a0 - a1 cos(th) + a2 cos(2 th)
-        i = np.arange(n, dtype=np.longdouble)
-        th = 2 * np.longdouble(np.pi) * i / np.longdouble(n - 1)
-        wph = np.ascontiguousarray(np.stack([np.cos(th), np.sin(th)], axis=1).astype(dtype))
-        p.winphase = _p(wph)
-        p.win_a0, p.win_a1, p.win_a2 = winrot
     mode = 0
     if specialised:  # compile-time specialised kernel (MD_* bits); preconditions are the caller's job
         assert p.vec_ok and cfull
         mode = (1 if "amp" in want else 0) | (2 if "phase" in want else 0) | (4 if "peak" in want else 0) | \
                (8 if "complex" in want else 0) | (16 if sides == "two" else 0) | (32 if frame_len < n else 0)
+        if staged:  # bulk-staged sample loads: 16-byte aligned whole frames
+            assert samples.ctypes.data % 16 == 0 and (hop * samples.itemsize) % 16 == 0 and frame_len >= n
+            mode |= 64
     if variant:
         assert mode in (1, 5, 4) and n == 1024
         rc = lib().emu_r2c_var(int(dtype == np.float64), variant, C.byref(p), nblocks, mode)

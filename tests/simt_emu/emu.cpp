@@ -18,7 +18,9 @@ static int run_r2c_m(const R2CParams& p, int nblocks) {
   using C = KCfg<T, LOG2M, VAR>;
   using E = FftEngine<T, LOG2M, C::LOG2P, C::MAXRB>;
   constexpr int THREADS = C::THREADS, SLOTS = THREADS / E::TF;
-  constexpr size_t SMEM = sizeof(cx<T>) * E::SMEM_ELEMS * SLOTS;
+  constexpr size_t SMEM = r2c_smem_bytes<T, E, MODE, SLOTS>() + sizeof(cx<T>);
+  if constexpr ((MODE & MD_STAGED) != 0 && E::TF > 32) return -3;
+  else
   simt::emu_launch(nblocks, THREADS, SMEM, [&] { r2c_kernel<T, LOG2M, C::LOG2P, C::MAXRB, THREADS, C::MINB, MODE>(p); });
   return 0;
 }
@@ -37,6 +39,12 @@ static int run_r2c(const R2CParams& p, int nblocks, int mode) {
       case MD_AMP | MD_PEAK | MD_PAD: return run_r2c_m<T, LOG2M, MD_AMP | MD_PEAK | MD_PAD>(p, nblocks);
       case MD_AMP | MD_PHASE | MD_PEAK | MD_PAD: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK | MD_PAD>(p, nblocks);
       case MD_AMP | MD_PHASE | MD_PEAK | MD_TWO: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK | MD_TWO>(p, nblocks);
+      // bulk-staged sample loads (frames that fit a warp)
+      case MD_AMP | MD_STAGED: return run_r2c_m<T, LOG2M, MD_AMP | MD_STAGED>(p, nblocks);
+      case MD_AMP | MD_PEAK | MD_STAGED: return run_r2c_m<T, LOG2M, MD_AMP | MD_PEAK | MD_STAGED>(p, nblocks);
+      case MD_PEAK | MD_STAGED: return run_r2c_m<T, LOG2M, MD_PEAK | MD_STAGED>(p, nblocks);
+      case MD_CPLX | MD_STAGED: return run_r2c_m<T, LOG2M, MD_CPLX | MD_STAGED>(p, nblocks);
+      case MD_AMP | MD_PHASE | MD_PEAK | MD_STAGED: return run_r2c_m<T, LOG2M, MD_AMP | MD_PHASE | MD_PEAK | MD_STAGED>(p, nblocks);
       default: break;
     }
   }

@@ -300,20 +300,24 @@ def test_fused_peer_scatter_single_gpu(ctx):
 
 @pytest.mark.parametrize("tma,interleave,prefetch", [("1", "1", "1"), ("0", "1", "1"), ("1", "0", "1"), ("0", "0", "0"),
                                                      ("1", "1", "0")])
-def test_large_fft_tma_and_plain_paths_agree(ctx, monkeypatch, tma, interleave, prefetch):
+def test_large_fft_tma_and_plain_paths_agree(ctx, tma, interleave, prefetch):
     """K2's strided passes have two implementations: TMA tile loads (cp.async.bulk.tensor + mbarrier) and
-    per-thread coalesced loads (PDSP_BIG_TMA=0), an interleaved or planar work buffer between the passes
-    (PDSP_BIG_INTERLEAVE) and an optional L2 prefetch of the next tile.  All must give the same transform."""
+    per-thread coalesced loads (tunable big_tma=0), an interleaved or planar work buffer between the passes
+    (big_interleave) and an optional L2 prefetch of the next tile.  All must give the same transform."""
     from pragma_dsp_b200.core import ComplexArray, Radix2Fft
-    monkeypatch.setenv("PDSP_BIG_TMA", tma)
-    monkeypatch.setenv("PDSP_BIG_INTERLEAVE", interleave)
-    monkeypatch.setenv("PDSP_BIG_PREFETCH", prefetch)
-    for log2n in (14, 18, 22):
-        n = 1 << log2n
-        rng = np.random.default_rng(log2n)
-        re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
-        out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
-        assert rel_l2(out.real + 1j * out.imag, np.fft.fft(re + 1j * im)) <= 1e-12 * log2n
+    ctx.tune("big_tma", tma)
+    ctx.tune("big_interleave", interleave)
+    ctx.tune("big_prefetch", prefetch)
+    try:
+        for log2n in (14, 18, 22):
+            n = 1 << log2n
+            rng = np.random.default_rng(log2n)
+            re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+            out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
+            assert rel_l2(out.real + 1j * out.imag, np.fft.fft(re + 1j * im)) <= 1e-12 * log2n
+    finally:
+        for k in ("big_tma", "big_interleave", "big_prefetch"):
+            ctx.tune(k, None)
 
 
 def test_fast_atan2_accuracy_and_special_values(ctx):

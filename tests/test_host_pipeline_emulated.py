@@ -28,6 +28,20 @@ def emu_api():
         _lib.LIB_PATH, _lib._lib, _lib._default_ctx = saved
 
 
+@pytest.fixture
+def tune(emu_api):
+    """Sets tunables of the default context (pdsp_ctx_tune) and restores the defaults afterwards."""
+    used = []
+
+    def _set(key, value):
+        emu_api.default_context().tune(key, value)
+        used.append(key)
+
+    yield _set
+    for key in used:
+        emu_api.default_context().tune(key, None)
+
+
 def multitone(rng, batch, n, dtype=np.float64):
     t = np.arange(n)
     k = rng.integers(8, n // 2 - 8, size=(batch, 3)) + rng.uniform(-0.25, 0.25, size=(batch, 3))
@@ -56,14 +70,14 @@ def test_spectrum_host_entry_windowed(emu_api):
     assert one["peak"]["index"] == ref1["peak"]["index"] and len(one["amplitude"]) == 513
 
 
-def test_chunked_pipeline_many_chunks(emu_api, monkeypatch):
+def test_chunked_pipeline_many_chunks(emu_api, tune):
     """A job cut into many chunks over the 3 staging slots returns every frame, in order, for pageable
     and pinned buffers; fp32 plan; amplitude + peak outputs."""
     from pragma_dsp_b200 import spectrum_batch
     L = emu_api.lib()
     rng = np.random.default_rng(2)
-    # pick_chunk targets ~24 MB per chunk; the PDSP_CHUNK_BYTES hook shrinks it so a small job is cut into ~10 chunks
-    monkeypatch.setenv("PDSP_CHUNK_BYTES", str(256 << 10))
+    # pick_chunk targets ~24 MB per chunk; the chunk_bytes tunable shrinks it so a small job is cut into ~10 chunks
+    tune("chunk_bytes", 256 << 10)
     n, batch = 1024, 300  # 4 KB + 4 KB per frame -> 31 frames per chunk
     x = multitone(rng, batch, n, np.float32)
     got = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann", precision="f64", outputs=("amplitude", "peak"))
@@ -160,21 +174,19 @@ def test_launch_and_plan_accounting(emu_api):
 @pytest.mark.parametrize("factors,n,env", [("6,6", 4096, {}), ("7,6", 8192, {}), ("6,6,6", 1 << 18, {}),
                                            ("7,7", 1 << 14, {}),
                                            # switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
-                                           ("7,6", 8192, {"PDSP_BIG_TMA": "0"}),
-                                           ("7,6", 8192, {"PDSP_BIG_TMA": "1"}),
-                                           ("6,6", 4096, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "1"}),
-                                           ("7,6", 8192, {"PDSP_BIG_INTERLEAVE": "0", "PDSP_BIG_TMA": "0",
-                                                          "PDSP_BIG_PREFETCH": "0"})])
-def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n, env):
-    """K2: the multi-pass (four-step / six-step) path, forced onto small sizes with PDSP_BIG_FACTORS so the
+                                           ("7,6", 8192, {"big_tma": "0"}),
+                                           ("7,6", 8192, {"big_tma": "1"}),
+                                           ("6,6", 4096, {"big_interleave": "0", "big_tma": "1"}),
+                                           ("7,6", 8192, {"big_interleave": "0", "big_tma": "0",
+                                                          "big_prefetch": "0"})])
+def test_multipass_large_fft_emulated(emu_api, tune, factors, n, env):
+    """K2: the multi-pass (four-step / six-step) path, forced onto small sizes with the big_factors tunable so the
     emulator can run it: forward, inverse, real-input forward, batch of 2."""
     from pragma_dsp_b200.core import Radix2Fft
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    if n > 8192:
-        monkeypatch.delenv("PDSP_BIG_FACTORS", raising=False) if factors == "7,7" else monkeypatch.setenv("PDSP_BIG_FACTORS", factors)
-    else:
-        monkeypatch.setenv("PDSP_BIG_FACTORS", factors)
+        tune(k, v)
+    if not (n > 8192 and factors == "7,7"):  # 2^14 = 128 x 128 is the default split
+        tune("big_factors", factors)
     rng = np.random.default_rng(n)
     batch = 2 if n <= 8192 else 1
     re, im = rng.standard_normal((batch, n)), rng.standard_normal((batch, n))
@@ -198,11 +210,11 @@ def test_multipass_large_fft_emulated(emu_api, monkeypatch, factors, n, env):
 
 
 @pytest.mark.parametrize("sides,frame_len", [("one", 4096), ("two", 4096), ("one", 3000)])
-def test_large_spectrum_path_emulated(emu_api, monkeypatch, sides, frame_len):
+def test_large_spectrum_path_emulated(emu_api, tune, sides, frame_len):
     """spectrum() beyond one CTA (N > 16384 on the device): window -> multi-pass transform -> epilogue kernel with
-    findPeak.  Forced onto N=4096 with PDSP_BIG_FACTORS so the emulator can run it; compared with the oracle."""
+    findPeak.  Forced onto N=4096 with the big_factors tunable so the emulator can run it; compared with the oracle."""
     from pragma_dsp_b200 import spectrum_batch
-    monkeypatch.setenv("PDSP_BIG_FACTORS", "6,6")
+    tune("big_factors", "6,6")
     rng = np.random.default_rng(11)
     n, batch = 4096, 3
     x = multitone(rng, batch, frame_len)
@@ -229,7 +241,7 @@ def test_large_spectrum_path_emulated(emu_api, monkeypatch, sides, frame_len):
     assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= 2e-6
 
 
-def test_fused_fftshift_two_sided_emulated(emu_api, monkeypatch):
+def test_fused_fftshift_two_sided_emulated(emu_api, tune):
     """fftShift fused into the two-sided stores (desc.fft_shift) equals fftShift() applied afterwards,
     in the fused single-CTA kernel and in the large-N epilogue; one-sided + shift is rejected."""
     from pragma_dsp_b200 import spectrum_batch
@@ -245,7 +257,7 @@ def test_fused_fftshift_two_sided_emulated(emu_api, monkeypatch):
         assert (fused["peaks"] == plain["peaks"]).all()
     with pytest.raises(Exception, match="two-sided"):
         spectrum_batch(multitone(rng, 1, 64), fftSize=64, sides="one", shift=True)
-    monkeypatch.setenv("PDSP_BIG_FACTORS", "6,6")
+    tune("big_factors", "6,6")
     x = multitone(rng, 2, 4096)
     plain = spectrum_batch(x, sampleRate=8000.0, fftSize=4096, sides="two")
     fused = spectrum_batch(x, sampleRate=8000.0, fftSize=4096, sides="two", shift=True)
