@@ -3,19 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-Metric (BASELINE.json): batched N=1024 FFT frames/s (+ achieved HBM GB/s).  A "step" is one pass
-of the fused kernel (frame build + window + FFT + amplitude + peak) over one batch of synthetic
-multi-tone frames.  Default workload = BASELINE configs[1] ("c2"): 65,536 frames x N=1024 fp32,
-Hann, one-sided amplitude + peak @ 48 kHz per GPU (weak scaling: every rank owns a batch of that
-size; with N>1 every rank also receives all ranks' per-frame peaks - by default through NVLink peer
-stores fused into the kernel's epilogue (--gather p2p), alternatively a side-stream NCCL all_gather).  Other workloads: "north_star" (fp64 Hann FFT + one-sided magnitude),
-"c5" (fp64 window + FFT + peak only).
+Metric (BASELINE.json): batched N=1024 FFT frames/s (+ achieved HBM GB/s).  A "step" is one launch of the fused
+kernel (frame build + window + FFT + magnitude / amplitude / peak) over one batch of synthetic multi-tone frames.
+Default workload = BASELINE.json's stated target ("north_star"): fp64 Hann-windowed FFT + one-sided magnitude,
+N=1024, 2^20 frames per GPU and step - 16 x the 65,536-frame batch of configs[1], so that the K timed steps
+cover >= 50 ms at the clocks the part sustains under its power cap (a 65,536-frame launch lasts 0.17 ms; its
+back-to-back "burst" rate is reported as a secondary key).  Weak scaling: every rank owns a batch of that size;
+with N>1 and a peak output every rank also receives all ranks' per-frame peaks - by default through NVLink peer
+stores fused into the kernel's epilogue (--gather p2p), alternatively a side-stream NCCL all_gather.
+Other workloads: "c2" (configs[1]: spectrum() fp32 amplitude + peak), "c5" (configs[4]: 2^20 frames, fp64
+window + FFT + peak only, frame-sharded; --scaling strong splits the 2^20 frames over the ranks), "c3", "c4_*",
+"run_ts_*", "c1" (single-call latency of Radix2Fft.forward / spectrum()).
 
 One JSON line on stdout (rank 0).  `value` = whole-job frames/s with inputs resident in HBM;
-`e2e` = the same metric through the public host API (pragma_dsp_b200.spectrum_batch ->
-pdsp_spectrum) from pinned host buffers, H2D and D2H inside the timed region.
-`--impl reference` times the CPU oracle port of the reference algorithm (the reference is
-TypeScript and cannot run here) on all host threads over a bounded sample of the same workload.
+`e2e` = the same metric through the public host API (pdsp_spectrum) from pinned host buffers, H2D and D2H inside
+the timed region.  `--impl reference` times the CPU oracle port of the reference algorithm (the reference is
+TypeScript and cannot run here) on all host threads over a bounded sample of the same workload, computing the
+same outputs as the GPU arm.
 """
 from __future__ import annotations
 
@@ -46,14 +50,19 @@ def emit_line(obj):
 
 WORKLOADS = {
     # name: (precision, sample dtype, window, outputs, frames/GPU, N, description)
-    "c2": dict(prec="f32", sdtype="f32", window="hann", outputs=("amplitude", "peak"), frames=65536, n=1024,
-               desc="spectrum() batched: 65536 frames x N=1024 fp32, Hann, one-sided amplitude + peak @48kHz"),
-    "north_star": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude",), frames=65536, n=1024,
-                       desc="fp64 Hann-windowed FFT + one-sided magnitude, 65536 frames x N=1024"),
+    "north_star": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude",), frames=1 << 20, n=1024,
+                       desc="BASELINE target: fp64 Hann-windowed FFT + one-sided magnitude, N=1024, 2^20 frames per step "
+                            "(16 x the 65,536-frame batch of configs[1]: 20 steps = a sustained >= 50 ms region)"),
+    "c2": dict(prec="f32", sdtype="f32", window="hann", outputs=("amplitude", "peak"), frames=1 << 21, n=1024,
+               desc="configs[1] spectrum() batched, N=1024 fp32, Hann, one-sided amplitude + peak @48kHz; 2^21 frames per step "
+                    "(32 x 65,536)"),
     # BASELINE config C3: STFT via spectrumStream - 10 min @ 48 kHz, N=4096, hop 1024, Hann, magnitude + phase,
     # Float32Array frames (spectrumStream's element type) computed in fp64 like the reference
     "c3": dict(prec="f64", sdtype="f32", window="hann", outputs=("amplitude", "phase"), frames=28122, n=4096, hop=1024,
                desc="STFT: 28,800,000 fp32 samples (10 min @48kHz), N=4096 hop 1024 Hann, fp64 amplitude + phase, 28122 frames"),
+    # spectrum()'s own output set (amplitude + phase + peak, src/public/spectrum.ts:121-134), batched
+    "spectrum_f64": dict(prec="f64", sdtype="f64", window="hann", outputs=("amplitude", "phase", "peak"), frames=1 << 19, n=1024,
+                         desc="spectrum() default outputs (amplitude + phase + peak), fp64 N=1024 Hann, 2^19 frames per step"),
     # bench/run.ts's own workloads: FFT.forward(input, out) on real fp64 frames, all N bins out
     "run_ts_2048": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=32768, n=2048, kind="r2c_forward",
                         desc="bench/run.ts shape: FFT.forward(input, out), N=2048 real fp64 -> N complex bins, 32768 frames"),
@@ -64,9 +73,13 @@ WORKLOADS = {
                     desc="complex fp64 FFT, N=2^20, 8 transforms per step (multi-pass 1024x1024)"),
     "c4_2e24": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=1, n=1 << 24, kind="c2c",
                     desc="complex fp64 FFT, N=2^24 (multi-pass 256x256x256)"),
-    "c5": dict(prec="f64", sdtype="f64", window="hann", outputs=("peak",), frames=131072, n=1024,
-               desc="fp64 window + FFT + peak argmax only, frame-sharded"),
+    # BASELINE config C5 as written: 2^20 frames x N=1024, window + FFT + peak argmax, peaks gathered on every rank
+    "c5": dict(prec="f64", sdtype="f64", window="hann", outputs=("peak",), frames=1 << 20, n=1024,
+               desc="configs[4]: 2^20 frames x N=1024 fp64 window + FFT + peak argmax only, frame-sharded, peaks gathered"),
+    "c1": dict(prec="f64", sdtype="f64", window="rect", outputs=("complex",), frames=1, n=1024, kind="latency",
+               desc="configs[0]: Radix2Fft.forward N=1024 fp64 on one frame of sin(i) (README core example) - us per call"),
 }
+BURST_FRAMES = 65536  # the batch of BASELINE configs[1]: secondary "burst" timing of the same kernel
 
 
 def algorithmic_bytes_per_frame(w) -> int:
@@ -108,6 +121,23 @@ def run_reference(args, w):
 
     threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1; the oracle takes an explicit count
     n = w["n"]
+    if w.get("kind") == "latency":
+        po = oracle.FFT(n)
+        x = np.sin(np.arange(n, dtype=np.float64))
+        calls = max(200, args.steps * 50)
+        for _ in range(20):
+            po.forward(x)
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            po.forward(x)
+        us = (time.perf_counter() - t0) / calls * 1e6
+        emit_line({"impl": "reference", "metric": "us_per_call", "value": us, "unit": "us", "n_gpus": args.gpus, "steps": calls,
+                   "warmup": 20, "ms_per_step": us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                   "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
+                   "cpu_baseline": {"value": us, "unit": "us", "cores": 1, "kind": "port",
+                                    "sample": "Radix2Fft.forward on one frame of sin(i) through oracle/pragma_oracle.c, one core"},
+                   "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return 0
     if w.get("kind") in ("c2c", "r2c_forward"):
         rng = np.random.default_rng(SEED)
         nf = 1 if w["kind"] == "c2c" else min(w["frames"], 2048 * threads)
@@ -133,10 +163,19 @@ def run_reference(args, w):
     # bounded sample: about 0.5 s of all-core work per step
     sample = int(min(w["frames"], max(2048, 12000 * threads)))
     x = synth_frames_numpy(sample, n, np.float64 if w["sdtype"] == "f64" else np.float32)
+    outs = tuple(w["outputs"])
+    hop = w.get("hop", n)
+    if hop != n:  # STFT: overlapping views of one stream
+        x = np.ascontiguousarray(x.reshape(-1)[:(sample - 1) * hop + n])
+        kw = dict(frameLen=n, hop=hop, batch=sample)
+    else:
+        kw = {}
 
     def step():
+        # the outputs the GPU arm produces, nothing more: lean=True runs Math.atan2 only where an output needs it
         oracle.spectrum_batch(x, fftSize=n, sampleRate=48000.0, window=w["window"], sides="one",
-                              want_amplitude=True, want_phase=True, threads=threads)  # spectrum() computes all of it
+                              want_amplitude="amplitude" in outs, want_phase="phase" in outs, want_peaks="peak" in outs,
+                              threads=threads, lean=True, **kw)
 
     for _ in range(args.warmup):
         step()
@@ -145,15 +184,18 @@ def run_reference(args, w):
         step()
     dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
+    what = "window, radix-2 FFT, hypot, scaling" + (", atan2 per bin" if "phase" in outs else "") + \
+           (", findPeak + atan2 at the peak bin" if "peak" in outs and "phase" not in outs else "") + \
+           (", findPeak" if "peak" in outs and "phase" in outs else "")
     line = {
         "impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, w),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames/step of the same synthetic workload; oracle/pragma_oracle.c "
-                                   f"(op-for-op C port of src/core/fft.ts + spectrum.ts: window, radix-2 FFT, hypot, atan2, "
-                                   f"scaling, findPeak), gcc -O2 -ffp-contract=off, OpenMP static split"},
+                         "sample": f"{sample} frames/step of the same synthetic workload, same outputs as the GPU arm "
+                                   f"({', '.join(outs)}): oracle/pragma_oracle.c (op-for-op C port of src/core/fft.ts + "
+                                   f"spectrum.ts: {what}), gcc -O2 -ffp-contract=off, OpenMP static split"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_line(line)
@@ -165,7 +207,7 @@ def workload_config(args, w):
             "frames_per_gpu": w["frames"],
             "window": w["window"], "sides": "one", "sample_rate": 48000, "outputs": list(w["outputs"]),
             "sample_dtype": w["sdtype"], "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)",
-            "parallelism": f"frames sharded x{args.gpus}"}
+            "parallelism": f"frames sharded x{args.gpus}", "scaling": getattr(args, "scaling", "weak")}
 
 
 # ----------------------------------------------------------------------------- synthetic data
@@ -280,13 +322,17 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- b200 arm
-def _traffic_of(workload):
-    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu capture (None if not captured)."""
+def _traffic_of(workload, frames):
+    """DRAM bytes per launch of the workload's dominant kernel: the per-frame figure of the committed `ncu --set full`
+    capture (profiles/traffic.json names the capture) scaled to this launch's frame count.  (None, None) if not captured."""
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(tp)).get(workload)
+        e = json.load(open(tp)).get(workload)
+        if isinstance(e, dict):
+            return e["dram_bytes_per_frame"] * frames, e.get("source")
     except Exception:
-        return None
+        pass
+    return None, None
 
 
 def run_b200(args, w):
@@ -308,6 +354,8 @@ def run_b200(args, w):
         dist.init_process_group("nccl", device_id=dev)
     ctx = _lib.Context(local)
     n, frames = w["n"], args.frames or w["frames"]
+    if args.scaling == "strong":  # total work fixed: the workload's frames are split over the ranks
+        frames = -(-frames // world)
     prec = F64 if w["prec"] == "f64" else F32
     tdt = torch.float64 if w["prec"] == "f64" else torch.float32
     sdt = torch.float64 if w["sdtype"] == "f64" else torch.float32
@@ -362,10 +410,9 @@ def run_b200(args, w):
         with torch.cuda.stream(compute):
             if comm is not None and i >= 2:
                 compute.wait_event(gather_done[i & 1])  # the gather that last read this peaks buffer
-            # per-launch duration (roofline.achieved): CUDA events around every 4th launch of the timed region - an
-            # event pair around every launch adds ~4 us of stream bubbles per step to the step time itself
-            probe = timed and (i % 4 == 0)
-            if probe:
+            # per-launch duration (roofline.achieved): CUDA events around every launch of the timed region (a launch
+            # lasts milliseconds at these batch sizes: the event pair's few microseconds do not show)
+            if timed:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(compute)
@@ -374,7 +421,7 @@ def run_b200(args, w):
                                                  rank * frames, C.c_void_p(compute.cuda_stream)))
             else:
                 check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(pb), C.c_void_p(compute.cuda_stream)))
-            if probe:
+            if timed:
                 e1.record(compute)
                 kernel_events.append((e0, e1))
             if comm is not None:
@@ -395,9 +442,38 @@ def run_b200(args, w):
 
     sampler = ClockSampler(local) if rank == 0 else None
 
-    # ---- warm-up, then the timed region: EXACTLY K steps, device time, max over ranks
-    for i in range(max(3, args.warmup)):
+    # ---- secondary "burst" figure: 20 back-to-back launches of the 65,536-frame batch from a cool start (~3 ms at
+    # boost clocks) - what round 1 reported as `value`
+    burst = None
+    if frames > BURST_FRAMES and not args.quick and hop == n:
+        bdesc = SpectrumDesc(sample_dtype=desc.sample_dtype, frame_len=n, hop=hop, batch=BURST_FRAMES, window=desc.window,
+                             sides=desc.sides, sample_rate=48000.0, raw_magnitude=0)
+
+        def burst_launch():
+            check(L.pdsp_spectrum_dev(plan, C.byref(bdesc), vp(x), vp(amp), vp(ph), vp(peaks[0]) if want_peak else None,
+                                      C.c_void_p(compute.cuda_stream)))
+        for _ in range(3):
+            burst_launch()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(compute)
+        for _ in range(20):
+            burst_launch()
+        b1.record(compute)
+        barrier()
+        burst = {"frames_per_launch": BURST_FRAMES, "launches": 20, "ms_per_launch": b0.elapsed_time(b1) / 20}
+
+    # ---- warm-up: at least W steps AND at least 0.2 s, so that the timed region runs at the clocks the part sustains
+    # under its power cap rather than at the first milliseconds' boost; then EXACTLY K timed steps, device time,
+    # max over ranks
+    t0 = time.perf_counter()
+    i = 0
+    while i < max(3, args.warmup) or (not args.quick and time.perf_counter() - t0 < 0.2):
         step(i)
+        i += 1
+        if i % 8 == 0:
+            compute.synchronize()
+    warm_steps = i
     barrier()
     launches0 = ctx.launch_count
     if sampler:
@@ -411,6 +487,8 @@ def run_b200(args, w):
         compute.wait_stream(comm)
     t_end.record(compute)
     barrier()
+    if sampler:
+        sampler.stop()
     launches = ctx.launch_count - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
@@ -421,30 +499,25 @@ def run_b200(args, w):
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt[0])
-
-    # ---- sustained probe: same launches for ~0.6 s so NVML sees the clocks this kernel runs at
-    if sampler and not args.quick:
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 0.6:
-            for i in range(50):
-                check(L.pdsp_spectrum_dev(plan, C.byref(desc), vp(x), vp(amp), vp(ph), vp(peaks[0]) if want_peak else None,
-                                          C.c_void_p(compute.cuda_stream)))
-            compute.synchronize()
-    if sampler:
-        sampler.stop()
     barrier()
 
     gather_check = None
     if peers is not None:
-        # every rank's segment of the local gathered buffer must hold that rank's records
-        host = np.zeros(world * frames * pk_bytes, dtype=np.uint8)
-        check(L.pdsp_memcpy_d2h(ctx.h, C.c_void_p(host.ctypes.data), gbuf, host.nbytes, C.c_void_p(compute.cuda_stream)))
+        # EVERY segment of this rank's gathered buffer must be byte-equal to what the owning rank computed: all-gather
+        # the ranks' local record buffers with NCCL (outside every timed region) and compare the whole buffer
+        mine = peaks[(args.steps - 1) & 1]
+        ref = torch.empty((world * frames, pk_bytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(ref, mine)
+        host = torch.empty((world * frames, pk_bytes), dtype=torch.uint8).pin_memory()
+        check(L.pdsp_memcpy_d2h(ctx.h, C.c_void_p(host.data_ptr()), gbuf, host.numel(), C.c_void_p(compute.cuda_stream)))
         compute.synchronize()
-        rec = host.view(PEAK_F64 if prec == F64 else PEAK_F32)
-        mine = peaks[(args.steps - 1) & 1].cpu().numpy().view(PEAK_F64 if prec == F64 else PEAK_F32).reshape(-1)
-        ok_self = bool((rec[rank * frames:(rank + 1) * frames] == mine).all())
-        ok_all = bool(((rec["index"] >= 8) & (rec["index"] < n // 2)).all())
-        gather_check = {"mode": "p2p", "own_segment_equal": ok_self, "all_segments_filled": ok_all}
+        ref_h = ref.cpu()
+        seg_ok = [bool(torch.equal(host[g_ * frames:(g_ + 1) * frames], ref_h[g_ * frames:(g_ + 1) * frames])) for g_ in range(world)]
+        ok = torch.tensor([int(all(seg_ok))], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_check = {"mode": "p2p", "segments_byte_equal_on_rank0": seg_ok, "all_ranks_all_segments_equal": bool(int(ok[0])),
+                        "checked_against": "NCCL all_gather of every rank's local records"}
+        del ref, ref_h, host
         barrier()
         for g_ in range(world):
             if g_ != rank:
@@ -452,24 +525,30 @@ def run_b200(args, w):
         barrier()
         check(L.pdsp_dev_free(ctx.h, gbuf))
     elif gathered is not None:
-        gather_check = {"mode": "nccl"}
+        mine = peaks[(args.steps - 1) & 1]
+        got = gathered[(args.steps - 1) & 1]
+        gather_check = {"mode": "nccl", "own_segment_equal": bool(torch.equal(got[rank * frames:(rank + 1) * frames], mine))}
 
     # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
+    e2e_frames = min(frames, 131072) if hop == n else frames
     e2e_steps = max(2, min(args.steps, 10)) if not args.quick else 1
-    hx = torch.empty(tuple(x.shape), dtype=sdt).pin_memory()
-    hx.copy_(x.cpu())
+    xs = x[:e2e_frames] if hop == n else x
+    hx = torch.empty(tuple(xs.shape), dtype=sdt).pin_memory()
+    hx.copy_(xs.cpu())
     hx_np = hx.numpy()
     outs = tuple(w["outputs"])
     h2d = hx.numel() * hx.element_size()
-    d2h = frames * ((bins * (8 if prec == F64 else 4) if "amplitude" in outs else 0) +
-                    (bins * (8 if prec == F64 else 4) if "phase" in outs else 0) + (pk_bytes if want_peak else 0))
+    d2h = e2e_frames * ((bins * (8 if prec == F64 else 4) if "amplitude" in outs else 0) +
+                        (bins * (8 if prec == F64 else 4) if "phase" in outs else 0) + (pk_bytes if want_peak else 0))
     # pinned output buffers handed to the C-ABI directly (what createComplexArray-style pinned arrays give JS)
-    h_amp = torch.empty((frames, bins), dtype=tdt).pin_memory() if "amplitude" in outs else None
-    h_ph = torch.empty((frames, bins), dtype=tdt).pin_memory() if "phase" in outs else None
-    h_pk = torch.empty((frames, pk_bytes), dtype=torch.uint8).pin_memory() if want_peak else None
+    h_amp = torch.empty((e2e_frames, bins), dtype=tdt).pin_memory() if "amplitude" in outs else None
+    h_ph = torch.empty((e2e_frames, bins), dtype=tdt).pin_memory() if "phase" in outs else None
+    h_pk = torch.empty((e2e_frames, pk_bytes), dtype=torch.uint8).pin_memory() if want_peak else None
+    edesc = SpectrumDesc(sample_dtype=desc.sample_dtype, frame_len=n, hop=hop, batch=e2e_frames, window=desc.window,
+                         sides=desc.sides, sample_rate=48000.0, raw_magnitude=0)
 
     def e2e_step():
-        check(L.pdsp_spectrum(plan, C.byref(desc), C.c_void_p(hx.data_ptr()),
+        check(L.pdsp_spectrum(plan, C.byref(edesc), C.c_void_p(hx.data_ptr()),
                               C.c_void_p(h_amp.data_ptr()) if h_amp is not None else None,
                               C.c_void_p(h_ph.data_ptr()) if h_ph is not None else None,
                               C.c_void_p(h_pk.data_ptr()) if h_pk is not None else None))
@@ -486,34 +565,35 @@ def run_b200(args, w):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
-    e2e_fps = frames * world * e2e_steps / e2e_s
+    e2e_fps = e2e_frames * world * e2e_steps / e2e_s
 
-    # ---- ingestion ring: the same frames pushed in blocks of 256 from pageable memory, results
-    # popped in order - what a frame-at-a-time source (spectrumStream) sees; one host thread does the copies
+    # ---- ingestion ring: 65,536 of the frames pushed in blocks of 256 from pageable memory, results
+    # popped in order - what a frame-at-a-time source (spectrumStream) sees
     ingest = None
     if rank == 0 and world == 1 and not args.quick and hop == n:
         from pragma_dsp_b200 import IngestRing
-        src = np.array(hx_np, copy=True)  # pageable, like a JS typed array
+        ing_frames = min(e2e_frames, 65536)
+        src = np.array(hx_np[:ing_frames], copy=True)  # pageable, like a JS typed array
         ring = IngestRing(n, sampleRate=48000.0, fftSize=n, window=w["window"], precision=w["prec"],
                           sample_dtype=src.dtype, outputs=outs, framesPerChunk=4096, depth=3, context=ctx)
 
         def ingest_pass():
             pushed = popped = 0
-            while pushed < frames:
+            while pushed < ing_frames:
                 k = ring.push(src[pushed:pushed + 256])
                 pushed += k
                 if k == 0:
                     popped += ring.pop(4096)["count"]
             ring.flush()
-            while popped < frames:
+            while popped < ing_frames:
                 popped += ring.pop(4096)["count"]
         ingest_pass()
         t0 = time.perf_counter()
         ingest_pass()
         ingest_s = time.perf_counter() - t0
         ring.close()
-        ingest = {"value": frames / ingest_s, "unit": "frames/s", "api": "pdsp_ingest_push/pop, 256-frame pushes, pageable source",
-                  "frames_per_chunk": 4096, "depth": 3}
+        ingest = {"value": ing_frames / ingest_s, "unit": "frames/s", "api": "pdsp_ingest_push/pop, 256-frame pushes, pageable source",
+                  "frames_per_chunk": 4096, "depth": 3, "frames": ing_frames}
 
     # ---- parity spot check (outside every timed region): first 256 frames vs the oracle
     parity = None
@@ -529,22 +609,24 @@ def run_b200(args, w):
         parity = {"frames": 256, "peak_index_equal": bool((got["peaks"]["index"] == ref["peaks"]["index"]).all()),
                   "amp_max_abs_err": float(np.abs(got["amplitude"] - ref["amplitude"]).max())}
         if world == 1 and not args.quick:
-            sample = min(frames, 65536 if n <= 1024 else 16384)
+            sample = min(e2e_frames, 65536 if n <= 1024 else 16384)
             if hop == n:
                 sx, skw = hx_np[:sample], {}
             else:
                 sx, skw = hx_np[:(sample - 1) * hop + n], dict(frameLen=n, hop=hop, batch=sample)
+            okw = dict(fftSize=n, sampleRate=48000.0, window=w["window"], want_amplitude="amplitude" in outs,
+                       want_phase="phase" in outs, want_peaks=want_peak, lean=True)
             t0 = time.perf_counter()
-            oracle.spectrum_batch(sx, fftSize=n, sampleRate=48000.0, window=w["window"], threads=1, **skw)
+            oracle.spectrum_batch(sx, threads=1, **okw, **skw)
             one = sample / (time.perf_counter() - t0)
             thr = oracle.max_threads()
             t0 = time.perf_counter()
-            oracle.spectrum_batch(sx, fftSize=n, sampleRate=48000.0, window=w["window"], threads=thr, **skw)
+            oracle.spectrum_batch(sx, threads=thr, **okw, **skw)
             allc = sample / (time.perf_counter() - t0)
             cpu_baseline = {"value": one, "unit": "frames/s", "cores": 1, "kind": "port",
-                            "sample": f"first {sample} frames of the same batch through oracle/pragma_oracle.c "
-                                      f"(single thread, like the single-threaded JS reference); all {thr} host threads: "
-                                      f"{allc:.0f} frames/s"}
+                            "sample": f"first {sample} frames of the same batch, same outputs ({', '.join(outs)}), through "
+                                      f"oracle/pragma_oracle.c (single thread, like the single-threaded JS reference); all {thr} "
+                                      f"host threads: {allc:.0f} frames/s"}
 
     if rank == 0:
         total_frames = frames * world
@@ -552,19 +634,25 @@ def run_b200(args, w):
         bpf = algorithmic_bytes_per_frame(w)
         peak, peak_src = measured_hbm_peak()
         achieved = bpf * frames / (kern_ms * 1e-3) / 1e9
-        traffic = _traffic_of(args.workload)
+        traffic, traffic_src = _traffic_of(args.workload, frames)
+        if burst:
+            burst["value"] = BURST_FRAMES / (burst["ms_per_launch"] * 1e-3)
+            burst["frac"] = bpf * burst["value"] / 1e9 / peak
+            burst["note"] = "boost clocks, ~3 ms: not the sustained rate"
         line = {
             "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": w["prec"], "data": "synthetic",
-            "config": workload_config(args, w),
+            "warmup": warm_steps, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": w["prec"], "data": "synthetic",
+            "config": dict(workload_config(args, w), frames_per_gpu=frames),
             "hbm_gbs": fps * bpf / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "r2c_kernel",
-                         "algorithmic_bytes_per_frame": bpf, "kernel_ms": kern_ms},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "r2c_kernel",
+                         "algorithmic_bytes_per_frame": bpf, "kernel_ms": kern_ms,
+                         "timed": f"CUDA events around each of the {args.steps} launches of the timed region, mean"},
+            "burst": burst,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pdsp_spectrum (host pinned buffers)"},
+                    "steps": e2e_steps, "frames_per_step": e2e_frames, "api": "pdsp_spectrum (host pinned buffers)"},
             "ingest": ingest,
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
@@ -696,7 +784,8 @@ def run_b200_c2c(args, w):
                        "parallelism": f"replicas x{world}"},
             "hbm_gbs": fps * bpf / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic_of(args.workload), "peak_source": peak_src,
+                         "traffic": _traffic_of(args.workload, frames)[0], "traffic_source": _traffic_of(args.workload, frames)[1],
+                         "peak_source": peak_src,
                          "kernel": "r2c_kernel (MD_CPLX)" if real_in else "bigfft_pass(_tma)_kernel (all passes of a transform)",
                          "algorithmic_bytes_per_frame": bpf, "kernel_ms": step_ms},
             "cpu_baseline": cpu_baseline,
@@ -709,6 +798,84 @@ def run_b200_c2c(args, w):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+# ----------------------------------------------------------------------------- b200 arm, single-call latency (C1)
+def run_b200_latency(args, w):
+    """BASELINE configs[0]: Radix2Fft.forward(input, out) on ONE N=1024 fp64 frame of sin(i) (README.md:43-50) - the
+    reference's primary call shape.  Reports microseconds per call through the C ABI (pdsp_fft_forward_real, pageable
+    host arrays like JS typed arrays) and through spectrum()'s entry (pdsp_spectrum, one frame), next to the 1-core
+    oracle on the same frame, and the batch size at which the host entry point overtakes the CPU port."""
+    import torch  # noqa: F401  (device bring-up only)
+
+    import oracle
+    from pragma_dsp_b200 import _lib
+    from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = _lib.Context(local)
+    L = lib()
+    n = w["n"]
+    plan = ctx.plan(n, F64)
+    x = np.sin(np.arange(n, dtype=np.float64))
+    ore, oim = np.empty(n), np.empty(n)
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    calls = max(200, args.steps * 50)
+
+    def time_calls(fn, k):
+        for _ in range(max(10, args.warmup * 4)):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        return (time.perf_counter() - t0) / k * 1e6
+
+    fwd_us = time_calls(lambda: check(L.pdsp_fft_forward_real(plan, vp(x), F64, 1, vp(ore), vp(oim))), calls)
+    bins = n // 2 + 1
+    amp, ph, pk = np.empty(bins), np.empty(bins), np.zeros(1, dtype=PEAK_F64)
+    d1 = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=1, window=WINDOWS["hann"], sides=SIDES["one"],
+                      sample_rate=48000.0, raw_magnitude=0)
+    spec_us = time_calls(lambda: check(L.pdsp_spectrum(plan, C.byref(d1), vp(x), vp(amp), vp(ph), vp(pk))), calls)
+    # the same two calls on the CPU port, one core
+    po = oracle.FFT(n)
+    cpu_fwd_us = time_calls(lambda: po.forward(x), calls)
+    cpu_spec_us = time_calls(lambda: oracle.spectrum_batch(x[None, :], fftSize=n, sampleRate=48000.0, window="hann"), calls)
+    rre, rim = po.forward(x)
+    rel = float(np.linalg.norm((ore - rre.reshape(-1)) + 1j * (oim - rim.reshape(-1))) / np.linalg.norm(rre + 1j * rim))
+    # crossover: frames per pdsp_spectrum call at which the GPU entry point beats the 1-core port
+    cross = None
+    per_frame_cpu = None
+    xs = np.tile(x, (4096, 1))
+    table = []
+    for b in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024, 4096):
+        a_b, p_b, k_b = np.empty((b, bins)), np.empty((b, bins)), np.zeros(b, dtype=PEAK_F64)
+        db = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=b, window=WINDOWS["hann"], sides=SIDES["one"],
+                          sample_rate=48000.0, raw_magnitude=0)
+        g_us = time_calls(lambda: check(L.pdsp_spectrum(plan, C.byref(db), vp(xs), vp(a_b), vp(p_b), vp(k_b))), max(20, calls // 10))
+        c_us = time_calls(lambda: oracle.spectrum_batch(xs[:b], fftSize=n, sampleRate=48000.0, window="hann"), max(5, calls // 40))
+        table.append({"frames": b, "gpu_us": g_us, "cpu_1core_us": c_us})
+        if cross is None and g_us < c_us:
+            cross = b
+        per_frame_cpu = c_us / b
+    line = {
+        "metric": "us_per_call", "value": fwd_us, "unit": "us", "n_gpus": 1, "steps": calls, "warmup": max(10, args.warmup * 4),
+        "ms_per_step": fwd_us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
+        "latency": {"Radix2Fft.forward_us": fwd_us, "spectrum_us": spec_us, "cpu_port_forward_us": cpu_fwd_us,
+                    "cpu_port_spectrum_us": cpu_spec_us, "gpu_overtakes_cpu_at_frames_per_call": cross,
+                    "cpu_port_us_per_frame_batched": per_frame_cpu, "by_batch": table,
+                    "api": "pdsp_fft_forward_real / pdsp_spectrum, pageable host arrays, one call = H2D + kernel + D2H + sync"},
+        "cpu_baseline": {"value": cpu_fwd_us, "unit": "us", "cores": 1, "kind": "port",
+                         "sample": "the same single frame through oracle/pragma_oracle.c (ctypes call overhead included on both arms)"},
+        "e2e": {"value": fwd_us, "unit": "us", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n},
+        "gpu_launches": ctx.launch_count, "parity": {"rel_l2_vs_oracle": rel, "bound": 1e-12 * np.log2(n)},
+    }
+    emit_line(line)
     ctx.close()
     return 0
 
@@ -731,10 +898,12 @@ class StdoutToStderr:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every rank owns the workload's frame count; strong = the frame count is split over the ranks")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the workload's)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how per-frame peaks reach every rank - peer stores fused into the kernel epilogue (p2p) "
@@ -749,6 +918,8 @@ def main():
     try:
         if args.impl == "reference":
             return run_reference(args, w)
+        if w.get("kind") == "latency":
+            return run_b200_latency(args, w)
         if w.get("kind") in ("c2c", "r2c_forward"):
             return run_b200_c2c(args, w)
         return run_b200(args, w)

@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
         L.po_bin_frequencies.argtypes = [C.c_int, C.c_double, C.c_int, dp]
         L.po_spectrum_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                         C.c_longlong, C.c_double, C.c_int, dp, dp, C.c_void_p, C.c_int]
+        L.po_spectrum_batch_lean.argtypes = L.po_spectrum_batch.argtypes
         L.po_fft_batch.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_longlong, C.c_int, C.c_int]
         L.po_bench_checksum.restype = C.c_double
         L.po_bench_checksum.argtypes = [dp, dp, C.c_int]
@@ -169,11 +170,13 @@ def binFrequencies(size: int, sampleRate: float, sides: str = "one") -> np.ndarr
 
 
 def spectrum_batch(samples, *, fftSize=None, frameLen=None, hop=None, batch=None, sampleRate=1.0, window="rect",
-                   sides="one", want_amplitude=True, want_phase=True, threads=1):
+                   sides="one", want_amplitude=True, want_phase=True, want_peaks=True, threads=1, lean=False):
     """spectrum() (src/public/spectrum.ts:107-142) over a batch of frames.
 
     ``samples`` is a float32/float64 array; 2-D (batch, frameLen) or 1-D with explicit
     frameLen/hop/batch (STFT addressing).  Returns dict(amplitude, phase, peaks, frequencies).
+    lean=True (bench.py's reference arm): Math.atan2 only where an output needs it (all bins for the phase array,
+    the peak bin for a peak without one) instead of spectrum()'s unconditional phase pass.
     """
     samples = np.ascontiguousarray(samples)
     if samples.dtype not in (np.float32, np.float64):
@@ -191,11 +194,12 @@ def spectrum_batch(samples, *, fftSize=None, frameLen=None, hop=None, batch=None
     bins = size // 2 + 1 if sides == "one" else size
     amp = np.empty((batch, bins), dtype=np.float64) if want_amplitude else None
     ph = np.empty((batch, bins), dtype=np.float64) if want_phase else None
-    peaks = np.zeros(batch, dtype=PEAK_DTYPE)
-    used = lib().po_spectrum_batch(plan._h, WINDOWS[window], samples.ctypes.data_as(C.c_void_p),
+    peaks = np.zeros(batch, dtype=PEAK_DTYPE) if want_peaks else None
+    fn = lib().po_spectrum_batch_lean if lean else lib().po_spectrum_batch
+    used = fn(plan._h, WINDOWS[window], samples.ctypes.data_as(C.c_void_p),
                                    1 if samples.dtype == np.float64 else 0, int(frameLen), int(hop), int(batch),
                                    float(sampleRate), SIDES[sides], _dp(amp), _dp(ph),
-                                   peaks.ctypes.data_as(C.c_void_p), int(threads))
+                                   None if peaks is None else peaks.ctypes.data_as(C.c_void_p), int(threads))
     return {"amplitude": amp, "phase": ph, "peaks": peaks, "frequencies": binFrequencies(size, sampleRate, sides),
             "threads": used}
 

@@ -276,9 +276,12 @@ PO_API void po_find_peak(const double* amplitude, const double* frequencies, int
  *                 exactly), buildFrame zero-pads / truncates to plan->size (:36-43)
  *   amplitude, phase_out, frequencies : bins = size/2+1 (one) or size (two); any may be NULL
  *   scratch : 5*size doubles of workspace */
-PO_API void po_spectrum_frame(const po_plan* p, const double* window, const double* samples, int len,
-                              double sample_rate, int sides, double* amplitude, double* phase_out,
-                              double* frequencies, po_peak* peak, double* scratch) {
+/* lean != 0 (bench.py's reference arm only, so that it computes the SAME outputs as the GPU arm it is compared
+ * with): Math.atan2 runs over all bins only when the phase array is requested; with a peak but no phase array it
+ * runs once, at the peak bin.  lean == 0 is spectrum() as written (all phases always, src/public/spectrum.ts:121-122). */
+static void po_spectrum_frame_ex(const po_plan* p, const double* window, const double* samples, int len,
+                                 double sample_rate, int sides, double* amplitude, double* phase_out,
+                                 double* frequencies, po_peak* peak, double* scratch, int lean) {
   const int size = p->size;
   double* frame = scratch;
   double* re = scratch + size;
@@ -291,7 +294,7 @@ PO_API void po_spectrum_frame(const po_plan* p, const double* window, const doub
   for (int i = 0; i < size; i += 1) frame[i] = frame[i] * window[i]; /* applyWindow */
   po_fft_transform(p, frame, NULL, re, im, 0);
   po_magnitude(re, im, size, mag);
-  po_phase(re, im, size, ang);
+  if (!lean || phase_out) po_phase(re, im, size, ang);
   const int bins = sides == PO_SIDES_ONE ? size / 2 + 1 : size;
   double* amp = amplitude ? amplitude : frame; /* frame is free again */
   if (sides == PO_SIDES_ONE)
@@ -326,8 +329,13 @@ PO_API void po_spectrum_frame(const po_plan* p, const double* window, const doub
     peak->_pad = 0;
     peak->frequency = (double)index * scale;
     peak->amplitude = amp[index];
-    peak->phase = ang[index]; /* peak.phase = phaseBins[peak.index] */
+    peak->phase = (lean && !phase_out) ? atan2(im[index], re[index]) : ang[index]; /* peak.phase = phaseBins[peak.index] */
   }
+}
+PO_API void po_spectrum_frame(const po_plan* p, const double* window, const double* samples, int len,
+                              double sample_rate, int sides, double* amplitude, double* phase_out,
+                              double* frequencies, po_peak* peak, double* scratch) {
+  po_spectrum_frame_ex(p, window, samples, len, sample_rate, sides, amplitude, phase_out, frequencies, peak, scratch, 0);
 }
 
 /* Batched driver over `batch` frames taken at samples + f*hop (element units), each
@@ -335,9 +343,9 @@ PO_API void po_spectrum_frame(const po_plan* p, const double* window, const doub
  * src/effect/index.ts:72-79).  Output rows are dense: bins per frame.  Any output may be NULL.
  * threads <= 1 runs single-threaded like the JS reference; threads > 1 splits frames
  * statically over OpenMP threads (used only by bench.py's reference arm). Returns threads used. */
-PO_API int po_spectrum_batch(const po_plan* p, int window_type, const void* samples, int dtype, int frame_len,
-                             long long hop, long long batch, double sample_rate, int sides, double* amplitude,
-                             double* phase_out, po_peak* peaks, int threads) {
+static int po_spectrum_batch_impl(const po_plan* p, int window_type, const void* samples, int dtype, int frame_len,
+                                  long long hop, long long batch, double sample_rate, int sides, double* amplitude,
+                                  double* phase_out, po_peak* peaks, int threads, int lean) {
   const int size = p->size;
   const int bins = sides == PO_SIDES_ONE ? size / 2 + 1 : size;
   double* window = (double*)malloc(sizeof(double) * (size_t)size);
@@ -363,16 +371,29 @@ PO_API int po_spectrum_batch(const po_plan* p, int window_type, const void* samp
       } else {
         src = (const double*)samples + f * hop;
       }
-      po_spectrum_frame(p, window, src, frame_len, sample_rate, sides,
-                        amplitude ? amplitude + f * (long long)bins : NULL,
-                        phase_out ? phase_out + f * (long long)bins : NULL, NULL, peaks ? peaks + f : NULL,
-                        scratch);
+      po_spectrum_frame_ex(p, window, src, frame_len, sample_rate, sides,
+                           amplitude ? amplitude + f * (long long)bins : NULL,
+                           phase_out ? phase_out + f * (long long)bins : NULL, NULL, peaks ? peaks + f : NULL,
+                           scratch, lean);
     }
     free(scratch);
     free(wide);
   }
   free(window);
   return used;
+}
+PO_API int po_spectrum_batch(const po_plan* p, int window_type, const void* samples, int dtype, int frame_len,
+                             long long hop, long long batch, double sample_rate, int sides, double* amplitude,
+                             double* phase_out, po_peak* peaks, int threads) {
+  return po_spectrum_batch_impl(p, window_type, samples, dtype, frame_len, hop, batch, sample_rate, sides, amplitude,
+                                phase_out, peaks, threads, 0);
+}
+/* bench.py --impl reference: only the outputs the GPU arm produces (see po_spectrum_frame_ex) */
+PO_API int po_spectrum_batch_lean(const po_plan* p, int window_type, const void* samples, int dtype, int frame_len,
+                                  long long hop, long long batch, double sample_rate, int sides, double* amplitude,
+                                  double* phase_out, po_peak* peaks, int threads) {
+  return po_spectrum_batch_impl(p, window_type, samples, dtype, frame_len, hop, batch, sample_rate, sides, amplitude,
+                                phase_out, peaks, threads, 1);
 }
 
 /* Batched forward/inverse transform, frames contiguous (stride = size). in_im may be NULL. */

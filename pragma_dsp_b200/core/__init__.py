@@ -37,6 +37,22 @@ def nextPowerOfTwo(n: int) -> int:
     return int(lib().pdsp_next_power_of_two(int(n)))
 
 
+def _check_plane(a, size: int, what: str) -> None:
+    """A caller-supplied output plane is handed to native code as a raw pointer: it must be exactly what the C ABI
+    writes - 1-D, `size` float64 elements, C-contiguous, writeable.  (The reference silently drops out-of-range
+    typed-array writes; a native memcpy would corrupt the heap instead, so this layer refuses.)"""
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{what} must be a numpy float64 array")
+    if a.dtype != np.float64:
+        raise TypeError(f"{what} must be float64 (Float64Array), got {a.dtype}")
+    if a.ndim != 1 or a.shape[0] != size:
+        raise ValueError(f"{what} must have length {size}, got shape {a.shape}")
+    if not a.flags.c_contiguous:
+        raise ValueError(f"{what} must be contiguous")
+    if not a.flags.writeable:
+        raise ValueError(f"{what} must be writeable")
+
+
 def _as_samples(x):
     """ArrayLike<number> -> contiguous float32/float64 (`?? 0` for missing elements is a JS-only notion)."""
     a = np.asarray(x)
@@ -56,16 +72,17 @@ class Radix2Fft:
         self._plan = self._ctx.plan(self.size, F64)
 
     def _out(self, out):
-        result = out if out is not None else createComplexArray(self.size)
-        if result.real.dtype != np.float64 or result.imag.dtype != np.float64:
-            raise TypeError("ComplexArray planes must be float64")
-        return result
+        if out is None:
+            return createComplexArray(self.size)
+        _check_plane(out.real, self.size, "out.real")
+        _check_plane(out.imag, self.size, "out.imag")
+        return out
 
     def forward(self, input, out: ComplexArray | None = None) -> ComplexArray:
         """:77-79 - real input of length size -> all N bins; returns the same `out` object."""
         x = _as_samples(input)
-        if x.shape[0] != self.size:
-            raise ValueError(f"FFT input length {x.shape[0]} != size {self.size}")
+        if x.ndim != 1 or x.shape[0] != self.size:
+            raise ValueError(f"FFT input length {x.shape[0] if x.ndim else 0} != size {self.size}")
         if self.size > 16384 and x.dtype != np.float64:
             x = x.astype(np.float64)  # the multi-pass path reads planes in the plan's precision
         result = self._out(out)
@@ -76,10 +93,10 @@ class Radix2Fft:
     def _complex(self, input: ComplexArray, out, fn):
         re = np.ascontiguousarray(input.real, dtype=np.float64)
         im = np.ascontiguousarray(input.imag, dtype=np.float64)
-        if re.shape[0] != self.size:
-            raise ValueError(f"FFT input length {re.shape[0]} != size {self.size}")
-        if im.shape[0] != self.size:
-            raise ValueError(f"FFT input length {im.shape[0]} != size {self.size}")
+        if re.ndim != 1 or re.shape[0] != self.size:
+            raise ValueError(f"FFT input length {re.shape[0] if re.ndim else 0} != size {self.size}")
+        if im.ndim != 1 or im.shape[0] != self.size:
+            raise ValueError(f"FFT input length {im.shape[0] if im.ndim else 0} != size {self.size}")
         result = self._out(out)
         check(fn(self._plan, ptr(re), ptr(im), 1, ptr(result.real), ptr(result.imag)))
         return result

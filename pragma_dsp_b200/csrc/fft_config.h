@@ -48,7 +48,10 @@ struct KCfg {
   static constexpr int THREADS = LOG2P == 5 ? (TF > 32 ? TF : 32) : (TF > 128 ? TF : 128);
   // occupancy target via __launch_bounds__(THREADS, MINB): 128 regs/thread, except 96 for floats holding
   // 8 or 16 points.  MAXREG > 0 selects a hard __maxnreg__ cap instead (tuning variants).
-  static constexpr int MINB = (sizeof(T) == 8 && LOG2P == 5) ? (256 / THREADS > 0 ? 256 / THREADS : 1)
+#ifndef PDSP_F64_MINB_M9
+#define PDSP_F64_MINB_M9 4  // experiment: CTAs per SM of the fp64 N = 1024 kernels (4 = 128 registers, 5 = 102)
+#endif
+  static constexpr int MINB = (sizeof(T) == 8 && LOG2M == 9 && LOG2P == 4) ? PDSP_F64_MINB_M9 : (sizeof(T) == 8 && LOG2P == 5) ? (256 / THREADS > 0 ? 256 / THREADS : 1)
                               : (sizeof(T) == 4 && LOG2P < 5 && THREADS <= 128) ? 5 : (512 / THREADS > 0 ? 512 / THREADS : 1);
   static constexpr int MAXREG = 0;
 };

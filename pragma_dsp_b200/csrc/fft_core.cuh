@@ -211,6 +211,14 @@ PDSP_DEVICE void frame_sync(int slot, int slots_per_cta) {
 #ifndef PDSP_SHUFFLE_EXCHANGE
 #define PDSP_SHUFFLE_EXCHANGE 1
 #endif
+// fp64: derive the last pass' / the post-pass' twiddles from one table entry per thread (DP instructions) instead of
+// loading one per butterfly (L1 wavefronts); experiment switches, see profiles/r2/README.md
+#ifndef PDSP_DERIVE_LAST
+#define PDSP_DERIVE_LAST 1
+#endif
+#ifndef PDSP_DERIVE_POST
+#define PDSP_DERIVE_POST 1
+#endif
 
 template <typename T, int LOG2M, int LOG2P, int MAXRB>
 struct FftEngine {
@@ -287,7 +295,7 @@ struct FftEngine {
       // compile-time 32nd root of unity for the others - P/R - 1 fewer L1 loads per leg.
       // (doubles only: the fp64 kernels are L1-bound with DP slack, the fp32 kernels are issue-bound with
       // L1 slack - there a load is cheaper than the four FP instructions of the derivation)
-      constexpr bool DERIVE = sizeof(T) == 8 && last && NSL > 0 && BPT > 1 && (32 % P) == 0;
+      constexpr bool DERIVE = PDSP_DERIVE_LAST && sizeof(T) == 8 && last && NSL > 0 && BPT > 1 && (32 % P) == 0;
       // Exchange by shuffle (fp64, M = 512 = 16 x 16 x 2, one warp per frame): the radix-2 last pass pairs element
       // j with j + 256, and after this radix-16 pass thread (h, l) = (t >> 4, t & 15) holds the 16 outputs
       // k = 0..15 of position 256h + l + 16k.  The natural layout t' + 32q the last pass reads wants, in thread

@@ -508,7 +508,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     } else {
       // W_N^k * (-i/2) for k = t + TF*q: one table entry per thread (k = t) times the constant
       // W_N^{TF*q} = exp(-2*pi*i*q/(2P)) when that is a 32nd root of unity, else a load per pair
-      constexpr bool DERIVE = sizeof(T) == 8 && (16 % P) == 0 && P >= 2;  // see FftEngine::fft
+      constexpr bool DERIVE = PDSP_DERIVE_POST && sizeof(T) == 8 && (16 % P) == 0 && P >= 2;  // see FftEngine::fft
       const T hs = FOLD ? (T)0.5 * s_mid : (T)0.5;                         // folded amplitude scale (a power of two)
       cx<T> post0{(T)0, (T)0};
       if constexpr (DERIVE) {

@@ -8,7 +8,7 @@ import numpy as np
 
 from .. import _lib
 from .._lib import SIDES, WINDOWS, check, lib, ptr
-from ..core import ComplexArray, Radix2Fft, createComplexArray, isPowerOfTwo
+from ..core import ComplexArray, Radix2Fft, _check_plane, createComplexArray, isPowerOfTwo
 
 WindowType = str  # "rect" | "hann" | "hamming" | "blackman"
 FftSides = str    # "one" | "two"
@@ -56,6 +56,11 @@ class FFT:
 def _elementwise(fn, input: ComplexArray, out):
     re = np.ascontiguousarray(input.real, dtype=np.float64)
     im = np.ascontiguousarray(input.imag, dtype=np.float64)
+    if re.ndim != 1 or im.shape != re.shape:
+        # the reference reads a missing imaginary element as `?? 0`; a native read past a shorter plane is not an option
+        raise ValueError(f"real and imaginary planes must be 1-D and of equal length, got {re.shape} and {im.shape}")
+    if out is not None:
+        _check_plane(out, re.shape[0], "out")
     result = out if out is not None else np.empty(re.shape[0], dtype=np.float64)
     check(fn(_lib.default_context().h, ptr(re), ptr(im), re.shape[0], ptr(result)))
     return result
@@ -75,8 +80,10 @@ def applyWindow(input, window, out: np.ndarray | None = None) -> np.ndarray:
     """src/xform/fourier.ts:54-67 - elementwise product (the fused spectrum path never materialises it)."""
     x = np.ascontiguousarray(input, dtype=np.float64)
     w = np.ascontiguousarray(window, dtype=np.float64)
-    if x.shape[0] != w.shape[0]:
+    if x.ndim != 1 or w.ndim != 1 or x.shape[0] != w.shape[0]:
         raise ValueError("Window length must match input length.")
+    if out is not None:
+        _check_plane(out, x.shape[0], "out")
     result = out if out is not None else np.empty(x.shape[0], dtype=np.float64)
     check(lib().pdsp_apply_window(_lib.default_context().h, ptr(x), ptr(w), x.shape[0], ptr(result)))
     return result
@@ -85,6 +92,10 @@ def applyWindow(input, window, out: np.ndarray | None = None) -> np.ndarray:
 def fftShift(input, out: np.ndarray | None = None) -> np.ndarray:
     """src/xform/fourier.ts:122-134 - rotate by floor(n/2) so DC sits in the middle."""
     x = np.ascontiguousarray(input, dtype=np.float64)
+    if x.ndim != 1:
+        raise ValueError(f"fftShift expects a 1-D array, got shape {x.shape}")
+    if out is not None:
+        _check_plane(out, x.shape[0], "out")
     result = out if out is not None else np.empty(x.shape[0], dtype=np.float64)
     if x.shape[0]:
         check(lib().pdsp_fft_shift(_lib.default_context().h, ptr(x), x.shape[0], ptr(result)))
@@ -93,6 +104,8 @@ def fftShift(input, out: np.ndarray | None = None) -> np.ndarray:
 
 def fftShiftComplex(input: ComplexArray, out: ComplexArray | None = None) -> ComplexArray:
     """src/xform/fourier.ts:136-145"""
+    if np.shape(input.imag) != np.shape(input.real):
+        raise ValueError("real and imaginary planes must be of equal length")
     result = out if out is not None else createComplexArray(input.real.shape[0])
     fftShift(input.real, result.real)
     fftShift(input.imag, result.imag)

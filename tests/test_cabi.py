@@ -80,3 +80,31 @@ def test_fails_loudly_without_gpu():
         Radix2Fft(8)
     with pytest.raises(ValueError, match="FFT size must be power of two, got 12"):
         Radix2Fft(12)  # validation precedes device work
+
+
+def test_out_arrays_are_validated_before_native_code():
+    """a caller-supplied `out` goes to native code as a raw pointer - short, strided, read-only or
+    wrong-dtype planes must be refused by the host layer (no GPU needed: validation precedes device work)."""
+    from pragma_dsp_b200.core import ComplexArray, _check_plane
+    from pragma_dsp_b200.xform import fourier
+    good = np.zeros(8)
+    _check_plane(good, 8, "out")
+    for bad, exc in ((np.zeros(7), ValueError), (np.zeros(16)[::2], ValueError), (np.zeros(8, dtype=np.float32), TypeError),
+                     (np.zeros((2, 4)), ValueError), ([0.0] * 8, TypeError)):
+        with pytest.raises(exc):
+            _check_plane(bad, 8, "out")
+    ro = np.zeros(8)
+    ro.setflags(write=False)
+    with pytest.raises(ValueError, match="writeable"):
+        _check_plane(ro, 8, "out")
+    c = ComplexArray(np.zeros(8), np.zeros(8))
+    with pytest.raises(ValueError, match="length 8"):
+        fourier.magnitude(c, np.zeros(4))
+    with pytest.raises(ValueError, match="equal length"):
+        fourier.phase(ComplexArray(np.zeros(8), np.zeros(4)))
+    with pytest.raises(ValueError, match="length 8"):
+        fourier.applyWindow(np.zeros(8), np.ones(8), np.zeros(9))
+    with pytest.raises(ValueError, match="length 8"):
+        fourier.fftShift(np.zeros(8), np.zeros(16)[::2][:8][:4])
+    with pytest.raises(ValueError, match="equal length"):
+        fourier.fftShiftComplex(ComplexArray(np.zeros(8), np.zeros(4)))

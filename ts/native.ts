@@ -13,6 +13,8 @@ export interface Native {
   fftInverse(plan: Handle, inRe: Float64Array, inIm: Float64Array, outRe: Float64Array, outIm: Float64Array): void;
   magnitude(ctx: Handle, re: Float64Array, im: Float64Array, out: Float64Array): void;
   phase(ctx: Handle, re: Float64Array, im: Float64Array, out: Float64Array): void;
+  applyWindow(ctx: Handle, input: Float64Array, window: Float64Array, out: Float64Array): void;
+  fftShift(ctx: Handle, input: Float64Array, out: Float64Array): void;
   spectrum(plan: Handle, samples: Float32Array | Float64Array, opts: Record<string, number>,
            amplitude: Float32Array | Float64Array | null, phase: Float32Array | Float64Array | null,
            peaks: Uint8Array | null): void;

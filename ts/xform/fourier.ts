@@ -1,5 +1,5 @@
-// Drop-in for pragma-dsp/xform/fourier (reference src/xform/fourier.ts): FFT, createWindow,
-// magnitude, phase, binFrequencies keep their signatures and messages.
+// Drop-in for pragma-dsp/xform/fourier (reference src/xform/fourier.ts): every export - FFT, createWindow, applyWindow,
+// magnitude, phase, fftShift, fftShiftComplex, binFrequencies, WindowType, FftSides - keeps its signature and messages.
 import { type ComplexArray, Radix2Fft, createComplexArray, isPowerOfTwo } from "../core/fft.js";
 import { SIDES_CODE, WINDOW_CODE, ctx, native } from "../native.js";
 
@@ -12,6 +12,22 @@ export const createWindow = (type: WindowType, size: number): Float64Array => {
   if (code === undefined) throw new Error(`Unsupported window type: ${type}`);
   const out = new Float64Array(size);
   native().createWindow(code, size, out);
+  return out;
+};
+
+// applyWindow(input, window, out?) - reference src/xform/fourier.ts:54-67 (the fused spectrum() path never materialises it)
+export const applyWindow = (input: ArrayLike<number>, window: ArrayLike<number>, out?: Float64Array): Float64Array => {
+  if (input.length !== window.length) throw new Error("Window length must match input length.");
+  const result = out ?? new Float64Array(input.length);
+  if (result.length < input.length) throw new Error("Window length must match input length.");
+  native().applyWindow(ctx(), toF64(input), toF64(window), result);
+  return result;
+};
+
+const toF64 = (a: ArrayLike<number>): Float64Array => {
+  if (a instanceof Float64Array) return a;
+  const out = new Float64Array(a.length);
+  for (let i = 0; i < a.length; i += 1) out[i] = a[i] ?? 0;
   return out;
 };
 
@@ -38,6 +54,21 @@ export const magnitude = (input: ComplexArray, out?: Float64Array): Float64Array
 export const phase = (input: ComplexArray, out?: Float64Array): Float64Array => {
   const result = out ?? new Float64Array(input.real.length);
   native().phase(ctx(), input.real, input.imag, result);
+  return result;
+};
+
+// fftShift(input, out?) - reference src/xform/fourier.ts:122-134: rotate by floor(n/2) so that DC sits in the middle
+export const fftShift = (input: ArrayLike<number>, out?: Float64Array): Float64Array => {
+  const result = out ?? new Float64Array(input.length);
+  if (input.length > 0) native().fftShift(ctx(), toF64(input), result);
+  return result;
+};
+
+// fftShiftComplex(input, out?) - reference src/xform/fourier.ts:136-145: fftShift applied to each plane
+export const fftShiftComplex = (input: ComplexArray, out?: ComplexArray): ComplexArray => {
+  const result = out ?? createComplexArray(input.real.length);
+  fftShift(input.real, result.real);
+  fftShift(input.imag, result.imag);
   return result;
 };
 
