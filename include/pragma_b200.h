@@ -15,7 +15,10 @@
  *     input length) stays in the host language; the library re-checks and fails with its own text.
  *   - "host" entry points take ordinary host pointers (JS typed-array memory), stage through
  *     pinned buffers owned by the context, run on the context's stream and return after the
- *     results are in the caller's arrays (the reference is synchronous).
+ *     results are in the caller's arrays (the reference is synchronous).  Jobs of up to 256 KB (input +
+ *     outputs: Radix2Fft.forward or spectrum() on one or a few frames) take the single-call fast lane:
+ *     one kernel launch reading and writing a host-mapped pinned buffer, completion by a doorbell word;
+ *     larger jobs are cut into chunks and pipelined (H2D, kernel, D2H) over three streams.
  *   - "dev" entry points take device pointers and a CUDA stream and only enqueue work.
  *   - there is no CPU execution path: without a CUDA device pdsp_ctx_create fails.
  */
@@ -66,13 +69,16 @@ int pdsp_ctx_destroy(pdsp_ctx* ctx);
 int pdsp_ctx_sync(pdsp_ctx* ctx);
 int pdsp_ctx_device(const pdsp_ctx* ctx);
 /* Tuning / test hook: sets one tunable of the context ("staged", "chunk_bytes", "big_tma", "big_interleave",
- * "big_prefetch", "big_chunk", "big_factors", "big_resident", "variant"); value NULL or "" restores the default.  The same
+ * "big_prefetch", "big_chunk", "big_factors", "big_resident", "fast", "copy_threads", "variant"); value NULL or "" restores the default.  The same
  * tunables are read ONCE from the environment (PDSP_<KEY>) when the context is created; nothing on the launch
  * path reads the environment.  Results do not depend on them (parity tests run every setting). */
 int pdsp_ctx_tune(pdsp_ctx* ctx, const char* key, const char* value);
 int pdsp_ctx_sm_count(const pdsp_ctx* ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 int64_t pdsp_ctx_launch_count(const pdsp_ctx* ctx);
+/* number of host calls served by the single-call fast lane (small jobs: one launch through a host-mapped pinned
+ * buffer, completion by doorbell; see "host entry points" above) */
+int64_t pdsp_ctx_fast_call_count(const pdsp_ctx* ctx);
 
 /* ---- pure host helpers (no device work) -------------------------------------------------- */
 /* src/core/fft.ts:16 isPowerOfTwo, :18-23 nextPowerOfTwo */
@@ -175,6 +181,14 @@ int pdsp_ingest_open(pdsp_plan* plan, const pdsp_spectrum_desc* desc, int want_a
                      int64_t frames_per_chunk, int depth, pdsp_ingest** ring);
 /* copies `count` frames, `stride` samples apart (0 = frame_len); *accepted < count means the ring is full */
 int pdsp_ingest_push(pdsp_ingest* ring, const void* frames, int64_t count, int64_t stride, int64_t* accepted);
+/* as pdsp_ingest_push for frames in pinned (page-locked) host memory - e.g. an ArrayBuffer from pdsp_host_alloc: no host
+ * copy, the frames go to the device by DMA straight from `frames`, which must stay unchanged until they have been popped.
+ * A chunk holds either copied or pinned frames (flush between the two kinds). */
+int pdsp_ingest_push_pinned(pdsp_ingest* ring, const void* frames, int64_t count, int64_t stride, int64_t* accepted);
+/* non-blocking progress: frames that pdsp_ingest_pop would return without waiting, frames sent and still in flight,
+ * frames waiting in the partially filled chunk (any pointer may be NULL).  What a latency-bound caller polls:
+ * flush when nothing is in flight, pop what is finished. */
+int pdsp_ingest_ready(pdsp_ingest* ring, int64_t* finished, int64_t* in_flight, int64_t* pending);
 /* sends the partially filled chunk (end of stream / latency bound) */
 int pdsp_ingest_flush(pdsp_ingest* ring);
 /* up to max_frames finished frames, in arrival order, appended densely to the caller's arrays (NULL = skip);

@@ -45,6 +45,7 @@ SYMBOLS = {
     "pdsp_plan_release_stream": (C.c_int, [_vp, _vp]),
     "pdsp_ctx_sm_count": (C.c_int, [_vp]),
     "pdsp_ctx_launch_count": (_i64, [_vp]),
+    "pdsp_ctx_fast_call_count": (_i64, [_vp]),
     "pdsp_is_power_of_two": (C.c_int, [_i32]),
     "pdsp_next_power_of_two": (_i32, [_i32]),
     "pdsp_create_window": (C.c_int, [C.c_int, _i32, _dp]),
@@ -76,6 +77,8 @@ SYMBOLS = {
     "pdsp_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "pdsp_ingest_open": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, C.c_int, C.POINTER(C.c_void_p)]),
     "pdsp_ingest_push": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_i64)]),
+    "pdsp_ingest_push_pinned": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_i64)]),
+    "pdsp_ingest_ready": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "pdsp_ingest_flush": (C.c_int, [_vp]),
     "pdsp_ingest_pop": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "pdsp_ingest_close": (C.c_int, [_vp]),
@@ -133,6 +136,10 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().pdsp_ctx_launch_count(self.h))
+
+    @property
+    def fast_call_count(self) -> int:
+        return int(lib().pdsp_ctx_fast_call_count(self.h))
 
     def close(self) -> None:
         if self.h:

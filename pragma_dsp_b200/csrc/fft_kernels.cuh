@@ -30,6 +30,28 @@ struct PeakRec<float> {  // 16 B
   float frequency, amplitude, phase;
 };
 
+// Completion doorbell of a launch (null flag = none): every CTA makes its results visible system-wide and bumps `count`
+// (device memory, zero between launches); the last one resets it and stores `seq` to `flag`, a word in host-mapped pinned
+// memory the host spins on.  Used by the single-call fast path (Radix2Fft.forward / spectrum() on one frame), where a
+// stream synchronisation would cost as much as the transform.
+struct Doorbell {
+  unsigned* flag;
+  unsigned* count;
+  unsigned seq;
+};
+PDSP_DEVICE void ring_doorbell(const Doorbell& d) {
+  if (d.flag == nullptr) return;
+  simt::fence_system();
+  simt::sync_block();
+  if (simt::tid() == 0) {
+    if (simt::atomic_add(d.count, 1u) == (unsigned)simt::nblocks() - 1u) {
+      *d.count = 0u;
+      simt::fence_system();
+      simt::store_volatile(d.flag, d.seq);
+    }
+  }
+}
+
 struct R2CParams {
   // input: frame f starts at samples + f*hop (elements), frame_len samples are valid
   const void* samples;
@@ -58,6 +80,7 @@ struct R2CParams {
   void* peer[8];
   int n_peers;
   long long peer_offset;
+  Doorbell door;
 };
 
 struct C2CParams {
@@ -68,6 +91,7 @@ struct C2CParams {
   long long batch;
   const void* tw;  // cx<T>[E::TW_ELEMS]: per-pass twiddles (set by the launcher)
   int inverse;     // conjugate transform and multiply by 1/N
+  Doorbell door;
 };
 
 template <typename T>
@@ -797,6 +821,7 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       for (int g = 0; g < p.n_peers; ++g) static_cast<PeakRec<T>*>(p.peer[g])[p.peer_offset + f] = rec;
     }
   }
+  ring_doorbell(p.door);
 }
 
 // Kernel entry points: the occupancy target is either __launch_bounds__(THREADS, MINB) or, for the
@@ -855,6 +880,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(THREADS, MINB) c2c_kernel(const C2CParams p)
       });
     }
   }
+  ring_doorbell(p.door);
 }
 
 }  // namespace pdsp

@@ -100,12 +100,11 @@ cudaError_t launch_c2c_t(const C2CParams& p, const LaunchCtx& lc) {
 #define PDSP_STAGED_MODES(X) \
   X(MD_AMP) X(MD_AMP | MD_PEAK) X(MD_PEAK) X(MD_CPLX) X(MD_AMP | MD_PHASE) X(MD_AMP | MD_PHASE | MD_PEAK)
 
-// staged kernels are built for frames that fit a warp, from N = 512 up (smaller frames gain nothing: several frames
-// share one warp's load instructions already)
+// staged kernels are an opt-in experiment (pdsp_ctx_tune "staged"), built for the headline size only
 template <typename T, int LOG2M>
 constexpr bool staged_supported() {
   using C = KCfg<T, LOG2M>;
-  return LOG2M >= 8 && C::TF <= 32;
+  return LOG2M == kVariantLog2M && C::TF <= 32;
 }
 
 inline bool mode_is_specialised(int mode) {

@@ -17,8 +17,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -70,8 +72,10 @@ struct Tune {
   int big_factors[3] = {0, 0, 0};  // PDSP_BIG_FACTORS "a,b[,c]": log2 of forced pass lengths (test hook)
   int n_big_factors = 0;
   long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
-  int staged = -1;            // PDSP_STAGED: -1 auto, 0 / 1 force the direct / bulk-staged sample loads
+  int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
   int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
+  int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
+  int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
 };
 static int tune_set(Tune& t, const char* key, const char* val) {
   if (!key) return 1;
@@ -99,6 +103,10 @@ static int tune_set(Tune& t, const char* key, const char* val) {
     t.staged = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_resident")) {
     t.big_resident = unset ? -1 : (v[0] != '0');
+  } else if (!strcmp(key, "fast")) {
+    t.fast = unset ? 1 : (v[0] != '0');
+  } else if (!strcmp(key, "copy_threads")) {
+    t.copy_threads = unset ? 3 : (atoi(v) < 0 ? 0 : atoi(v));
   } else {
     return 1;
   }
@@ -109,7 +117,7 @@ static void tune_from_env(Tune& t) {
                                         {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
                                         {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
                                         {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
-                                        {"big_resident", "PDSP_BIG_RESIDENT"}};
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}};
   for (auto& k : keys)
     if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
@@ -344,6 +352,20 @@ struct Slot {
   bool busy = false;
 };
 
+// Single-call fast lane (Radix2Fft.forward / spectrum() on one or a few frames: src/core/fft.ts:77-79,
+// src/public/spectrum.ts:107-142 are synchronous one-frame calls).  The 3-slot pipeline costs four driver calls,
+// two copy-engine hops and an event wait per call - more than the transform.  Small jobs instead go through ONE
+// kernel launch: samples are memcpy'd into a host-mapped pinned buffer that the kernel reads and writes directly
+// over PCIe, and completion is a doorbell word the last CTA stores into that buffer (the host spins on it).
+struct FastLane {
+  unsigned char* h = nullptr;  // pinned + mapped: [in | outputs], kFastBytes, then the doorbell word
+  unsigned char* d = nullptr;  // device alias of h
+  unsigned* d_count = nullptr;  // CTA counter of the doorbell (device memory, zero between launches)
+  unsigned seq = 0;
+  cudaStream_t stream = nullptr;
+};
+static const size_t kFastBytes = 256u << 10;
+
 struct pdsp_ctx {
   int device = 0;
   int sm_count = 0;
@@ -355,6 +377,8 @@ struct pdsp_ctx {
   std::map<std::tuple<int, int, int>, void*> pass_tw;  // (f64, log2m, rb) -> per-pass twiddle table
   std::atomic<long long> launches{0};
   Tune tune;  // read from the environment at creation, changed by pdsp_ctx_tune
+  FastLane fast;
+  std::atomic<long long> fast_calls{0};
 };
 
 // multi-pass plan of a transform too long for one CTA: N = 2^lg[0] * 2^lg[1] (* 2^lg[2])
@@ -587,12 +611,13 @@ struct PeerSpec {
 struct BigPlan;
 static int big_plan(pdsp_plan* pl, BigPlan** out);
 static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
-                      int inverse, cudaStream_t st);
+                      int inverse, cudaStream_t st, const Doorbell* door = nullptr, bool* door_used = nullptr);
 static int launch_spectrum_big(pdsp_plan* pl, const R2CParams& p, long long batch, cudaStream_t st);
 
 static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* d_samples, long long batch,
                            void* d_amp, void* d_phase, void* d_peaks, void* d_cre, void* d_cim, int cfull,
-                           cudaStream_t st, const PeerSpec* peers = nullptr) {
+                           cudaStream_t st, const PeerSpec* peers = nullptr, const Doorbell* door = nullptr,
+                           bool* door_used = nullptr) {
   pdsp_ctx* c = pl->ctx;
   const int n = pl->n;
   R2CParams p;
@@ -630,6 +655,7 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     p.scale_mid = 2.0 / (double)n;   // (2 * mag) / size, identical bits for power-of-two size
   }
   p.bin_hz = d->sample_rate / (double)n;  // binFrequencies: quotient first (fourier.ts:160)
+  if (door_used) *door_used = false;
   {
     // beyond one CTA (or forced by the big_factors test hook): window -> multi-pass transform -> epilogue
     bool big = pl->log2n - 1 > kMaxLog2M;
@@ -662,11 +688,16 @@ static int launch_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const voi
     if ((mode & MD_PAD) && (d->frame_len & 1)) mode = -1;  // MD_PAD loads whole sample pairs: even frame lengths only
     const bool regular = p.vec_ok && (d_cre == nullptr || (cfull && !p.two_sided)) &&
                          mode_is_specialised(mode);
-    if (regular && c->tune.staged != 0 && !(mode & (MD_PAD | MD_TWO)) && d->frame_len >= n) {
-      // bulk-staged sample loads (MD_STAGED): 16-byte aligned frames, sample type no wider than the plan's;
-      // dispatch falls back to the direct-load kernel for sizes that have no staged form
+    if (regular && c->tune.staged > 0 && !(mode & (MD_PAD | MD_TWO)) && d->frame_len >= n) {
+      // bulk-staged sample loads (MD_STAGED), opt-in: measured 3-9 % SLOWER than the direct loads on B200
+      // (profiles/r2/README.md), kept as a switchable experiment for N = 1024.  16-byte aligned frames, sample type
+      // no wider than the plan's; dispatch falls back to the direct-load kernel for sizes that have no staged form
       const bool aligned = (reinterpret_cast<uintptr_t>(d_samples) % 16) == 0 && ((size_t)d->hop * es) % 16 == 0 && ((size_t)n * es) % 16 == 0;
       if (aligned && es <= esize(pl->precision)) mode |= MD_STAGED;
+    }
+    if (door) {
+      p.door = *door;
+      if (door_used) *door_used = true;
     }
     e = dispatch_r2c(pl->precision == PDSP_F64, pl->log2n - 1, regular ? mode : MD_GENERIC, c->tune.variant, p, lc);
   }
@@ -911,8 +942,9 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
 }
 
 static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
-                      int inverse, cudaStream_t st) {
+                      int inverse, cudaStream_t st, const Doorbell* door, bool* door_used) {
   pdsp_ctx* c = pl->ctx;
+  if (door_used) *door_used = false;
   if (pl->log2n > kMaxLog2M || c->tune.n_big_factors) {
     BigPlan* bp = nullptr;
     if (big_plan(pl, &bp)) return 1;
@@ -926,6 +958,10 @@ static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long lo
   p.out_im = d_oim;
   p.batch = batch;
   p.inverse = inverse;
+  if (door) {
+    p.door = *door;
+    if (door_used) *door_used = true;
+  }
   LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   cudaError_t e = dispatch_c2c(pl->precision == PDSP_F64, pl->log2n, p, lc);
   if (e != cudaSuccess) return fail("c2c launch (n=%d): %s", pl->n, cudaGetErrorString(e));
@@ -1089,6 +1125,8 @@ static long long pick_chunk(const pdsp_ctx* ctx, long long batch, size_t bytes_p
   return c;
 }
 
+static int fast_init(pdsp_ctx* c);
+
 // ------------------------------------------------------------------------------ C ABI
 PDSP_EXPORT int pdsp_abi_version(void) { return PDSP_ABI_VERSION; }
 PDSP_EXPORT const char* pdsp_last_error(void) { return g_err.c_str(); }
@@ -1122,6 +1160,7 @@ PDSP_EXPORT int pdsp_ctx_create(int device, pdsp_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->slots[i].stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming));
   }
+  if (fast_init(c)) return 1;
   *out = c;
   return 0;
 }
@@ -1160,6 +1199,9 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
     cudaEventDestroy(s.done);
     cudaStreamDestroy(s.stream);
   }
+  cudaFreeHost(c->fast.h);
+  cudaFree(c->fast.d_count);
+  if (c->fast.stream) cudaStreamDestroy(c->fast.stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -1181,6 +1223,7 @@ PDSP_EXPORT int pdsp_ctx_tune(pdsp_ctx* c, const char* key, const char* value) {
 PDSP_EXPORT int pdsp_ctx_device(const pdsp_ctx* c) { return c ? c->device : -1; }
 PDSP_EXPORT int pdsp_ctx_sm_count(const pdsp_ctx* c) { return c ? c->sm_count : 0; }
 PDSP_EXPORT int64_t pdsp_ctx_launch_count(const pdsp_ctx* c) { return c ? (int64_t)c->launches.load() : 0; }
+PDSP_EXPORT int64_t pdsp_ctx_fast_call_count(const pdsp_ctx* c) { return c ? (int64_t)c->fast_calls.load() : 0; }
 
 PDSP_EXPORT int pdsp_is_power_of_two(int32_t n) { return n > 0 && (n & (n - 1)) == 0; }
 PDSP_EXPORT int32_t pdsp_next_power_of_two(int32_t n) {
@@ -1371,6 +1414,56 @@ PDSP_EXPORT int pdsp_fft_complex_dev(pdsp_plan* pl, const void* d_re, const void
   return launch_c2c(pl, d_re, d_im, batch, d_ore, d_oim, inverse, st);
 }
 
+// ---- single-call fast lane
+static int fast_init(pdsp_ctx* c) {
+  FastLane& f = c->fast;
+  CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+  void* h = nullptr;
+  CU(cudaHostAlloc(&h, kFastBytes + 256, cudaHostAllocMapped));
+  f.h = static_cast<unsigned char*>(h);
+  void* d = nullptr;
+  CU(cudaHostGetDevicePointer(&d, h, 0));
+  f.d = static_cast<unsigned char*>(d);
+  memset(f.h + kFastBytes, 0, 256);
+  void* cnt = nullptr;
+  CU(cudaMalloc(&cnt, 256));
+  CU(cudaMemset(cnt, 0, 256));
+  f.d_count = static_cast<unsigned*>(cnt);
+  return 0;
+}
+static Doorbell fast_door(pdsp_ctx* c) {
+  FastLane& f = c->fast;
+  ++f.seq;
+  if (f.seq == 0) f.seq = 1;
+  return Doorbell{reinterpret_cast<unsigned*>(f.d + kFastBytes), f.d_count, f.seq};
+}
+// Waits for the launch that carries doorbell `seq` (door_used), or for the lane's stream otherwise.
+static int fast_wait(pdsp_ctx* c, bool door_used) {
+  FastLane& f = c->fast;
+  if (!door_used) {
+    CU(cudaStreamSynchronize(f.stream));
+    return 0;
+  }
+  volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(f.h + kFastBytes);
+  for (unsigned long long spins = 1;; ++spins) {
+    if (*flag == f.seq) break;
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0xffffull) == 0) {
+      // a faulted kernel never rings: let the runtime report it instead of spinning for ever
+      const cudaError_t q = cudaStreamQuery(f.stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return fail("fast lane: %s", cudaGetErrorString(q));
+      if (q == cudaSuccess && *flag != f.seq) {
+        CU(cudaStreamSynchronize(f.stream));  // finished without ringing (should not happen): results are complete anyway
+        break;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return 0;
+}
+
 // ---- host-buffer spectrum: chunked, pipelined over kSlots streams
 PDSP_EXPORT int pdsp_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const void* samples, void* amplitude,
                               void* phase, void* peaks) {
@@ -1386,6 +1479,28 @@ PDSP_EXPORT int pdsp_spectrum(pdsp_plan* pl, const pdsp_spectrum_desc* d, const 
   const size_t pk = pl->precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
   const size_t out_per_frame = (amplitude ? bins * os : 0) + (phase ? bins * os : 0) + (peaks ? pk : 0);
   const size_t in_per_frame = (size_t)(d->hop > 0 ? (d->hop < d->frame_len ? d->hop : d->frame_len) : 0) * es;
+  {
+    // single-call fast lane: the whole job (input span + outputs) fits the mapped buffer and runs as one fused kernel
+    const size_t span = d->frame_len > 0 ? ((size_t)(d->batch - 1) * (size_t)d->hop + (size_t)d->frame_len) * es : 0;
+    const size_t a_bytes = amplitude ? (size_t)d->batch * bins * os : 0, p_bytes = phase ? (size_t)d->batch * bins * os : 0;
+    const size_t k_bytes = peaks ? (size_t)d->batch * pk : 0;
+    const size_t a_off = align256(span), p_off = a_off + align256(a_bytes), k_off = p_off + align256(p_bytes);
+    if (c->tune.fast && n > 1 && pl->log2n - 1 <= kMaxLog2M && !c->tune.n_big_factors && k_off + align256(k_bytes) <= kFastBytes) {
+      FastLane& f = c->fast;
+      if (span) memcpy(f.h, samples, span);
+      const Doorbell door = fast_door(c);
+      bool used = false;
+      if (launch_spectrum(pl, d, f.d, d->batch, amplitude ? f.d + a_off : nullptr, phase ? f.d + p_off : nullptr,
+                          peaks ? f.d + k_off : nullptr, nullptr, nullptr, 0, f.stream, nullptr, &door, &used))
+        return 1;
+      if (fast_wait(c, used)) return 1;
+      if (amplitude) memcpy(amplitude, f.h + a_off, a_bytes);
+      if (phase) memcpy(phase, f.h + p_off, p_bytes);
+      if (peaks) memcpy(peaks, f.h + k_off, k_bytes);
+      c->fast_calls++;
+      return 0;
+    }
+  }
   const long long chunk = pick_chunk(c, d->batch, in_per_frame + out_per_frame);
   const bool src_pinned = samples ? is_device_visible(samples) : true;
   const bool pin[3] = {amplitude ? is_device_visible(amplitude) : true, phase ? is_device_visible(phase) : true,
@@ -1437,6 +1552,39 @@ static int host_transform(pdsp_plan* pl, const void* in_re, const void* in_im, i
   const size_t n = (size_t)pl->n;
   const size_t es = mode == 0 ? esize(in_dtype) : 8;
   const size_t in_per_frame = n * es * (mode == 0 ? 1 : 2);
+  {
+    // single-call fast lane (the reference's primary call shape: one frame in, one ComplexArray out)
+    const size_t plane = (size_t)batch * n * es, oplane = (size_t)batch * n * 8;
+    const size_t im_off = align256(plane), or_off = im_off + (mode != 0 ? align256(plane) : 0), oi_off = or_off + align256(oplane);
+    const bool single_cta_kernel = mode == 0 ? (pl->log2n - 1 <= kMaxLog2M && n > 1) : pl->log2n <= kMaxLog2M;
+    if (c->tune.fast && single_cta_kernel && !c->tune.n_big_factors && oi_off + align256(oplane) <= kFastBytes) {
+      FastLane& f = c->fast;
+      memcpy(f.h, in_re, plane);
+      if (mode != 0) memcpy(f.h + im_off, in_im, plane);
+      const Doorbell door = fast_door(c);
+      bool used = false;
+      int rc;
+      if (mode == 0) {
+        pdsp_spectrum_desc dd;
+        memset(&dd, 0, sizeof dd);
+        dd.sample_dtype = in_dtype;
+        dd.frame_len = pl->n;
+        dd.hop = pl->n;
+        dd.batch = batch;
+        dd.window = PDSP_WIN_RECT;
+        dd.sample_rate = 1.0;
+        rc = launch_spectrum(pl, &dd, f.d, batch, nullptr, nullptr, nullptr, f.d + or_off, f.d + oi_off, 1, f.stream, nullptr, &door, &used);
+      } else {
+        rc = launch_c2c(pl, f.d, f.d + im_off, batch, f.d + or_off, f.d + oi_off, mode == 2, f.stream, &door, &used);
+      }
+      if (rc) return 1;
+      if (fast_wait(c, used)) return 1;
+      memcpy(out_re, f.h + or_off, oplane);
+      memcpy(out_im, f.h + oi_off, oplane);
+      c->fast_calls++;
+      return 0;
+    }
+  }
   const long long chunk = pick_chunk(c, batch, in_per_frame + 16 * n);
   const bool pin_re = is_device_visible(in_re), pin_im = in_im ? is_device_visible(in_im) : true;
   const bool pin[2] = {is_device_visible(out_re), is_device_visible(out_im)};
@@ -1516,9 +1664,34 @@ static int host_elementwise(pdsp_ctx* c, const double* re, const double* im, int
   if (set_device(c)) return 1;
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(c->mu);
+  const size_t bytes = (size_t)n * 8, al = align256(bytes);
+  if (c->tune.fast && 3 * al <= kFastBytes) {
+    // small arrays (the reference calls these on one frame's bins): mapped buffer, one launch, no copy-engine hops
+    FastLane& f = c->fast;
+    memcpy(f.h, re, bytes);
+    if (im) memcpy(f.h + al, im, bytes);
+    long long fb = (n + 255) / 256;
+    if (fb > (long long)c->sm_count * 8) fb = (long long)c->sm_count * 8;
+    const double* f_re = reinterpret_cast<const double*>(f.d);
+    const double* f_im = reinterpret_cast<const double*>(f.d + al);
+    double* f_o = reinterpret_cast<double*>(f.d + 2 * al);
+    if (mag)
+      PDSP_LAUNCH(k_magnitude, (int)fb, 256, 0, f.stream, f_re, f_im, (long long)n, f_o);
+    else if (op == 1)
+      PDSP_LAUNCH(k_phase, (int)fb, 256, 0, f.stream, f_re, f_im, (long long)n, f_o);
+    else if (op == 2)
+      PDSP_LAUNCH(k_apply_window, (int)fb, 256, 0, f.stream, f_re, f_im, (long long)n, f_o);
+    else
+      PDSP_LAUNCH(k_fft_shift, (int)fb, 256, 0, f.stream, f_re, (long long)n, f_o);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaStreamSynchronize(f.stream));
+    memcpy(out, f.h + 2 * al, bytes);
+    c->fast_calls++;
+    return 0;
+  }
   Slot& s = c->slots[0];
   if (slot_wait(s)) return 1;
-  const size_t bytes = (size_t)n * 8, al = align256(bytes);
   if (ensure(&s.d_in, &s.d_in_cap, 2 * al, false)) return 1;
   if (ensure(&s.d_out, &s.d_out_cap, al, false)) return 1;
   char* din = static_cast<char*>(s.d_in);
@@ -1617,6 +1790,89 @@ PDSP_EXPORT int pdsp_memcpy_d2h(pdsp_ctx* c, void* h, const void* d, size_t byte
   return 0;
 }
 
+// ------------------------------------------------------------------------------ host copy pool
+// Row-wise memcpy split over a few persistent threads: the ingestion ring moves every frame through pinned memory
+// (4-8 KB in, 2-8 KB out per frame), and one thread's ~10 GB/s was the ring's bound (profiles/r1: 1.5e6 frames/s).
+// Workers spin briefly after a job (a streaming source pushes back to back) and then sleep on a condition variable.
+struct CopyPool {
+  struct Job {
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t rows = 0, row_bytes = 0, dst_stride = 0, src_stride = 0;
+  };
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  Job job;
+  std::atomic<unsigned> generation{0};
+  std::atomic<int> remaining{0};
+  std::atomic<bool> stop{false};
+  int parts = 1;
+
+  static void copy_part(const Job& j, int part, int parts) {
+    const size_t r0 = j.rows * (size_t)part / (size_t)parts, r1 = j.rows * (size_t)(part + 1) / (size_t)parts;
+    if (j.dst_stride == j.row_bytes && j.src_stride == j.row_bytes) {
+      memcpy(j.dst + r0 * j.row_bytes, j.src + r0 * j.row_bytes, (r1 - r0) * j.row_bytes);
+    } else {
+      for (size_t r = r0; r < r1; ++r) memcpy(j.dst + r * j.dst_stride, j.src + r * j.src_stride, j.row_bytes);
+    }
+  }
+  void worker(int idx) {
+    unsigned seen = 0;
+    for (;;) {
+      // wait for a new generation: spin for a while, then block
+      int spins = 0;
+      while (generation.load(std::memory_order_acquire) == seen && !stop.load()) {
+        if (++spins < 20000) {
+#if defined(__x86_64__) || defined(__i386__)
+          __builtin_ia32_pause();
+#endif
+          continue;
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return generation.load() != seen || stop.load(); });
+      }
+      if (stop.load()) return;
+      seen = generation.load(std::memory_order_acquire);
+      copy_part(job, idx + 1, parts);
+      remaining.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+  void start(int n_workers) {
+    parts = n_workers + 1;
+    for (int i = 0; i < n_workers; ++i) workers.emplace_back([this, i] { worker(i); });
+  }
+  // rows x row_bytes from src (row stride src_stride) to dst (row stride dst_stride); the caller copies part 0
+  void run(void* dst, const void* src, size_t rows, size_t row_bytes, size_t dst_stride, size_t src_stride) {
+    Job j{static_cast<char*>(dst), static_cast<const char*>(src), rows, row_bytes, dst_stride, src_stride};
+    if (workers.empty() || rows * row_bytes < (256u << 10) || rows < (size_t)parts) {
+      copy_part(j, 0, 1);
+      return;
+    }
+    job = j;
+    remaining.store((int)workers.size(), std::memory_order_release);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      generation.fetch_add(1, std::memory_order_acq_rel);
+    }
+    cv.notify_all();
+    copy_part(j, 0, parts);
+    while (remaining.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop.store(true);
+    }
+    cv.notify_all();
+    for (auto& t : workers) t.join();
+  }
+};
+
 // ------------------------------------------------------------------------------ ingestion ring
 // spectrumStream (src/effect/index.ts:190-194) maps a stream of frames 1:1, in order.  The ring turns that into
 // batched launches without the caller assembling batches: frames are copied into a pinned chunk as they arrive;
@@ -1632,6 +1888,7 @@ struct IngestChunk {
   long long frames = 0;   // frames copied in so far
   long long popped = 0;   // frames already handed back
   bool in_flight = false;
+  bool direct = false;    // frames reached d_in by DMA from caller-pinned memory (pdsp_ingest_push_pinned)
 };
 struct pdsp_ingest {
   pdsp_plan* plan = nullptr;
@@ -1644,11 +1901,12 @@ struct pdsp_ingest {
   int fill = 0;  // chunk receiving frames
   int head = 0;  // oldest chunk with results not yet handed back
   std::mutex mu;
+  CopyPool pool;  // host copies of push / pop (PDSP_COPY_THREADS helper threads, default 3)
 };
 
 static int ingest_submit(pdsp_ingest* g, IngestChunk& ch) {
   if (ch.frames == 0 || ch.in_flight) return 0;
-  CU(cudaMemcpyAsync(ch.d_in, ch.h_in, (size_t)ch.frames * g->in_frame, cudaMemcpyHostToDevice, ch.stream));
+  if (!ch.direct) CU(cudaMemcpyAsync(ch.d_in, ch.h_in, (size_t)ch.frames * g->in_frame, cudaMemcpyHostToDevice, ch.stream));
   pdsp_spectrum_desc d = g->desc;
   d.batch = ch.frames;
   char* dout = static_cast<char*>(ch.d_out);
@@ -1712,6 +1970,13 @@ PDSP_EXPORT int pdsp_ingest_open(pdsp_plan* pl, const pdsp_spectrum_desc* d, int
     pdsp_ingest_close(g);
     return 1;
   }
+  {
+    int helpers = pl->ctx->tune.copy_threads;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (helpers > hw - 1) helpers = hw - 1;
+    if (helpers > 15) helpers = 15;
+    if (helpers > 0) g->pool.start(helpers);
+  }
   *out = g;
   return 0;
 }
@@ -1736,7 +2001,10 @@ PDSP_EXPORT int pdsp_ingest_close(pdsp_ingest* g) {
 // Copies `count` frames (frame_len samples each, `stride` samples apart; 0 = frame_len) into the ring, sending
 // every chunk that fills up.  *accepted is how many were taken: fewer than `count` means the ring is full -
 // the next chunk still holds results the caller has not collected with pdsp_ingest_pop.
-PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t count, int64_t stride, int64_t* accepted) {
+// pinned != 0 (pdsp_ingest_push_pinned): `frames` is pinned / registered host memory and is NOT copied - each run of
+// frames is sent to the device by DMA straight from the caller's buffer, which must stay unchanged until those frames
+// have been popped.
+static int ingest_push_impl(pdsp_ingest* g, const void* frames, int64_t count, int64_t stride, int64_t* accepted, int pinned) {
   if (!g || (!frames && count > 0)) return fail("null argument");
   if (count < 0 || stride < 0) return fail("negative count or stride");
   if (accepted) *accepted = 0;
@@ -1744,6 +2012,7 @@ PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t cou
   std::lock_guard<std::mutex> lk(g->mu);
   const size_t es = esize(g->desc.sample_dtype);
   const size_t step = (size_t)(stride ? stride : g->desc.frame_len) * es;
+  if (pinned && count > 0 && !is_device_visible(frames)) return fail("pdsp_ingest_push_pinned needs pinned (page-locked) host memory");
   const char* src = static_cast<const char*>(frames);
   int64_t done = 0;
   while (done < count) {
@@ -1751,11 +2020,19 @@ PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t cou
     if (ch.in_flight) break;  // ring full
     long long take = g->cap - ch.frames;
     if (take > count - done) take = count - done;
-    char* dst = static_cast<char*>(ch.h_in) + (size_t)ch.frames * g->in_frame;
-    if (step == g->in_frame) {
-      memcpy(dst, src, (size_t)take * g->in_frame);
+    if (pinned) {
+      // DMA from the caller's memory into the chunk's device buffer (the chunk's host staging is bypassed)
+      char* ddst = static_cast<char*>(ch.d_in) + (size_t)ch.frames * g->in_frame;
+      if (step == g->in_frame) {
+        CU(cudaMemcpyAsync(ddst, src, (size_t)take * g->in_frame, cudaMemcpyHostToDevice, ch.stream));
+      } else {
+        CU(cudaMemcpy2DAsync(ddst, g->in_frame, src, step, g->in_frame, (size_t)take, cudaMemcpyHostToDevice, ch.stream));
+      }
+      ch.direct = true;
     } else {
-      for (long long i = 0; i < take; ++i) memcpy(dst + (size_t)i * g->in_frame, src + (size_t)i * step, g->in_frame);
+      char* dst = static_cast<char*>(ch.h_in) + (size_t)ch.frames * g->in_frame;
+      g->pool.run(dst, src, (size_t)take, g->in_frame, g->in_frame, step);
+      if (ch.direct) return fail("one chunk cannot mix copied and pinned pushes: flush between them");
     }
     ch.frames += take;
     done += take;
@@ -1766,6 +2043,46 @@ PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t cou
     }
   }
   if (accepted) *accepted = done;
+  return 0;
+}
+PDSP_EXPORT int pdsp_ingest_push(pdsp_ingest* g, const void* frames, int64_t count, int64_t stride, int64_t* accepted) {
+  return ingest_push_impl(g, frames, count, stride, accepted, 0);
+}
+PDSP_EXPORT int pdsp_ingest_push_pinned(pdsp_ingest* g, const void* frames, int64_t count, int64_t stride, int64_t* accepted) {
+  return ingest_push_impl(g, frames, count, stride, accepted, 1);
+}
+
+// Non-blocking progress report: frames whose results can be popped without waiting (`finished`: the leading run of
+// completed chunks), frames sent and still in flight, frames sitting in the partially filled chunk (not sent yet).
+PDSP_EXPORT int pdsp_ingest_ready(pdsp_ingest* g, int64_t* finished, int64_t* in_flight, int64_t* pending) {
+  if (!g) return fail("null argument");
+  if (set_device(g->plan->ctx)) return 1;
+  std::lock_guard<std::mutex> lk(g->mu);
+  int64_t fin = 0, fly = 0;
+  bool leading = true;
+  const int nch = (int)g->chunks.size();
+  for (int i = 0; i < nch; ++i) {
+    IngestChunk& ch = g->chunks[(size_t)((g->head + i) % nch)];
+    if (!ch.in_flight) break;
+    bool complete = false;
+    if (leading) {
+      const cudaError_t q = cudaEventQuery(ch.done);
+      if (q == cudaSuccess)
+        complete = true;
+      else if (q != cudaErrorNotReady)
+        return fail("cudaEventQuery: %s", cudaGetErrorString(q));
+    }
+    if (complete) {
+      fin += ch.frames - ch.popped;
+    } else {
+      leading = false;
+      fly += ch.frames - ch.popped;
+    }
+  }
+  const IngestChunk& fc = g->chunks[(size_t)g->fill];
+  if (finished) *finished = fin;
+  if (in_flight) *in_flight = fly;
+  if (pending) *pending = fc.in_flight ? 0 : fc.frames;
   return 0;
 }
 
@@ -1799,15 +2116,18 @@ PDSP_EXPORT int pdsp_ingest_pop(pdsp_ingest* g, void* amplitude, void* phase, vo
     if (take > max_frames - n) take = max_frames - n;
     const char* hout = static_cast<const char*>(ch.h_out);
     if (amplitude && g->want_amp)
-      memcpy(static_cast<char*>(amplitude) + (size_t)n * g->row, hout + g->a_off + (size_t)ch.popped * g->row, (size_t)take * g->row);
+      g->pool.run(static_cast<char*>(amplitude) + (size_t)n * g->row, hout + g->a_off + (size_t)ch.popped * g->row, (size_t)take,
+                  g->row, g->row, g->row);
     if (phase && g->want_phase)
-      memcpy(static_cast<char*>(phase) + (size_t)n * g->row, hout + g->p_off + (size_t)ch.popped * g->row, (size_t)take * g->row);
+      g->pool.run(static_cast<char*>(phase) + (size_t)n * g->row, hout + g->p_off + (size_t)ch.popped * g->row, (size_t)take, g->row,
+                  g->row, g->row);
     if (peaks && g->want_peaks)
       memcpy(static_cast<char*>(peaks) + (size_t)n * g->pk, hout + g->k_off + (size_t)ch.popped * g->pk, (size_t)take * g->pk);
     ch.popped += take;
     n += take;
     if (ch.popped == ch.frames) {
       ch.in_flight = false;
+      ch.direct = false;
       ch.frames = ch.popped = 0;
       g->head = (g->head + 1) % (int)g->chunks.size();
     }

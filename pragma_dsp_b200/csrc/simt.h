@@ -91,6 +91,11 @@ PDSP_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::c
 PDSP_DEVICE void prefetch_l2_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// completion doorbell (low-latency host entry points): the last CTA to finish writes a sequence number into
+// host-mapped pinned memory; the host spins on it instead of going through a stream synchronisation
+PDSP_DEVICE void fence_system() { __threadfence_system(); }
+PDSP_DEVICE unsigned atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+PDSP_DEVICE void store_volatile(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
 PDSP_DEVICE unsigned char* smem() {
   extern __shared__ __align__(16) unsigned char pdsp_smem_[];
   return pdsp_smem_;
@@ -193,6 +198,9 @@ inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over 
   for (int m = 16; m >= 1; m >>= 1) acc |= shfl_xor(acc, m, 32);
   return acc != 0;
 }
+inline void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomic_add(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void store_volatile(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned char* smem() { return emu_self.smem; }
 template <typename T>
 inline T ldg(const T* p) {

@@ -88,12 +88,24 @@ def spectrumFx(samples, options: dict | None = None) -> Callable[[FourierService
 
 
 def spectrumStream(frames: Iterable, options: dict | None = None, *, service: FourierService | None = None,
-                   chunk: int = 4096) -> Iterator[dict]:
+                   chunk: int = 1024, lockstep: bool = False) -> Iterator[dict]:
     """src/effect/index.ts:190-194 - ordered 1:1 map over a stream of (Float32Array) frames.
 
-    Frames go through the ingestion ring (pdsp_ingest_*): each is copied into a pinned chunk as it arrives, a
-    full chunk of `chunk` frames is transformed on its own stream while the next one fills, and results are
-    yielded in arrival order.  A frame of a different length or dtype drains the ring and opens a new one."""
+    Batching contract.  Frames go through the ingestion ring (pdsp_ingest_*): each is copied into a pinned chunk as it
+    arrives and results are yielded in arrival order, one per frame.  Chunks are cut ADAPTIVELY, not by a fixed size:
+
+    * before the next frame is pulled from the source, every result that is already finished is yielded (a
+      non-blocking poll, pdsp_ingest_ready);
+    * whenever no chunk is in flight (the GPU is idle), the frames pushed so far are sent at once - a slow source
+      (microphone, websocket) sees its result after one small launch, not after `chunk` frames;
+    * while a chunk is in flight, arriving frames accumulate (up to `chunk`) and go out together when it completes - a
+      fast source fills whole chunks and the copies overlap the kernels.
+
+    So the latency of a result is bounded by one launch of at most `chunk` frames plus the time the source takes to
+    yield the next frame.  A source that needs result i before it can produce frame i+1 (feedback) must pass
+    lockstep=True: every frame is then sent and its result yielded before the next one is pulled - the reference's
+    strictly sequential `Stream.mapEffect` behaviour, at one launch per frame.
+    A frame of a different length or dtype drains the ring and opens a new one."""
     from ..public.ingest import IngestRing
     opts = dict(options or {})
     svc = service or FourierService()
@@ -101,17 +113,17 @@ def spectrumStream(frames: Iterable, options: dict | None = None, *, service: Fo
     key = None
     pending = 0  # frames pushed and not yet yielded
 
-    def drain(r, n_wait):
-        """Yield finished frames; n_wait > 0 insists on at least that many (the ring is full or the stream ended)."""
+    def take(r, n):
+        """Yield n finished-or-in-flight frames (pop blocks only on chunks already sent)."""
         nonlocal pending
-        while n_wait > 0 and pending > 0:
-            out = r.pop(min(pending, chunk))
+        while n > 0 and pending > 0:
+            out = r.pop(min(n, pending, chunk))
             if out["count"] == 0:
                 break
             for i in range(out["count"]):
                 yield _result(out, i)
             pending -= out["count"]
-            n_wait -= out["count"]
+            n -= out["count"]
 
     for frame in frames:
         f = np.asarray(frame)
@@ -120,7 +132,7 @@ def spectrumStream(frames: Iterable, options: dict | None = None, *, service: Fo
         k = (f.shape, f.dtype)
         if ring is not None and k != key:
             ring.flush()
-            yield from drain(ring, pending)
+            yield from take(ring, pending)
             ring.close()
             ring = None
         if f.size == 0:  # spectrum([]) is a one-bin result; not worth a ring
@@ -136,11 +148,20 @@ def spectrumStream(frames: Iterable, options: dict | None = None, *, service: Fo
                               depth=3, context=svc._ctx)
             key = k
         while ring.push(f) == 0:  # ring full: hand back the oldest chunk, then retry
-            yield from drain(ring, 1)
+            yield from take(ring, 1)
         pending += 1
+        if lockstep:
+            ring.flush()
+            yield from take(ring, pending)
+            continue
+        finished, in_flight, waiting = ring.ready()
+        if in_flight == 0 and waiting > 0:  # nothing to overlap with: send what has arrived
+            ring.flush()
+        if finished:
+            yield from take(ring, finished)
     if ring is not None:
         ring.flush()
-        yield from drain(ring, pending)
+        yield from take(ring, pending)
         ring.close()
 
 

@@ -56,6 +56,24 @@ class IngestRing:
         check(lib().pdsp_ingest_push(self._h, x.ctypes.data_as(C.c_void_p), x.shape[0], 0, C.byref(acc)))
         return int(acc.value)
 
+    def push_pinned(self, frames) -> int:
+        """As push() for frames that live in pinned host memory (pdsp_host_alloc): no host copy - the device reads them
+        by DMA after this call returns, so they must stay unchanged until popped."""
+        x = np.asarray(frames)
+        if x.dtype != self.sample_dtype or not x.flags.c_contiguous:
+            raise ValueError("push_pinned needs a contiguous array of the ring's sample dtype (it is not copied)")
+        x = x.reshape(-1, self.frameLen)
+        acc = C.c_int64(0)
+        check(lib().pdsp_ingest_push_pinned(self._h, x.ctypes.data_as(C.c_void_p), x.shape[0], 0, C.byref(acc)))
+        return int(acc.value)
+
+    def ready(self) -> tuple[int, int, int]:
+        """(finished, in_flight, pending) frames, without blocking: what pop() would return at once, what was sent and
+        is still being processed, what sits in the partially filled chunk."""
+        fin, fly, pend = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib().pdsp_ingest_ready(self._h, C.byref(fin), C.byref(fly), C.byref(pend)))
+        return int(fin.value), int(fly.value), int(pend.value)
+
     def flush(self) -> None:
         check(lib().pdsp_ingest_flush(self._h))
 
@@ -70,6 +88,26 @@ class IngestRing:
         k = int(got.value)
         return {"frequencies": self.frequencies, "amplitude": None if amp is None else amp[:k],
                 "phase": None if ph is None else ph[:k], "peaks": None if pk is None else pk[:k], "count": k}
+
+    def pop_into(self, amplitude=None, phase=None, peaks=None, max_frames: int | None = None) -> int:
+        """pop() into caller-owned arrays (rows appended densely from row 0): no allocation per call - what a steady
+        stream should use.  Arrays must be C-contiguous, of the plan precision / peak dtype, with room for max_frames."""
+        cap = []
+        for a, dt, name in ((amplitude, self._dt, "amplitude"), (phase, self._dt, "phase"), (peaks, self._pk, "peaks")):
+            if a is None:
+                continue
+            if a.dtype != dt or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"{name} must be a writeable contiguous array of dtype {np.dtype(dt)}")
+            cap.append(a.shape[0])
+        if not cap:
+            raise ValueError("no output array given")
+        n = min(cap) if max_frames is None else int(max_frames)
+        if n > min(cap):
+            raise ValueError("max_frames exceeds the room in the output arrays")
+        got = C.c_int64(0)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(lib().pdsp_ingest_pop(self._h, p(amplitude), p(phase), p(peaks), n, C.byref(got)))
+        return int(got.value)
 
     def close(self) -> None:
         if self._h:

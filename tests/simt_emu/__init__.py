@@ -23,12 +23,14 @@ class R2CParams(C.Structure):
                 ("post", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p), ("cfull", C.c_int),
                 ("amp", C.c_void_p), ("phase", C.c_void_p), ("peaks", C.c_void_p), ("two_sided", C.c_int), ("shift", C.c_int),
                 ("scale_edge", C.c_double), ("scale_mid", C.c_double), ("bin_hz", C.c_double),
-                ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong)]
+                ("peer", C.c_void_p * 8), ("n_peers", C.c_int), ("peer_offset", C.c_longlong),
+                ("door_flag", C.c_void_p), ("door_count", C.c_void_p), ("door_seq", C.c_uint)]
 
 
 class C2CParams(C.Structure):
     _fields_ = [("in_re", C.c_void_p), ("in_im", C.c_void_p), ("out_re", C.c_void_p), ("out_im", C.c_void_p),
-                ("batch", C.c_longlong), ("tw", C.c_void_p), ("inverse", C.c_int)]
+                ("batch", C.c_longlong), ("tw", C.c_void_p), ("inverse", C.c_int),
+                ("door_flag", C.c_void_p), ("door_count", C.c_void_p), ("door_seq", C.c_uint)]
 
 
 PEAK64 = np.dtype([("index", "<i4"), ("_pad", "<i4"), ("frequency", "<f8"), ("amplitude", "<f8"), ("phase", "<f8")])

@@ -12,6 +12,7 @@ typedef enum {
   cudaSuccess = 0,
   cudaErrorInvalidValue = 1,
   cudaErrorInvalidDevice = 101,
+  cudaErrorNotReady = 600,
   cudaErrorLaunchOutOfResources = 701
 } cudaError_t;
 typedef struct pdsp_stub_stream* cudaStream_t;
@@ -24,7 +25,7 @@ struct cudaPointerAttributes {
   cudaMemoryType type;
 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 cudaError_t cudaGetDeviceCount(int* n);
@@ -37,8 +38,14 @@ cudaError_t cudaMalloc(void** p, size_t bytes);
 cudaError_t cudaFree(void* p);
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned flags);
 cudaError_t cudaFreeHost(void* p);
+cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned flags);
+cudaError_t cudaMemset(void* p, int value, size_t bytes);
+cudaError_t cudaStreamQuery(cudaStream_t s);
+cudaError_t cudaEventQuery(cudaEvent_t e);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
+                              cudaStream_t s);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);

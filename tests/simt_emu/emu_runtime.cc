@@ -184,6 +184,16 @@ cudaError_t cudaFreeHost(void* p) {
   free(p);
   return cudaSuccess;
 }
+cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) {
+  *d = h;
+  return cudaSuccess;
+}
+cudaError_t cudaMemset(void* p, int value, size_t bytes) {
+  memset(p, value, bytes);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
   if (kind == cudaMemcpyHostToDevice) ++g_h2d;
   if (kind == cudaMemcpyDeviceToHost) ++g_d2h;
@@ -192,6 +202,13 @@ cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind 
 }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t) {
   return cudaMemcpy(dst, src, bytes, kind);
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
+                              cudaStream_t) {
+  if (kind == cudaMemcpyHostToDevice) ++g_h2d;
+  if (kind == cudaMemcpyDeviceToHost) ++g_d2h;
+  for (size_t r = 0; r < height; ++r) memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+  return cudaSuccess;
 }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   *s = reinterpret_cast<cudaStream_t>(malloc(1));

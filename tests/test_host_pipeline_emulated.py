@@ -307,6 +307,119 @@ def test_ingestion_ring_emulated(emu_api):
         IngestRing(n, depth=1)
 
 
+def test_ring_pinned_push_ready_and_threaded_copies_emulated(emu_api, tune):
+    """Round-2 ring features: pdsp_ingest_push_pinned (no host copy: the H2D count stays flat while frames are taken),
+    pdsp_ingest_ready (non-blocking progress), pop_into caller-owned arrays, the host copy pool on large pushes, and a
+    chunk refusing to mix copied and pinned frames."""
+    from pragma_dsp_b200 import IngestRing, spectrum_batch
+    L = emu_api.lib()
+    ctx = emu_api.default_context()
+    rng = np.random.default_rng(31)
+    n, total = 1024, 96
+    x = multitone(rng, total, n, np.float32)
+    ref = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann", outputs=("amplitude", "peak"))
+    # pinned source: allocate through the library, view as numpy
+    hp = C.c_void_p()
+    assert L.pdsp_host_alloc(ctx.h, x.nbytes, C.byref(hp)) == 0
+    xp = np.ctypeslib.as_array((C.c_float * x.size).from_address(hp.value)).reshape(x.shape)
+    xp[:] = x
+    amp = np.empty((total, n // 2 + 1))
+    pk = np.zeros(total, dtype=emu_api.PEAK_F64)
+    with IngestRing(n, sampleRate=48000.0, window="hann", sample_dtype=np.float32, outputs=("amplitude", "peak"),
+                    framesPerChunk=32, depth=3) as ring:
+        assert ring.ready() == (0, 0, 0)
+        assert ring.push_pinned(xp[:40]) == 40          # one full chunk sent, 8 frames waiting
+        fin, fly, pend = ring.ready()
+        assert fin + fly == 32 and pend == 8
+        with pytest.raises(Exception, match="mix"):
+            ring.push(x[40:41])                          # a copied frame into the chunk that holds pinned ones
+        assert ring.push_pinned(xp[40:]) == 56
+        ring.flush()
+        got = 0
+        while got < total:
+            k = ring.pop_into(amp[got:], None, pk[got:], max_frames=min(50, total - got))
+            assert k > 0
+            got += k
+        assert ring.ready() == (0, 0, 0)
+        with pytest.raises(ValueError):
+            ring.pop_into(amp.astype(np.float32))
+        with pytest.raises(Exception, match="pinned"):
+            ring.push_pinned(x[:1])                      # pageable memory is refused, not silently copied
+    assert np.array_equal(amp, ref["amplitude"]) and (pk == ref["peaks"]).all()
+    L.pdsp_host_free(ctx.h, hp)
+    # threaded host copies: pushes of 1 MB and more are split over the pool's threads (copy_threads tunable)
+    for threads in (0, 3):
+        tune("copy_threads", threads)
+        with IngestRing(n, sampleRate=48000.0, window="hann", sample_dtype=np.float32, outputs=("amplitude", "peak"),
+                        framesPerChunk=96, depth=2) as ring:
+            assert ring.push(np.tile(x, (1, 1))) == total and ring.ready()[0] + ring.ready()[1] == total
+            out = ring.pop(total)
+        assert out["count"] == total and np.array_equal(out["amplitude"], ref["amplitude"])
+
+
+def test_spectrum_stream_latency_contract_emulated(emu_api):
+    """spectrumStream must not sit on results.  With an idle ring every frame is sent as soon as it arrives,
+    so a lazy source sees result i before it is asked for frame i + 2 at the latest; lockstep=True gives the reference's
+    strict one-in-one-out order (a source that depends on the previous result does not deadlock)."""
+    from pragma_dsp_b200.effect import FourierLive, spectrumStream
+    rng = np.random.default_rng(41)
+    n = 1024  # a size the emulated library instantiates
+    x = multitone(rng, 12, n, np.float32)
+    svc = FourierLive()
+    produced, consumed = [], []
+
+    def source():
+        for i in range(12):
+            produced.append(i)
+            yield x[i]
+
+    for r in spectrumStream(source(), {"sampleRate": 8000.0}, service=svc, chunk=64):
+        consumed.append(len(produced))                  # frames the source had produced when result len(consumed)-1 came out
+    assert len(consumed) == 12
+    assert all(c - i <= 2 for i, c in enumerate(consumed)), consumed   # never `chunk` frames behind
+    # feedback source: frame i+1 is only produced after result i was seen
+    seen = []
+
+    def feedback():
+        for i in range(6):
+            assert len(seen) == i, "the stream asked for frame %d before yielding result %d" % (i, i - 1)
+            yield x[i]
+
+    for r in spectrumStream(feedback(), {"sampleRate": 8000.0}, service=svc, lockstep=True):
+        seen.append(r["peak"]["index"])
+    ref = [oracle.spectrum(x[i], sampleRate=8000.0)["peak"]["index"] for i in range(6)]
+    assert seen == ref
+
+
+def test_single_call_fast_lane_emulated(emu_api, tune):
+    """one-frame calls (Radix2Fft.forward, spectrum()) take the fast lane - one launch through the
+    host-mapped buffer, no staging slots - and give the same bits as the pipeline; jobs beyond 256 KB do not."""
+    from pragma_dsp_b200 import spectrum_batch
+    from pragma_dsp_b200.core import ComplexArray, Radix2Fft
+    ctx = emu_api.default_context()
+    rng = np.random.default_rng(51)
+    n = 1024
+    x = multitone(rng, 3, n)
+    f0, h0 = ctx.fast_call_count, emu_api.lib().pdsp_stub_counter(0)
+    fft = Radix2Fft(n)
+    a = fft.forward(x[0])
+    b = fft.inverse(fft.forwardComplex(ComplexArray(x[1], x[2])))
+    s = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann")
+    assert ctx.fast_call_count == f0 + 4 and emu_api.lib().pdsp_stub_counter(0) == h0   # no H2D copy calls at all
+    assert np.abs(b.real - x[1]).max() <= 1e-12 and np.abs(b.imag - x[2]).max() <= 1e-12
+    tune("fast", 0)
+    a2 = fft.forward(x[0])
+    s2 = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann")
+    assert ctx.fast_call_count == f0 + 4
+    assert np.array_equal(a.real, a2.real) and np.array_equal(a.imag, a2.imag)
+    assert np.array_equal(s["amplitude"], s2["amplitude"]) and np.array_equal(s["phase"], s2["phase"]) and (s["peaks"] == s2["peaks"]).all()
+    tune("fast", 1)
+    big = multitone(rng, 40, n)                           # 40 x (8 KB in + 8 KB out) > 256 KB: the staging pipeline
+    f1 = ctx.fast_call_count
+    spectrum_batch(big, sampleRate=48000.0, fftSize=n)
+    assert ctx.fast_call_count == f1
+
+
 def test_fused_peer_scatter_emulated(emu_api):
     """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
     from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
