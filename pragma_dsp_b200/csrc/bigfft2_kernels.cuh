@@ -1,0 +1,203 @@
+// bigfft2_kernels.cuh - K2, second generation: one pass of the multi-pass large-N FFT (N > 8192 complex points;
+// BASELINE config C4: N = 2^20, 2^24) with TMA on BOTH sides of the tile.
+//
+// N = L1*L2(*L3) as in bigfft_kernels.cuh.  A pass transforms the axis of length L of a 3-D view of the data; a CTA works
+// on a tile of C adjacent sequences:
+//
+//   * column passes (every pass but the last): the tile is C adjacent columns of the view [O][L][I] - fetched by
+//     cp.async.bulk.tensor box loads into shared memory, transformed in place (the landing zone is also the exchange
+//     buffer of the Stockham engine), multiplied by the Cooley-Tukey twiddle, written back to shared memory in tile
+//     order and sent to global memory by cp.async.bulk.tensor box STORES (SASS UTMASTG);
+//   * the last pass reads C contiguous rows with coalesced per-thread loads (its input was just written by the previous
+//     pass: L2 hits) and writes its output TRANSPOSED (digit-reversed: X[k1 + L1*k2 (+ L1*L2*k3)]) with the same box
+//     stores - the transpose of the four-step algorithm is a TMA store of a {C, rows} box, not a scatter of C*8-byte
+//     segments from the LSU.
+//
+// Global traffic no longer passes through the LSU (the first generation spent 2/7 of its L1 wavefronts on it); tiles are
+// half the size of the first generation's (C = 4 for L = 1024, 16 for L = 256), so that TWO CTAs share an SM and the
+// memory phases of one overlap the arithmetic of the other; stores drain asynchronously while the CTA loads its next
+// tile.  The reference runs the same transform as log2(N) strided in-place sweeps (/root/reference/src/core/fft.ts:116-140).
+#pragma once
+#include "bigfft_kernels.cuh"
+
+namespace pdsp {
+
+struct BigTileParams {
+  long long n_groups;  // tiles per transform; group g = g_hi * n_lo + g_lo
+  long long n_lo;
+  long long n_frames;  // transforms in this launch (work item = frame * n_groups + g)
+  // TMA coordinates of a tile's first box: coord[d] = g_lo * c_lo[d] + g_hi * c_hi[d] + frame * c_fr[d]; successive
+  // boxes of the tile advance dimension box_dim by box_step
+  int in_lo[3], in_hi[3], in_fr[3], in_box_dim, in_box_step, in_boxes;
+  int out_lo[3], out_hi[3], out_fr[3], out_box_dim, out_box_step, out_boxes;
+  unsigned in_box_bytes, out_box_bytes;  // bytes one box moves (per plane)
+  // last pass only: per-thread staged row loads (element strides as in BigPassParams)
+  const void* in_re;
+  const void* in_im;
+  long long in_frame, in_g_hi, in_g_lo, in_c;
+  const void* tw;     // per-pass twiddles of the L-point schedule (set by the launcher)
+  const void* tw_hi;  // two-level inter-pass twiddle, null on the last pass
+  const void* tw_lo;
+  int log_b;
+  int swap_in, swap_out;  // inverse transform = swap(FFT(swap(x))) / N
+  double scale;
+  int has_im;  // planar input with an imaginary plane (0: real input, zeros)
+};
+
+// IO bit 0: input is the interleaved work buffer; bit 1: output is; bit 2: last pass (row tile in, transposed box out)
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
+    bigfft_tile_kernel(const BigTileParams p, const PDSP_GRID_CONSTANT simt::TensorMap tm_in_re,
+                       const PDSP_GRID_CONSTANT simt::TensorMap tm_in_im, const PDSP_GRID_CONSTANT simt::TensorMap tm_out_re,
+                       const PDSP_GRID_CONSTANT simt::TensorMap tm_out_im) {
+  constexpr bool IN_CPLX = (IO & 1) != 0, OUT_CPLX = (IO & 2) != 0, LAST = (IO & 4) != 0;
+  using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
+  constexpr int L = E::M, P = E::P, TF = E::TF;
+  constexpr int THREADS = TF * C;
+  constexpr int SLOT = E::SMEM_ELEMS | 1;  // odd stride: neighbouring sequences start in neighbouring banks
+  constexpr size_t PLANE = sizeof(T) * (size_t)L * C;
+  const int tid = simt::tid();
+  const int c = tid % C;
+  const int t = tid / C;
+  // one 128-byte aligned region: landing zone of the tile, exchange buffer, staging of the outgoing tile
+  unsigned char* base = simt::smem();
+  base += (128 - (reinterpret_cast<uintptr_t>(base) & 127)) & 127;
+  cx<T>* smem = reinterpret_cast<cx<T>*>(base);
+  cx<T>* sm = smem + (size_t)c * SLOT;
+  constexpr size_t REGION = sizeof(cx<T>) * (size_t)SLOT * C > 2 * PLANE ? sizeof(cx<T>) * (size_t)SLOT * C : 2 * PLANE;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + ((REGION + 15) & ~(size_t)15));
+  const T scale = (T)p.scale;
+  const long long total = p.n_groups * p.n_frames;
+  if (tid == 0) simt::mbar_init(bar, 1);
+  simt::sync_block();
+  unsigned phase = 0u;
+
+  for (long long w = simt::bid(); w < total; w += simt::nblocks()) {
+    const long long fb = w / p.n_groups, g = w % p.n_groups;
+    const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
+    cx<T> v[P];
+    if constexpr (!LAST) {
+      // ---- tile in: TMA box loads into the (free) region.  The previous item's stores must have finished READING it.
+      if (tid == 0) {
+        simt::bulk_wait_read();
+        simt::fence_proxy_async();
+        int co[3];
+        for (int d = 0; d < 3; ++d) co[d] = (int)(g_lo * p.in_lo[d] + g_hi * p.in_hi[d] + fb * p.in_fr[d]);
+        const int planes = IN_CPLX ? 1 : (p.has_im ? 2 : 1);
+        simt::mbar_expect_tx(bar, (unsigned)planes * p.in_box_bytes * (unsigned)p.in_boxes);
+        for (int j = 0; j < p.in_boxes; ++j) {
+          simt::tma_load_3d(base + (size_t)j * p.in_box_bytes, &tm_in_re, co[0], co[1], co[2], bar);
+          if (!IN_CPLX && p.has_im) simt::tma_load_3d(base + PLANE + (size_t)j * p.in_box_bytes, &tm_in_im, co[0], co[1], co[2], bar);
+          co[p.in_box_dim] += p.in_box_step;
+        }
+      }
+      simt::mbar_wait(bar, phase);
+      phase ^= 1u;
+      const T* tre = reinterpret_cast<const T*>(base);
+      const T* tim = reinterpret_cast<const T*>(base + PLANE);
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        const int e = t + TF * q;
+        if constexpr (IN_CPLX) {
+          v[q] = reinterpret_cast<const cx<T>*>(tre)[e * C + c];
+        } else {
+          const T re = tre[e * C + c];
+          const T im = p.has_im ? tim[e * C + c] : (T)0;
+          v[q] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        }
+      });
+      simt::sync_block();  // tile consumed: the exchanges may overwrite it
+    } else {
+      // ---- last pass: C contiguous rows, element index fastest across the CTA, parked in the padded exchange layout.
+      // (the region may still be read by the previous item's stores)
+      if (tid == 0) simt::bulk_wait_read();
+      simt::sync_block();
+      const long long in_base = fb * p.in_frame + g_hi * p.in_g_hi + g_lo * p.in_g_lo;
+      const T* PDSP_RESTRICT ire = static_cast<const T*>(p.in_re);
+      const T* PDSP_RESTRICT iim = static_cast<const T*>(p.in_im);
+      const cx<T>* PDSP_RESTRICT icx = static_cast<const cx<T>*>(p.in_re);
+      PDSP_UNROLL
+      for (int k = 0; k < P; ++k) {
+        const int idx = tid + k * THREADS;
+        const int cc = idx >> LOG2L, e = idx & (L - 1);
+        const long long a = in_base + cc * p.in_c + e;
+        if constexpr (IN_CPLX) {
+          smem[(size_t)cc * SLOT + E::pad(e)] = ldg_cx(icx + a);
+        } else {
+          const T re = ire[a];
+          const T im = iim != nullptr ? iim[a] : (T)0;
+          smem[(size_t)cc * SLOT + E::pad(e)] = p.swap_in ? cx<T>{im, re} : cx<T>{re, im};
+        }
+      }
+      simt::sync_block();
+      static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[E::pad(t + TF * decltype(q)::value)]; });
+      simt::sync_block();
+    }
+
+    E::template fft<true>(v, t, sm, static_cast<const cx<T>*>(p.tw), 0, 1);
+
+    if (p.tw_hi != nullptr) {
+      // W_NT^{k*i}, k = t + TF*q: start at W^{t*i}, step by W^{TF*i}
+      const cx<T>* PDSP_RESTRICT hi = static_cast<const cx<T>*>(p.tw_hi);
+      const cx<T>* PDSP_RESTRICT lo = static_cast<const cx<T>*>(p.tw_lo);
+      const long long i = g_lo * C + c;
+      cx<T> wv = big_twiddle(hi, lo, (long long)t * i, p.log_b);
+      const cx<T> step = big_twiddle(hi, lo, (long long)TF * i, p.log_b);
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        v[q] = cmul(v[q], wv);
+        if constexpr (q + 1 < P) wv = cmul(wv, step);
+      });
+    }
+
+    // ---- tile out: results to shared memory in tile order [k][c] (the engine's last pass left the region free), then
+    // box stores by one thread.  They drain while this CTA fetches its next tile.
+    simt::sync_block();  // every thread is past the last exchange read
+    {
+      T* sre = reinterpret_cast<T*>(base);
+      T* sim = reinterpret_cast<T*>(base + PLANE);
+      static_for<0, P>([&](auto qi) {
+        constexpr int q = decltype(qi)::value;
+        const int k = t + TF * q;
+        if constexpr (OUT_CPLX) {
+          reinterpret_cast<cx<T>*>(sre)[k * C + c] = v[q];
+        } else {
+          const T x = v[q].x * scale, y = v[q].y * scale;
+          sre[k * C + c] = p.swap_out ? y : x;
+          sim[k * C + c] = p.swap_out ? x : y;
+        }
+      });
+    }
+    simt::fence_proxy_async();  // generic-proxy writes before the async-proxy reads of the bulk stores
+    simt::sync_block();
+    if (tid == 0) {
+      int co[3];
+      for (int d = 0; d < 3; ++d) co[d] = (int)(g_lo * p.out_lo[d] + g_hi * p.out_hi[d] + fb * p.out_fr[d]);
+      for (int j = 0; j < p.out_boxes; ++j) {
+        simt::tma_store_3d(&tm_out_re, co[0], co[1], co[2], base + (size_t)j * p.out_box_bytes);
+        if (!OUT_CPLX) simt::tma_store_3d(&tm_out_im, co[0], co[1], co[2], base + PLANE + (size_t)j * p.out_box_bytes);
+        co[p.out_box_dim] += p.out_box_step;
+      }
+      simt::bulk_commit();
+    }
+  }
+  if (tid == 0) simt::bulk_wait_all();  // global writes complete before the kernel ends
+}
+
+// Tile configuration of the second generation: half the sequences of BigCfg, two CTAs per SM
+template <typename T, int LOG2L>
+struct BigCfg2 {
+  static constexpr int LOG2P = BigCfg<T, LOG2L>::LOG2P;
+  static constexpr int MAXRB = BigCfg<T, LOG2L>::MAXRB;
+  static constexpr int TF = (1 << LOG2L) >> LOG2P;
+#ifndef PDSP_BIG2_THREADS
+#define PDSP_BIG2_THREADS 256
+#endif
+  static constexpr int C = PDSP_BIG2_THREADS / TF > 0 ? PDSP_BIG2_THREADS / TF : 1;
+  using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
+  static constexpr size_t PLANE = sizeof(T) * (size_t)E::M * C;
+  static constexpr size_t EXCH = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * C;
+  static constexpr size_t SMEM = (((EXCH > 2 * PLANE ? EXCH : 2 * PLANE) + 15) & ~(size_t)15) + 16 + 128;
+};
+
+}  // namespace pdsp

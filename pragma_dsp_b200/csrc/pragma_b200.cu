@@ -26,7 +26,7 @@
 #include <vector>
 
 #include "../../include/pragma_b200.h"
-#include "bigfft_kernels.cuh"
+#include "bigfft2_kernels.cuh"
 #include "fft_launch.cuh"
 #include "inst_groups.h"
 
@@ -47,6 +47,9 @@ void big_pass_tma_box(int log2l, int* cols, int* rows);
 cudaError_t launch_big_pass(bool f64, int log2l, const BigPassParams& p, const LaunchCtx& lc);
 cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, const simt::TensorMap2D& tm_re,
                                 const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
+// second generation (bigfft2.cu): TMA tile loads and stores
+int big2_pass_c(int log2l);
+cudaError_t launch_big_tile(bool f64, int log2l, int io, const BigTileParams& p, const simt::TensorMap* maps, const LaunchCtx& lc);
 
 // tuning variants (inst_var.cu), one symbol per (type, variant): only in -DPDSP_TUNING builds
 // (python -m pragma_dsp_b200.build --tuning); the shipped library carries the default mapping alone
@@ -74,6 +77,7 @@ struct Tune {
   long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
   int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
   int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
+  int big_v2 = 1;             // PDSP_BIG_V2: 1 = second-generation large-FFT passes (TMA loads and stores, two CTAs per SM), 0 = first
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
 };
@@ -103,6 +107,8 @@ static int tune_set(Tune& t, const char* key, const char* val) {
     t.staged = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_resident")) {
     t.big_resident = unset ? -1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_v2")) {
+    t.big_v2 = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "copy_threads")) {
@@ -117,7 +123,7 @@ static void tune_from_env(Tune& t) {
                                         {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
                                         {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
                                         {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
-                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}};
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}};
   for (auto& k : keys)
     if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
@@ -941,6 +947,157 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
   return 0;
 }
 
+// Rank-3 tensor map: element (x, y, z) at base + (x + y*stride1 + z*stride2) elements, box {b0, b1, b2}.
+static int make_tensor_map3(simt::TensorMap* tm, const void* base, bool f64, const long long dims[3], long long stride1,
+                            long long stride2, const int box[3]) {
+  const long long es = f64 ? 8 : 4;
+#ifdef PDSP_EMU
+  tm->base = const_cast<void*>(base);
+  for (int d = 0; d < 3; ++d) tm->dim[d] = dims[d], tm->box[d] = box[d];
+  tm->stride_bytes[0] = stride1 * es;
+  tm->stride_bytes[1] = stride2 * es;
+  tm->esize = (int)es;
+  return 0;
+#else
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t gdims[3] = {(cuuint64_t)dims[0], (cuuint64_t)dims[1], (cuuint64_t)dims[2]};
+  const cuuint64_t gstr[2] = {(cuuint64_t)(stride1 * es), (cuuint64_t)(stride2 * es)};
+  const cuuint32_t gbox[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2]};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(tm, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
+                            gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (rank 3, dims %lld x %lld x %lld, box %d x %d x %d) failed: CUresult %d", dims[0], dims[1],
+                dims[2], box[0], box[1], box[2], (int)r);
+  return 0;
+#endif
+}
+
+// Second-generation multi-pass transform (bigfft2_kernels.cuh): every pass moves its tiles with TMA box loads and box
+// stores; the last pass stores transposed boxes.  `chunk` transforms go through all passes together: small chunks keep
+// the inter-pass work buffer (and the output lines being assembled from 32-byte box rows) resident in the 126 MB L2.
+static int launch_big2(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
+                       void* d_oim, int inverse, cudaStream_t st) {
+  pdsp_ctx* c = pl->ctx;
+  const bool f64 = pl->precision == PDSP_F64;
+  const size_t es = esize(pl->precision);
+  const long long N = 1LL << pl->log2n;
+  LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
+  const int np = bp->npass;
+  long long Ls[3] = {1, 1, 1};
+  for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
+  // transforms per group of passes: input + work buffer + output of a chunk should fit the L2 with room to spare
+  long long chunk = (long long)((size_t)(96u << 20) / (3 * 2 * es * (size_t)N));
+  if (c->tune.big_chunk > 0) chunk = c->tune.big_chunk;
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  const bool il = c->tune.big_interleave != 0;
+  BigPlan::Work* wk = nullptr;
+  {
+    std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
+    wk = &bp->work[st];
+    if (wk->frames < chunk || wk->interleaved != il) {
+      CU(cudaStreamSynchronize(st));
+      CU(cudaFree(wk->re));
+      CU(cudaFree(wk->im));
+      wk->re = wk->im = nullptr;
+      CU(cudaMalloc(&wk->re, (il ? 2 : 1) * es * (size_t)N * (size_t)chunk));
+      if (!il) CU(cudaMalloc(&wk->im, es * (size_t)N * (size_t)chunk));
+      wk->interleaved = il;
+      wk->frames = chunk;
+    }
+  }
+  for (long long f0 = 0; f0 < batch; f0 += chunk) {
+    const long long nf = batch - f0 < chunk ? batch - f0 : chunk;
+    const char* fre = static_cast<const char*>(d_re) + (size_t)f0 * N * es;
+    const char* fim = d_im ? static_cast<const char*>(d_im) + (size_t)f0 * N * es : nullptr;
+    char* gre = static_cast<char*>(d_ore) + (size_t)f0 * N * es;
+    char* gim = static_cast<char*>(d_oim) + (size_t)f0 * N * es;
+    long long O = 1, I = N;
+    for (int j = 0; j < np; ++j) {
+      const long long L = Ls[j];
+      I /= L;
+      const int C = big2_pass_c(bp->lg[j]);
+      const bool last = j == np - 1;
+      const bool in_cplx = il && j != 0, out_cplx = il && !last;
+      const int BR = (int)(L < 256 ? L : 256);
+      BigTileParams p;
+      memset(&p, 0, sizeof p);
+      simt::TensorMap maps[4];
+      p.n_frames = nf;
+      p.swap_in = (j == 0 && inverse) ? 1 : 0;
+      p.swap_out = (last && inverse) ? 1 : 0;
+      p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
+      const void* in_re = j == 0 ? (const void*)fre : wk->re;
+      const void* in_im = j == 0 ? (const void*)fim : (il ? nullptr : wk->im);
+      void* out_re = last ? (void*)gre : wk->re;
+      void* out_im = last ? (void*)gim : (il ? nullptr : wk->im);
+      p.has_im = in_im != nullptr ? 1 : 0;
+      int io;
+      if (!last) {
+        // view [nf*O][L][I]: tile = C adjacent columns (box {C, BR, 1}, L / BR boxes down the transformed axis)
+        if (I % C) return fail("internal: pass %d of 2^%d has %lld columns, not a multiple of the tile width %d", j, pl->log2n, I, C);
+        p.n_lo = I / C;
+        p.n_groups = O * p.n_lo;
+        p.tw_hi = bp->tw_hi[j];
+        p.tw_lo = bp->tw_lo[j];
+        p.log_b = bp->log_b[j];
+        const int wi = in_cplx ? 2 : 1, wo = out_cplx ? 2 : 1;  // scalars per element in the mapped buffer
+        const long long din[3] = {wi * I, L, nf * O}, dout[3] = {wo * I, L, nf * O};
+        const int bin[3] = {wi * C, BR, 1}, bout[3] = {wo * C, BR, 1};
+        if (make_tensor_map3(&maps[0], in_re, f64, din, wi * I, wi * I * L, bin)) return 1;
+        if (make_tensor_map3(&maps[1], in_im ? in_im : in_re, f64, din, wi * I, wi * I * L, bin)) return 1;
+        if (make_tensor_map3(&maps[2], out_re, f64, dout, wo * I, wo * I * L, bout)) return 1;
+        if (make_tensor_map3(&maps[3], out_im ? out_im : out_re, f64, dout, wo * I, wo * I * L, bout)) return 1;
+        p.in_lo[0] = wi * C, p.in_hi[2] = 1, p.in_fr[2] = (int)O;
+        p.in_box_dim = 1, p.in_box_step = BR, p.in_boxes = (int)(L / BR);
+        p.in_box_bytes = (unsigned)(wi * C * BR * es);
+        p.out_lo[0] = wo * C, p.out_hi[2] = 1, p.out_fr[2] = (int)O;
+        p.out_box_dim = 1, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
+        p.out_box_bytes = (unsigned)(wo * C * BR * es);
+        io = (in_cplx ? 1 : 0) | (out_cplx ? 2 : 0);
+      } else {
+        // rows (k1[, k2]), L contiguous elements each; output X[k1 + L1*k2 (+ L1*L2*k3)]: view {L1, L2', nf*L}, box {C, 1, BR}
+        const long long L1 = Ls[0], L2 = np == 3 ? Ls[1] : 1;
+        if (L1 % C) return fail("internal: last pass of 2^%d: %lld rows, not a multiple of the tile height %d", pl->log2n, L1, C);
+        p.n_lo = L2;
+        p.n_groups = (L1 / C) * L2;
+        p.in_re = in_re;
+        p.in_im = in_im;
+        p.in_frame = N;
+        p.in_g_hi = C * L2 * L;
+        p.in_g_lo = np == 3 ? L : 0;
+        p.in_c = L2 * L;
+        const long long dout[3] = {L1, L2, nf * L};
+        const int bout[3] = {C, 1, BR};
+        if (make_tensor_map3(&maps[2], out_re, f64, dout, L1, L1 * L2, bout)) return 1;
+        if (make_tensor_map3(&maps[3], out_im, f64, dout, L1, L1 * L2, bout)) return 1;
+        maps[0] = maps[2], maps[1] = maps[3];
+        p.out_lo[1] = 1, p.out_hi[0] = C, p.out_fr[2] = (int)L;
+        p.out_box_dim = 2, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
+        p.out_box_bytes = (unsigned)(C * BR * es);
+        io = 4 | (in_cplx ? 1 : 0);
+      }
+      const cudaError_t e = launch_big_tile(f64, bp->lg[j], io, p, maps, lc);
+      if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d, TMA tiles): %s", j, pl->log2n, cudaGetErrorString(e));
+      c->launches++;
+      O *= L;
+    }
+  }
+  return 0;
+}
+
 static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long long batch, void* d_ore, void* d_oim,
                       int inverse, cudaStream_t st, const Doorbell* door, bool* door_used) {
   pdsp_ctx* c = pl->ctx;
@@ -948,7 +1105,17 @@ static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long lo
   if (pl->log2n > kMaxLog2M || c->tune.n_big_factors) {
     BigPlan* bp = nullptr;
     if (big_plan(pl, &bp)) return 1;
-    if (bp) return launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st);
+    if (bp) {
+      // TMA needs 16-byte aligned planes and box rows of at least 16 bytes; anything else takes the first generation
+      bool v2 = c->tune.big_v2 != 0;
+      const uintptr_t al = reinterpret_cast<uintptr_t>(d_re) | reinterpret_cast<uintptr_t>(d_im) | reinterpret_cast<uintptr_t>(d_ore) |
+                           reinterpret_cast<uintptr_t>(d_oim);
+      if (al & 15u) v2 = false;
+      for (int j = 0; j < bp->npass && v2; ++j)
+        if ((size_t)big2_pass_c(bp->lg[j]) * esize(pl->precision) < 16) v2 = false;
+      return v2 ? launch_big2(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st)
+                : launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st);
+    }
   }
   C2CParams p;
   memset(&p, 0, sizeof p);

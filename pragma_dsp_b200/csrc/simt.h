@@ -68,6 +68,24 @@ PDSP_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, 
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// rank-3 forms (second-generation large-FFT passes): tile load, and tile STORE shared -> global (SASS UTMASTG) as a bulk
+// async-group operation: commit after issuing, wait_read before the source shared memory is reused, wait_all before exit
+typedef CUtensorMap TensorMap;
+PDSP_DEVICE void tma_load_3d(void* smem_dst, const TensorMap* map, int x, int y, int z, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+PDSP_DEVICE void tma_store_3d(const TensorMap* map, int x, int y, int z, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y), "r"(z),
+               "r"(smem_u32(smem_src))
+               : "memory");
+}
+PDSP_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+PDSP_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PDSP_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // L2 prefetch of the same box (no shared-memory destination, no barrier)
 PDSP_DEVICE void tma_prefetch_2d(const TensorMap2D* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
@@ -190,6 +208,43 @@ inline void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsig
   emu_mbar_complete_tx(bar, bytes);
 }
 inline void tma_prefetch_2d(const TensorMap2D*, int, int) {}
+// rank-3 description: element (x, y, z) at base + x*esize + y*stride_bytes[0] + z*stride_bytes[1]
+struct TensorMap {
+  void* base;
+  long long dim[3];
+  long long stride_bytes[2];
+  int box[3], esize;
+};
+inline void tma_load_3d(void* smem_dst, const TensorMap* m, int x, int y, int z, unsigned long long* bar) {
+  char* dst = static_cast<char*>(smem_dst);
+  size_t i = 0;
+  for (int c = 0; c < m->box[2]; ++c)
+    for (int b = 0; b < m->box[1]; ++b)
+      for (int a = 0; a < m->box[0]; ++a, ++i) {
+        const long long gx = x + a, gy = y + b, gz = z + c;
+        char* d = dst + i * (size_t)m->esize;
+        if (gx < m->dim[0] && gy < m->dim[1] && gz < m->dim[2])
+          memcpy(d, static_cast<const char*>(m->base) + gx * m->esize + gy * m->stride_bytes[0] + gz * m->stride_bytes[1], (size_t)m->esize);
+        else
+          memset(d, 0, (size_t)m->esize);
+      }
+  emu_mbar_complete_tx(bar, (unsigned)(m->box[0] * m->box[1] * m->box[2] * m->esize));
+}
+inline void tma_store_3d(const TensorMap* m, int x, int y, int z, const void* smem_src) {
+  const char* src = static_cast<const char*>(smem_src);
+  size_t i = 0;
+  for (int c = 0; c < m->box[2]; ++c)
+    for (int b = 0; b < m->box[1]; ++b)
+      for (int a = 0; a < m->box[0]; ++a, ++i) {
+        const long long gx = x + a, gy = y + b, gz = z + c;
+        if (gx < m->dim[0] && gy < m->dim[1] && gz < m->dim[2])  // out-of-bounds elements are not written
+          memcpy(static_cast<char*>(m->base) + gx * m->esize + gy * m->stride_bytes[0] + gz * m->stride_bytes[1], src + i * (size_t)m->esize,
+                 (size_t)m->esize);
+      }
+}
+inline void bulk_commit() {}
+inline void bulk_wait_read() {}
+inline void bulk_wait_all() {}
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu_mbar_wait(bar, parity); }
 inline void fence_proxy_async() {}
 inline void prefetch_l2_bulk(const void*, unsigned) {}

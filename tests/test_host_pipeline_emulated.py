@@ -174,10 +174,17 @@ def test_launch_and_plan_accounting(emu_api):
 @pytest.mark.parametrize("factors,n,env", [("6,6", 4096, {}), ("7,6", 8192, {}), ("6,6,6", 1 << 18, {}),
                                            ("7,7", 1 << 14, {}),
                                            # switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
-                                           ("7,6", 8192, {"big_tma": "0"}),
-                                           ("7,6", 8192, {"big_tma": "1"}),
-                                           ("6,6", 4096, {"big_interleave": "0", "big_tma": "1"}),
-                                           ("7,6", 8192, {"big_interleave": "0", "big_tma": "0",
+                                           # second generation (TMA tile loads AND stores): planar work planes, one transform per group
+                                           ("7,6", 8192, {"big_interleave": "0"}),
+                                           ("6,6,6", 1 << 18, {"big_interleave": "0"}),
+                                           ("7,6", 8192, {"big_chunk": "1"}),
+                                           # first generation, its switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
+                                           ("6,6", 4096, {"big_v2": "0"}),
+                                           ("6,6,6", 1 << 18, {"big_v2": "0"}),
+                                           ("7,6", 8192, {"big_v2": "0", "big_tma": "0"}),
+                                           ("7,6", 8192, {"big_v2": "0", "big_tma": "1"}),
+                                           ("6,6", 4096, {"big_v2": "0", "big_interleave": "0", "big_tma": "1"}),
+                                           ("7,6", 8192, {"big_v2": "0", "big_interleave": "0", "big_tma": "0",
                                                           "big_prefetch": "0"})])
 def test_multipass_large_fft_emulated(emu_api, tune, factors, n, env):
     """K2: the multi-pass (four-step / six-step) path, forced onto small sizes with the big_factors tunable so the
