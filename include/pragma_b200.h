@@ -196,6 +196,34 @@ int pdsp_ingest_flush(pdsp_ingest* ring);
 int pdsp_ingest_pop(pdsp_ingest* ring, void* amplitude, void* phase, void* peaks, int64_t max_frames, int64_t* got);
 int pdsp_ingest_close(pdsp_ingest* ring);
 
+/* ---- device groups: frame sharding over the GPUs of one box (BASELINE config C5).  No reference
+ *      counterpart - the reference is single-threaded; frames are independent (spectrumStream is a pure 1:1 map,
+ *      src/effect/index.ts:190-194), so device i of n owns the contiguous block [i*ceil(F/n), (i+1)*ceil(F/n)) of the
+ *      frame range.  One process, one context per device, peer access enabled between the devices. -------------------- */
+typedef struct pdsp_group pdsp_group;
+int pdsp_group_create(const int* devices, int n, pdsp_group** group); /* 1..8 distinct device ordinals */
+int pdsp_group_destroy(pdsp_group* group);
+int pdsp_group_size(const pdsp_group* group);
+pdsp_ctx* pdsp_group_ctx(pdsp_group* group, int i); /* the i-th device's context (owned by the group) */
+/* pdsp_spectrum over all devices of the group: host frames in, host results out.  Every device runs its block through
+ * its own staging pipeline on its own host thread (pinned to the CPUs of the device's NUMA node); results land in the
+ * caller's arrays at the block's offset, i.e. gathered on the way out.  Same arguments and results as pdsp_spectrum
+ * (size / precision select each device's plan). */
+int pdsp_group_spectrum(pdsp_group* group, int32_t size, int precision, const pdsp_spectrum_desc* desc, const void* samples,
+                        void* amplitude, void* phase, void* peaks);
+/* Device-resident sharded form (desc->batch = frames of the whole job).  Device i holds its block's samples at
+ * d_samples[i] and gets block-local rows in d_amplitude[i] / d_phase[i] (arrays or entries may be NULL).  d_peaks[i] is
+ * device i's GATHER buffer of desc->batch records: every device's kernel stores its block's records into all of them
+ * (NVLink peer stores fused into the kernel - the all-gather of per-frame peaks), so after pdsp_group_sync every device
+ * holds the peaks of all frames.  gather_root >= 0 additionally copies all blocks' amplitude / phase rows into
+ * d_amplitude_all / d_phase_all (desc->batch rows on device gather_root; either may be NULL) by peer DMA queued behind
+ * each block's kernel: the spectra gather "where the caller requests them on one device".  Work is queued on each
+ * context's own stream. */
+int pdsp_group_spectrum_dev(pdsp_group* group, int32_t size, int precision, const pdsp_spectrum_desc* desc,
+                            const void* const* d_samples, void* const* d_amplitude, void* const* d_phase, void* const* d_peaks,
+                            int gather_root, void* d_amplitude_all, void* d_phase_all);
+int pdsp_group_sync(pdsp_group* group);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ Same ladder as the reference's subpath exports (package.json:14-55):
 All compute goes through libpragma_b200.so (include/pragma_b200.h); there is no CPU fallback.
 """
 from ._lib import PragmaB200Error  # noqa: F401
+from .group import DeviceGroup  # noqa: F401
 from .public.ingest import IngestRing  # noqa: F401
 from .public.spectrum import spectrum, spectrum_batch, stft  # noqa: F401
 
-__all__ = ["spectrum", "spectrum_batch", "stft", "IngestRing", "PragmaB200Error"]
+__all__ = ["spectrum", "spectrum_batch", "stft", "IngestRing", "DeviceGroup", "PragmaB200Error"]

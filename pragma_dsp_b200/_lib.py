@@ -82,6 +82,14 @@ SYMBOLS = {
     "pdsp_ingest_flush": (C.c_int, [_vp]),
     "pdsp_ingest_pop": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "pdsp_ingest_close": (C.c_int, [_vp]),
+    "pdsp_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "pdsp_group_destroy": (C.c_int, [_vp]),
+    "pdsp_group_size": (C.c_int, [_vp]),
+    "pdsp_group_ctx": (_vp, [_vp, C.c_int]),
+    "pdsp_group_spectrum": (C.c_int, [_vp, _i32, C.c_int, C.POINTER(SpectrumDesc), _vp, _vp, _vp, _vp]),
+    "pdsp_group_spectrum_dev": (C.c_int, [_vp, _i32, C.c_int, C.POINTER(SpectrumDesc), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                          C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "pdsp_group_sync": (C.c_int, [_vp]),
 }
 
 _lib = None

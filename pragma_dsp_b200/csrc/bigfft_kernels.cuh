@@ -54,7 +54,8 @@ PDSP_DEVICE cx<T> big_twiddle(const cx<T>* PDSP_RESTRICT hi, const cx<T>* PDSP_R
 // IO: bit 0 = the input is the interleaved work buffer, bit 1 = the output is (compile time: a run-time test
 // inside the unrolled load / store loops cost 25-50 % of the kernel)
 template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_kernel(const BigPassParams p) {
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, (512 / (((1 << LOG2L) >> LOG2P) * C) > 0 ? 512 / (((1 << LOG2L) >> LOG2P) * C) : 1))
+    bigfft_pass_kernel(const BigPassParams p) {
   constexpr bool IN_CPLX = (IO & 1) != 0, OUT_CPLX = (IO & 2) != 0;
   using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
   constexpr int L = E::M, P = E::P, TF = E::TF;
@@ -171,7 +172,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1) bigfft_pass_
 // as the plain kernel.  Requires frames to be contiguous (in_frame = N) and the inner index to be the
 // tensor's contiguous dimension - i.e. any pass but the last.
 template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int STAGES, int IO>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 1)
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, (512 / (((1 << LOG2L) >> LOG2P) * C) > 0 ? 512 / (((1 << LOG2L) >> LOG2P) * C) : 1))
     bigfft_pass_tma_kernel(const BigPassParams p, const PDSP_GRID_CONSTANT simt::TensorMap2D tm_re,
                            const PDSP_GRID_CONSTANT simt::TensorMap2D tm_im) {
   using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
@@ -336,7 +337,10 @@ struct BigCfg {
 #ifndef PDSP_BIG_C_SMALL
 #define PDSP_BIG_C_SMALL 32
 #endif
-  static constexpr int C = LOG2L == 10 ? 8 : (LOG2L == 9 ? 16 : PDSP_BIG_C_SMALL);
+#ifndef PDSP_BIG_C_L10
+#define PDSP_BIG_C_L10 8  // experiment: 4 = half tiles, 256-thread CTAs, two per SM
+#endif
+  static constexpr int C = LOG2L == 10 ? PDSP_BIG_C_L10 : (LOG2L == 9 ? 16 : PDSP_BIG_C_SMALL);
 };
 constexpr int kBigMinLog2L = 6, kBigMaxLog2L = 10;
 

@@ -219,6 +219,11 @@ PDSP_DEVICE void frame_sync(int slot, int slots_per_cta) {
 #ifndef PDSP_DERIVE_POST
 #define PDSP_DERIVE_POST 1
 #endif
+// fp64, radix-16 middle passes: load W^r and W^{4r} only and build the other 13 twiddles W^{s*r} by complex products
+// (52 DP instructions for 13 L1 loads; depth <= 3 products, ~1e-15 relative).  Experiment switch, default off.
+#ifndef PDSP_DERIVE_MID
+#define PDSP_DERIVE_MID 0
+#endif
 
 template <typename T, int LOG2M, int LOG2P, int MAXRB>
 struct FftEngine {
@@ -317,6 +322,25 @@ struct FftEngine {
               const cx<T> w = mul_w32_full<(s * u * (32 / P)) % 32>(w0[s]);
               a[s] = cmul(a[s], w);
             });
+          } else if constexpr (PDSP_DERIVE_MID && sizeof(T) == 8 && R == 16 && !last) {
+            const cx<T>* PDSP_RESTRICT twp = tw + tw_offset(pass) + (j & (NS - 1));
+            cx<T> w[16];
+            w[1] = ldg_cx(twp);
+            w[4] = ldg_cx(twp + 3 * NS);
+            w[2] = cmul(w[1], w[1]);
+            w[3] = cmul(w[2], w[1]);
+            w[8] = cmul(w[4], w[4]);
+            w[5] = cmul(w[4], w[1]);
+            w[6] = cmul(w[4], w[2]);
+            w[7] = cmul(w[4], w[3]);
+            w[12] = cmul(w[8], w[4]);
+            w[9] = cmul(w[8], w[1]);
+            w[10] = cmul(w[8], w[2]);
+            w[11] = cmul(w[8], w[3]);
+            w[13] = cmul(w[12], w[1]);
+            w[14] = cmul(w[12], w[2]);
+            w[15] = cmul(w[12], w[3]);
+            static_for<1, R>([&](auto s) { a[decltype(s)::value] = cmul(a[decltype(s)::value], w[decltype(s)::value]); });
           } else {
             const cx<T>* PDSP_RESTRICT twp = tw + tw_offset(pass) + (j & (NS - 1));
             static_for<1, R>([&](auto s) {

@@ -77,7 +77,7 @@ struct Tune {
   long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
   int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
   int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
-  int big_v2 = 1;             // PDSP_BIG_V2: 1 = second-generation large-FFT passes (TMA loads and stores, two CTAs per SM), 0 = first
+  int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
 };
@@ -108,7 +108,7 @@ static int tune_set(Tune& t, const char* key, const char* val) {
   } else if (!strcmp(key, "big_resident")) {
     t.big_resident = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_v2")) {
-    t.big_v2 = unset ? 1 : (v[0] != '0');
+    t.big_v2 = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "copy_threads")) {
@@ -821,129 +821,95 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
 // Intermediate passes exchange interleaved (re, im) elements unless tune.big_interleave = 0: 512-byte instead of
 // 2 x 256-byte tile rows (2^24: 0.375 -> 0.353 ms, profiles/r1/README.md)
 
-static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
-                      void* d_oim, int inverse, cudaStream_t st) {
+// One pass of the first-generation path (bigfft_kernels.cuh: per-thread tile loads and stores, or TMA tile loads) over the
+// `nf` transforms of a group.  fre/fim, gre/gim: the group's caller-facing input / output planes; wk: its work buffer.
+static int launch_pass_v1(pdsp_plan* pl, BigPlan* bp, BigPlan::Work* wk, int j, long long O, long long I, long long nf,
+                          const char* fre, const char* fim, char* gre, char* gim, int inverse, const LaunchCtx& lc) {
   pdsp_ctx* c = pl->ctx;
   const size_t es = esize(pl->precision);
   const long long N = 1LL << pl->log2n;
-  LaunchCtx lc{c->device, c->sm_count, st, pass_twiddles_cb, c};
   const int np = bp->npass;
   long long Ls[3] = {1, 1, 1};
-  for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
-  // transforms are processed `chunk` at a time (all passes of a chunk share the work planes)
-  long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
-  if (c->tune.big_chunk > 0) chunk = c->tune.big_chunk;  // experiment / test hook: transforms per group of passes
-  if (chunk < 1) chunk = 1;
-  if (chunk > batch) chunk = batch;
-  BigPlan::Work* wk = nullptr;
-  {
-    std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
-    const bool want_il = c->tune.big_interleave != 0;
-    wk = &bp->work[st];  // std::map nodes are stable: the pointer outlives the lock
-    if (wk->frames < chunk || wk->interleaved != want_il) {
-      CU(cudaStreamSynchronize(st));
-      CU(cudaFree(wk->re));
-      CU(cudaFree(wk->im));
-      wk->re = wk->im = nullptr;
-      // `re` alone, twice the size, when the passes exchange interleaved cx<T> elements (default); two planar
-      // work planes with PDSP_BIG_INTERLEAVE=0
-      CU(cudaMalloc(&wk->re, (want_il ? 2 : 1) * es * (size_t)N * (size_t)chunk));
-      if (!want_il) CU(cudaMalloc(&wk->im, es * (size_t)N * (size_t)chunk));
-      wk->interleaved = want_il;
-      wk->frames = chunk;
-    }
+  for (int k = 0; k < np; ++k) Ls[k] = 1LL << bp->lg[k];
+  const long long L = Ls[j];
+  const int C = big_pass_c(bp->lg[j]);
+  const bool last = j == np - 1;
+  BigPassParams p;
+  memset(&p, 0, sizeof p);
+  const bool interleave = wk->interleaved;
+  p.in_re = j == 0 ? (const void*)fre : wk->re;
+  p.in_im = j == 0 ? (const void*)fim : (interleave ? nullptr : wk->im);
+  p.out_re = last ? (void*)gre : wk->re;
+  p.out_im = last ? (void*)gim : (interleave ? nullptr : wk->im);
+  p.in_cplx = (interleave && j != 0) ? 1 : 0;
+  p.out_cplx = (interleave && !last) ? 1 : 0;
+  p.n_frames = nf;
+  p.in_frame = p.out_frame = N;
+  p.swap_in = (j == 0 && inverse) ? 1 : 0;
+  p.swap_out = (last && inverse) ? 1 : 0;
+  p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
+  p.l2_prefetch = c->tune.big_prefetch;  // default on: 2^24 0.43 -> 0.37 ms (profiles/r1/README.md)
+  if (!last) {
+    // view [O][L][I]: C adjacent inner indices per CTA, transform along the stride-I axis in place
+    p.n_lo = I / C;
+    p.n_groups = O * p.n_lo;
+    p.in_hi = p.out_hi = L * I;
+    p.in_lo = p.out_lo = C;
+    p.in_c = p.out_c = 1;
+    p.in_e = p.out_e = I;
+    p.tw_hi = bp->tw_hi[j];
+    p.tw_lo = bp->tw_lo[j];
+    p.log_b = bp->log_b[j];
+    p.stage_in = 0;
+  } else if (np == 2) {
+    // rows k1 (contiguous, L2 long); C adjacent k1 per CTA; X[k1 + L1*k2]
+    p.n_lo = 1;
+    p.n_groups = Ls[0] / C;
+    p.in_hi = C * L;
+    p.in_c = L;
+    p.in_e = 1;
+    p.out_hi = C;
+    p.out_c = 1;
+    p.out_e = Ls[0];
+    p.stage_in = 1;
+  } else {
+    // rows (k1, k2); groups (k1 tile, k2); X[k1 + L1*k2 + L1*L2*k3]
+    p.n_lo = Ls[1];
+    p.n_groups = (Ls[0] / C) * Ls[1];
+    p.in_hi = C * Ls[1] * L;
+    p.in_lo = L;
+    p.in_c = Ls[1] * L;
+    p.in_e = 1;
+    p.out_hi = C;
+    p.out_lo = Ls[0];
+    p.out_c = 1;
+    p.out_e = Ls[0] * Ls[1];
+    p.stage_in = 1;
   }
-  for (long long f0 = 0; f0 < batch; f0 += chunk) {
-    const long long nf = batch - f0 < chunk ? batch - f0 : chunk;
-    const char* fre = static_cast<const char*>(d_re) + (size_t)f0 * N * es;
-    const char* fim = d_im ? static_cast<const char*>(d_im) + (size_t)f0 * N * es : nullptr;
-    char* gre = static_cast<char*>(d_ore) + (size_t)f0 * N * es;
-    char* gim = static_cast<char*>(d_oim) + (size_t)f0 * N * es;
-    long long O = 1, I = N;
-    for (int j = 0; j < np; ++j) {
-      const long long L = Ls[j];
-      I /= L;
-      const int C = big_pass_c(bp->lg[j]);
-      const bool last = j == np - 1;
-      BigPassParams p;
-      memset(&p, 0, sizeof p);
-      const bool interleave = wk->interleaved;
-      p.in_re = j == 0 ? (const void*)fre : wk->re;
-      p.in_im = j == 0 ? (const void*)fim : (interleave ? nullptr : wk->im);
-      p.out_re = last ? (void*)gre : wk->re;
-      p.out_im = last ? (void*)gim : (interleave ? nullptr : wk->im);
-      p.in_cplx = (interleave && j != 0) ? 1 : 0;
-      p.out_cplx = (interleave && !last) ? 1 : 0;
-      p.n_frames = nf;
-      p.in_frame = p.out_frame = N;
-      p.swap_in = (j == 0 && inverse) ? 1 : 0;
-      p.swap_out = (last && inverse) ? 1 : 0;
-      p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
-      p.l2_prefetch = c->tune.big_prefetch;  // default on: 2^24 0.43 -> 0.37 ms (profiles/r1/README.md)
-      if (!last) {
-        // view [O][L][I]: C adjacent inner indices per CTA, transform along the stride-I axis in place
-        p.n_lo = I / C;
-        p.n_groups = O * p.n_lo;
-        p.in_hi = p.out_hi = L * I;
-        p.in_lo = p.out_lo = C;
-        p.in_c = p.out_c = 1;
-        p.in_e = p.out_e = I;
-        p.tw_hi = bp->tw_hi[j];
-        p.tw_lo = bp->tw_lo[j];
-        p.log_b = bp->log_b[j];
-        p.stage_in = 0;
-      } else if (np == 2) {
-        // rows k1 (contiguous, L2 long); C adjacent k1 per CTA; X[k1 + L1*k2]
-        p.n_lo = 1;
-        p.n_groups = Ls[0] / C;
-        p.in_hi = C * L;
-        p.in_c = L;
-        p.in_e = 1;
-        p.out_hi = C;
-        p.out_c = 1;
-        p.out_e = Ls[0];
-        p.stage_in = 1;
-      } else {
-        // rows (k1, k2); groups (k1 tile, k2); X[k1 + L1*k2 + L1*L2*k3]
-        p.n_lo = Ls[1];
-        p.n_groups = (Ls[0] / C) * Ls[1];
-        p.in_hi = C * Ls[1] * L;
-        p.in_lo = L;
-        p.in_c = Ls[1] * L;
-        p.in_e = 1;
-        p.out_hi = C;
-        p.out_lo = Ls[0];
-        p.out_c = 1;
-        p.out_e = Ls[0] * Ls[1];
-        p.stage_in = 1;
-      }
-      cudaError_t e;
-      // TMA tile loads for the strided passes while one chunk's planes fit the L2 (2^20: 0.158 vs 0.169 ms per 8
-      // transforms); per-thread loads beyond that (2^24: 0.353 vs 0.373 ms).  PDSP_BIG_TMA=0/1 forces either.
-      const bool tma = c->tune.big_tma >= 0 ? c->tune.big_tma != 0 : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
-      if (!last && tma) {
-        // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
-        simt::TensorMap2D tm_re, tm_im;
-        int bc = 0, br = 0;
-        big_pass_tma_box(bp->lg[j], &bc, &br);
-        const bool f64p = pl->precision == PDSP_F64;
-        if (p.in_cplx) {
-          // interleaved work buffer viewed as [rows][2*I] scalars; {2*C, rows/2} boxes keep a box at 64 KB
-          if (make_tensor_map(&tm_re, p.in_re, f64p, 2 * I, nf * O * L, 2 * bc, br / 2)) return 1;
-          tm_im = tm_re;
-        } else {
-          if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
-          if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
-        }
-        e = launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
-      } else {
-        e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
-      }
-      if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d): %s", j, pl->log2n, cudaGetErrorString(e));
-      c->launches++;
-      O *= L;
+  cudaError_t e;
+  // TMA tile loads for the strided passes while one group's planes fit the L2 (2^20: 0.158 vs 0.169 ms per 8
+  // transforms); per-thread loads beyond that (2^24: 0.353 vs 0.373 ms).  Tunable big_tma forces either.
+  const bool tma = c->tune.big_tma >= 0 ? c->tune.big_tma != 0 : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
+  if (!last && tma) {
+    // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
+    simt::TensorMap2D tm_re, tm_im;
+    int bc = 0, br = 0;
+    big_pass_tma_box(bp->lg[j], &bc, &br);
+    const bool f64p = pl->precision == PDSP_F64;
+    if (p.in_cplx) {
+      // interleaved work buffer viewed as [rows][2*I] scalars; {2*C, rows/2} boxes keep a box at 64 KB
+      if (make_tensor_map(&tm_re, p.in_re, f64p, 2 * I, nf * O * L, 2 * bc, br / 2)) return 1;
+      tm_im = tm_re;
+    } else {
+      if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
+      if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
     }
+    e = launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
+  } else {
+    e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
   }
+  if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d): %s", j, pl->log2n, cudaGetErrorString(e));
+  c->launches++;
   return 0;
 }
 
@@ -984,11 +950,14 @@ static int make_tensor_map3(simt::TensorMap* tm, const void* base, bool f64, con
 #endif
 }
 
-// Second-generation multi-pass transform (bigfft2_kernels.cuh): every pass moves its tiles with TMA box loads and box
-// stores; the last pass stores transposed boxes.  `chunk` transforms go through all passes together: small chunks keep
-// the inter-pass work buffer (and the output lines being assembled from 32-byte box rows) resident in the 126 MB L2.
-static int launch_big2(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
-                       void* d_oim, int inverse, cudaStream_t st) {
+// Multi-pass transform.  Each pass runs on the generation that is faster for its length (both exchange the same work
+// buffer): the second (bigfft2_kernels.cuh: TMA box loads and box stores, two CTAs per SM, transposed box stores in the
+// last pass) wherever its tiles have rows of at least 64 bytes - passes of up to 256 points; measured 3-10 % ahead at
+// 2^16, 2^22 and 2^24 - and the first (bigfft_kernels.cuh) for the 512- and 1024-point passes, whose 4- and 8-column
+// tiles make 32-byte box rows (the TMA unit then spends its time on row requests: 2^20 = 1024 x 1024 ran 0.19 of the
+// roofline against 0.26).  `chunk` transforms go through all passes together.
+static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
+                      void* d_oim, int inverse, cudaStream_t st, bool v2_allowed) {
   pdsp_ctx* c = pl->ctx;
   const bool f64 = pl->precision == PDSP_F64;
   const size_t es = esize(pl->precision);
@@ -997,9 +966,8 @@ static int launch_big2(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void*
   const int np = bp->npass;
   long long Ls[3] = {1, 1, 1};
   for (int j = 0; j < np; ++j) Ls[j] = 1LL << bp->lg[j];
-  // transforms per group of passes: input + work buffer + output of a chunk should fit the L2 with room to spare
-  long long chunk = (long long)((size_t)(96u << 20) / (3 * 2 * es * (size_t)N));
-  if (c->tune.big_chunk > 0) chunk = c->tune.big_chunk;
+  long long chunk = (1LL << 25) / N;  // <= 2^25 elements (256 MB of doubles) per work plane
+  if (c->tune.big_chunk > 0) chunk = c->tune.big_chunk;  // experiment / test hook: transforms per group of passes
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   const bool il = c->tune.big_interleave != 0;
@@ -1030,6 +998,14 @@ static int launch_big2(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void*
       I /= L;
       const int C = big2_pass_c(bp->lg[j]);
       const bool last = j == np - 1;
+      // generation of this pass: tunable big_v2 = 0 / 1 forces the first / second (where TMA can take the shape at all)
+      const bool wide = (size_t)C * es >= 64;
+      const bool v2 = v2_allowed && (size_t)C * es >= 16 && (c->tune.big_v2 < 0 ? wide : c->tune.big_v2 != 0);
+      if (!v2) {
+        if (launch_pass_v1(pl, bp, wk, j, O, I, nf, fre, fim, gre, gim, inverse, lc)) return 1;
+        O *= L;
+        continue;
+      }
       const bool in_cplx = il && j != 0, out_cplx = il && !last;
       const int BR = (int)(L < 256 ? L : 256);
       BigTileParams p;
@@ -1106,15 +1082,10 @@ static int launch_c2c(pdsp_plan* pl, const void* d_re, const void* d_im, long lo
     BigPlan* bp = nullptr;
     if (big_plan(pl, &bp)) return 1;
     if (bp) {
-      // TMA needs 16-byte aligned planes and box rows of at least 16 bytes; anything else takes the first generation
-      bool v2 = c->tune.big_v2 != 0;
+      // TMA box stores need 16-byte aligned planes; anything else stays on the first generation
       const uintptr_t al = reinterpret_cast<uintptr_t>(d_re) | reinterpret_cast<uintptr_t>(d_im) | reinterpret_cast<uintptr_t>(d_ore) |
                            reinterpret_cast<uintptr_t>(d_oim);
-      if (al & 15u) v2 = false;
-      for (int j = 0; j < bp->npass && v2; ++j)
-        if ((size_t)big2_pass_c(bp->lg[j]) * esize(pl->precision) < 16) v2 = false;
-      return v2 ? launch_big2(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st)
-                : launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st);
+      return launch_big(pl, bp, d_re, d_im, batch, d_ore, d_oim, inverse, st, (al & 15u) == 0);
     }
   }
   C2CParams p;
@@ -2300,5 +2271,249 @@ PDSP_EXPORT int pdsp_ingest_pop(pdsp_ingest* g, void* amplitude, void* phase, vo
     }
   }
   *got = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ device groups
+// Frames are independent (the reference's spectrumStream is a pure 1:1 map, src/effect/index.ts:190-194), so a box of
+// GPUs is used by cutting the frame range into one contiguous block per device.  A group is a set of contexts in ONE
+// process with peer access enabled between their devices:
+//   * pdsp_group_spectrum      - host frames in, host results out: every device runs its block through its own staging
+//                                pipeline on its own host thread (pinned to the CPUs of the device's NUMA node), results
+//                                land in the caller's arrays at the block's offset - the gather happens on the way out;
+//   * pdsp_group_spectrum_dev  - device-resident blocks: every device's kernel also stores each finished peak record
+//                                into the gather buffers of ALL devices (the fused NVLink scatter of
+//                                pdsp_spectrum_dev_gather, with plain peer pointers), and amplitude / phase rows are
+//                                copied to one root device by peer DMA when the caller asks for them there.
+struct pdsp_group {
+  std::vector<pdsp_ctx*> ctx;
+  std::vector<std::vector<int>> cpus;  // CPUs of each device's NUMA node (empty: unknown, threads are left unpinned)
+};
+
+#ifndef PDSP_EMU
+#include <sched.h>
+#endif
+static std::vector<int> numa_cpus_of_device(int device) {
+  std::vector<int> cpus;
+#ifndef PDSP_EMU
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return cpus;
+  for (char* q = bus; *q; ++q)
+    if (*q >= 'A' && *q <= 'F') *q = (char)(*q - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  int node = -1;
+  if (f) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (node < 0) return cpus;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return cpus;
+  char list[4096] = {0};
+  if (fgets(list, sizeof list, f)) {
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+      int a = 0, b = 0;
+      const int got = sscanf(tok, "%d-%d", &a, &b);
+      if (got == 1) b = a;
+      if (got >= 1)
+        for (int k = a; k <= b; ++k) cpus.push_back(k);
+    }
+  }
+  fclose(f);
+#else
+  (void)device;
+#endif
+  return cpus;
+}
+static void pin_thread_to(const std::vector<int>& cpus) {
+#ifndef PDSP_EMU
+  if (cpus.empty()) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int k : cpus)
+    if (k >= 0 && k < CPU_SETSIZE) CPU_SET(k, &set);
+  sched_setaffinity(0, sizeof set, &set);  // best effort: an error leaves the thread where it was
+#else
+  (void)cpus;
+#endif
+}
+
+PDSP_EXPORT int pdsp_group_create(const int* devices, int n, pdsp_group** out) {
+  if (!devices || !out) return fail("null argument");
+  *out = nullptr;
+  if (n < 1 || n > 8) return fail("a group holds 1..8 devices, got %d", n);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < i; ++k)
+      if (devices[i] == devices[k]) return fail("device %d listed twice", devices[i]);
+  pdsp_group* g = new pdsp_group();
+  for (int i = 0; i < n; ++i) {
+    pdsp_ctx* c = nullptr;
+    if (pdsp_ctx_create(devices[i], &c)) {
+      for (pdsp_ctx* o : g->ctx) pdsp_ctx_destroy(o);
+      delete g;
+      return 1;
+    }
+    g->ctx.push_back(c);
+    g->cpus.push_back(numa_cpus_of_device(devices[i]));
+  }
+  // peer access both ways (NVLink / NVSwitch): the fused record scatter and the row gather write peer memory directly
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < n; ++k) {
+      if (i == k) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[k]);
+      if (!can) continue;
+      if (cudaSetDevice(devices[i]) != cudaSuccess) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fail("peer access %d -> %d: %s", devices[i], devices[k], cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  *out = g;
+  return 0;
+}
+PDSP_EXPORT int pdsp_group_destroy(pdsp_group* g) {
+  if (!g) return 0;
+  int rc = 0;
+  for (pdsp_ctx* c : g->ctx) rc |= pdsp_ctx_destroy(c);
+  delete g;
+  return rc;
+}
+PDSP_EXPORT int pdsp_group_size(const pdsp_group* g) { return g ? (int)g->ctx.size() : 0; }
+PDSP_EXPORT pdsp_ctx* pdsp_group_ctx(pdsp_group* g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[(size_t)i] : nullptr; }
+
+// block partition of `batch` frames over `n` devices: device i owns [i*per, min(batch, (i+1)*per)), per = ceil(batch / n)
+static void group_block(long long batch, int n, int i, long long* f0, long long* nf) {
+  const long long per = (batch + n - 1) / n;
+  long long a = per * i, b = a + per;
+  if (a > batch) a = batch;
+  if (b > batch) b = batch;
+  *f0 = a;
+  *nf = b - a;
+}
+
+PDSP_EXPORT int pdsp_group_spectrum(pdsp_group* g, int32_t size, int precision, const pdsp_spectrum_desc* d, const void* samples,
+                                    void* amplitude, void* phase, void* peaks) {
+  if (!g || !d) return fail("null argument");
+  const int n = (int)g->ctx.size();
+  std::vector<pdsp_plan*> plans((size_t)n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (pdsp_plan_get(g->ctx[(size_t)i], size, precision, &plans[(size_t)i])) return 1;
+  if (check_desc(plans[0], d)) return 1;
+  if (d->batch == 0) return 0;
+  const int bins = d->sides == PDSP_SIDES_TWO ? size : size / 2 + 1;
+  const size_t es = esize(d->sample_dtype), os = esize(precision);
+  const size_t pk = precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
+  std::vector<int> rcs((size_t)n, 0);
+  std::vector<std::string> errs((size_t)n);
+  auto work = [&](int i) {
+    long long f0, nf;
+    group_block(d->batch, n, i, &f0, &nf);
+    if (nf <= 0) return;
+    pin_thread_to(g->cpus[(size_t)i]);
+    pdsp_spectrum_desc dd = *d;
+    dd.batch = nf;
+    const char* src = samples ? static_cast<const char*>(samples) + (size_t)f0 * (size_t)d->hop * es : nullptr;
+    rcs[(size_t)i] = pdsp_spectrum(plans[(size_t)i], &dd, src, amplitude ? static_cast<char*>(amplitude) + (size_t)f0 * bins * os : nullptr,
+                                   phase ? static_cast<char*>(phase) + (size_t)f0 * bins * os : nullptr,
+                                   peaks ? static_cast<char*>(peaks) + (size_t)f0 * pk : nullptr);
+    if (rcs[(size_t)i]) errs[(size_t)i] = g_err;  // the message lives in this worker's thread-local slot
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i) th.emplace_back(work, i);
+  {
+    // the calling thread serves device 0; its affinity is restored afterwards
+#ifndef PDSP_EMU
+    cpu_set_t saved;
+    const bool have = sched_getaffinity(0, sizeof saved, &saved) == 0;
+#endif
+    work(0);
+#ifndef PDSP_EMU
+    if (have) sched_setaffinity(0, sizeof saved, &saved);
+#endif
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rcs[(size_t)i]) {
+      g_err = errs[(size_t)i];
+      return 1;
+    }
+  return 0;
+}
+
+// Device-resident sharded form.  Device i holds its block's samples at d_samples[i] (frame f of the block at f*hop) and
+// receives its outputs in d_amplitude[i] / d_phase[i] (block-local rows; entries or the arrays themselves may be NULL).
+// d_peaks[i] is device i's GATHER buffer, desc->batch records long: every device's kernel writes its block's records into
+// all of them (peer stores over NVLink fused into the kernel's finishing loop), so after pdsp_group_sync each device holds
+// the peaks of ALL frames.  gather_root >= 0: amplitude / phase rows of all blocks are also copied into
+// d_amplitude_all / d_phase_all (desc->batch rows, on device gather_root) by peer DMA queued behind each block's kernel.
+PDSP_EXPORT int pdsp_group_spectrum_dev(pdsp_group* g, int32_t size, int precision, const pdsp_spectrum_desc* d,
+                                        const void* const* d_samples, void* const* d_amplitude, void* const* d_phase,
+                                        void* const* d_peaks, int gather_root, void* d_amplitude_all, void* d_phase_all) {
+  if (!g || !d || !d_samples) return fail("null argument");
+  const int n = (int)g->ctx.size();
+  if (gather_root >= n) return fail("gather root %d out of range (%d devices)", gather_root, n);
+  if (gather_root >= 0 && ((d_amplitude_all && !d_amplitude) || (d_phase_all && !d_phase)))
+    return fail("a row gather needs the per-device row buffers it copies from");
+  std::vector<pdsp_plan*> plans((size_t)n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (pdsp_plan_get(g->ctx[(size_t)i], size, precision, &plans[(size_t)i])) return 1;
+  if (check_desc(plans[0], d)) return 1;
+  if (d->batch == 0) return 0;
+  if (d_peaks && size == 1) return fail("the fused peak gather needs an FFT size of at least 2");
+  const int bins = d->sides == PDSP_SIDES_TWO ? size : size / 2 + 1;
+  const size_t os = esize(precision);
+  const size_t pk = precision == PDSP_F64 ? sizeof(pdsp_peak_f64) : sizeof(pdsp_peak_f32);
+  void* peers[8] = {nullptr};
+  if (d_peaks)
+    for (int i = 0; i < n; ++i) {
+      if (!d_peaks[i]) return fail("null gather buffer for device %d", i);
+      peers[i] = d_peaks[i];
+    }
+  for (int i = 0; i < n; ++i) {
+    long long f0, nf;
+    group_block(d->batch, n, i, &f0, &nf);
+    if (nf <= 0) continue;
+    pdsp_ctx* c = g->ctx[(size_t)i];
+    if (set_device(c)) return 1;
+    if (!d_samples[i] && d->frame_len > 0) return fail("null samples for device %d", i);
+    pdsp_spectrum_desc dd = *d;
+    dd.batch = nf;
+    void* amp = d_amplitude ? d_amplitude[i] : nullptr;
+    void* ph = d_phase ? d_phase[i] : nullptr;
+    // the block's own segment of its gather buffer doubles as the kernel's local record workspace
+    void* local = d_peaks ? static_cast<char*>(d_peaks[i]) + (size_t)f0 * pk : nullptr;
+    PeerSpec ps{peers, n, f0};
+    // the kernel writes record f of the block to peer[g] + (offset + f): `local` is that same address on this device,
+    // so the self-entry is dropped from the peer list (no duplicate store)
+    void* others[8];
+    int no = 0;
+    for (int k = 0; k < n; ++k)
+      if (k != i) others[no++] = peers[k];
+    ps.ptrs = others;
+    ps.n = d_peaks ? no : 0;
+    if (launch_spectrum(plans[(size_t)i], &dd, d_samples[i], nf, amp, ph, local, nullptr, nullptr, 0, c->stream, d_peaks ? &ps : nullptr))
+      return 1;
+    if (gather_root >= 0) {
+      const int root_dev = g->ctx[(size_t)gather_root]->device;
+      if (d_amplitude_all && amp)
+        CU(cudaMemcpyPeerAsync(static_cast<char*>(d_amplitude_all) + (size_t)f0 * bins * os, root_dev, amp, c->device,
+                               (size_t)nf * bins * os, c->stream));
+      if (d_phase_all && ph)
+        CU(cudaMemcpyPeerAsync(static_cast<char*>(d_phase_all) + (size_t)f0 * bins * os, root_dev, ph, c->device,
+                               (size_t)nf * bins * os, c->stream));
+    }
+  }
+  return 0;
+}
+// waits for everything queued on the group's context streams
+PDSP_EXPORT int pdsp_group_sync(pdsp_group* g) {
+  if (!g) return fail("null argument");
+  for (pdsp_ctx* c : g->ctx) {
+    if (set_device(c)) return 1;
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }

@@ -37,7 +37,8 @@ PEAK64 = np.dtype([("index", "<i4"), ("_pad", "<i4"), ("frequency", "<f8"), ("am
 PEAK32 = np.dtype([("index", "<i4"), ("frequency", "<f4"), ("amplitude", "<f4"), ("phase", "<f4")])
 
 _lib = None
-_CXX = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-DPDSP_EMU=1", "-I", _HERE]
+_CXX = ["/usr/bin/g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-DPDSP_EMU=1", "-I", _HERE] + \
+       os.environ.get("PDSP_EMU_EXTRA", "").split()  # e.g. -DPDSP_DERIVE_MID=1 to run an experiment switch under the emulator
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 
 

@@ -13,6 +13,7 @@ typedef enum {
   cudaErrorInvalidValue = 1,
   cudaErrorInvalidDevice = 101,
   cudaErrorNotReady = 600,
+  cudaErrorPeerAccessAlreadyEnabled = 704,
   cudaErrorLaunchOutOfResources = 701
 } cudaError_t;
 typedef struct pdsp_stub_stream* cudaStream_t;
@@ -44,6 +45,10 @@ cudaError_t cudaStreamQuery(cudaStream_t s);
 cudaError_t cudaEventQuery(cudaEvent_t e);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);
+cudaError_t cudaDeviceCanAccessPeer(int* can, int dev, int peer);
+cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
+cudaError_t cudaMemcpyPeerAsync(void* dst, int dst_dev, const void* src, int src_dev, size_t bytes, cudaStream_t s);
+cudaError_t cudaDeviceGetPCIBusId(char* id, int len, int dev);
 cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
                               cudaStream_t s);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);

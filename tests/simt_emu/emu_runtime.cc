@@ -1,5 +1,7 @@
 // emu_runtime.cc - host SIMT emulator runtime + CUDA runtime stub (TEST ONLY, see simt.h / cuda_stub.h).
 // One OS thread per CUDA thread of a CTA; CTAs run one after another.
+#include <stdio.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <map>
@@ -143,11 +145,30 @@ std::set<void*> g_device;
 std::atomic<long long> g_h2d{0}, g_d2h{0};
 }  // namespace
 
+// PDSP_STUB_DEVICES=n pretends to have n devices (all of them this host's memory): lets the multi-device group API run
+static int stub_devices() {
+  const char* e = getenv("PDSP_STUB_DEVICES");
+  const int n = e ? atoi(e) : 1;
+  return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
 cudaError_t cudaGetDeviceCount(int* n) {
-  *n = 1;
+  *n = stub_devices();
   return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaSetDevice(int d) { return d >= 0 && d < stub_devices() ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
+  *can = 1;
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaMemcpyPeerAsync(void* dst, int, const void* src, int, size_t bytes, cudaStream_t) {
+  memcpy(dst, src, bytes);
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceGetPCIBusId(char* id, int len, int dev) {
+  snprintf(id, (size_t)len, "0000:%02x:00.0", dev);
+  return cudaSuccess;
+}
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   p->major = 10;
   p->minor = 0;

@@ -427,6 +427,51 @@ def test_single_call_fast_lane_emulated(emu_api, tune):
     assert ctx.fast_call_count == f1
 
 
+def test_device_group_emulated(emu_api, monkeypatch):
+    """pdsp_group_* with two pretend devices (PDSP_STUB_DEVICES: both are this host's memory): the host-sharded form
+    returns exactly what one device returns; the device-resident form leaves ALL peak records in EVERY device's gather
+    buffer (fused peer stores) and the root's row buffers hold every block's amplitude / phase rows."""
+    from pragma_dsp_b200 import DeviceGroup, spectrum_batch
+    from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
+    from pragma_dsp_b200.group import block_of
+    monkeypatch.setenv("PDSP_STUB_DEVICES", "2")
+    rng = np.random.default_rng(61)
+    n, batch = 1024, 11  # blocks of 6 and 5 frames
+    x = multitone(rng, batch, n)
+    ref = spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann")
+    with DeviceGroup([0, 1]) as grp:
+        got = grp.spectrum_batch(x, sampleRate=48000.0, fftSize=n, window="hann")
+        for key in ("amplitude", "phase"):
+            assert np.array_equal(got[key], ref[key]), key
+        assert (got["peaks"] == ref["peaks"]).all()
+        # STFT addressing across the block boundary (hop < N: the second block starts inside the first block's samples)
+        s = multitone(rng, 1, 10 * 256 + n)[0]
+        a = grp.spectrum_batch(s, sampleRate=48000.0, fftSize=n, window="hann", frameLen=n, hop=256, batch=11, outputs=("amplitude",))
+        b = spectrum_batch(s, sampleRate=48000.0, fftSize=n, window="hann", frameLen=n, hop=256, batch=11, outputs=("amplitude",))
+        assert np.array_equal(a["amplitude"], b["amplitude"])
+        # device-resident: "device" memory is host memory under the stub
+        bins = n // 2 + 1
+        blocks = [block_of(batch, 2, i) for i in range(2)]
+        d_x = [np.ascontiguousarray(x[f0:f0 + nf]) for f0, nf in blocks]
+        d_amp = [np.empty((nf, bins)) for _, nf in blocks]
+        d_ph = [np.empty((nf, bins)) for _, nf in blocks]
+        d_pk = [np.zeros(batch, dtype=PEAK_F64) for _ in blocks]
+        amp_all, ph_all = np.empty((batch, bins)), np.empty((batch, bins))
+        desc = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
+                            sample_rate=48000.0, raw_magnitude=0, fft_shift=0)
+        ptr = lambda arrs: [a_.ctypes.data for a_ in arrs]  # noqa: E731
+        grp.spectrum_dev(n, F64, desc, ptr(d_x), ptr(d_amp), ptr(d_ph), ptr(d_pk), gather_root=1,
+                         d_amplitude_all=amp_all.ctypes.data, d_phase_all=ph_all.ctypes.data)
+        grp.sync()
+        for i in range(2):
+            assert (d_pk[i] == ref["peaks"]).all(), i            # every device holds every frame's record
+        assert np.array_equal(amp_all, ref["amplitude"]) and np.array_equal(ph_all, ref["phase"])
+        with pytest.raises(Exception, match="out of range"):
+            grp.spectrum_dev(n, F64, desc, ptr(d_x), None, None, ptr(d_pk), gather_root=2)
+    with pytest.raises(Exception, match="listed twice"):
+        DeviceGroup([0, 0])
+
+
 def test_fused_peer_scatter_emulated(emu_api):
     """pdsp_spectrum_dev_gather on the emulated library: two 'peer' buffers receive every record."""
     from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc
