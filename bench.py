@@ -566,6 +566,43 @@ def run_b200(args, w):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt[0])
     e2e_fps = e2e_frames * world * e2e_steps / e2e_s
+    e2e_api = "pdsp_spectrum (host pinned buffers)"
+    e2e_per_rank = None
+    if world > 1 and hop == n and not args.quick:
+        # N GPUs through ONE host call: rank 0 drives all of the box's GPUs with the library's device group
+        # (pdsp_group_spectrum: one block of frames per device, each through its device's staging pipeline on a NUMA-pinned
+        # host thread) while the other ranks wait.  This is what a user of the library calls; the per-rank figure above
+        # (N processes, one pdsp_spectrum each) is kept beside it.
+        e2e_per_rank = {"value": e2e_fps, "api": "N processes x pdsp_spectrum, concurrently"}
+        barrier()
+        if rank == 0:
+            from pragma_dsp_b200 import DeviceGroup
+            gx = torch.empty((world * e2e_frames, n), dtype=sdt).pin_memory()
+            for r_ in range(world):
+                gx[r_ * e2e_frames:(r_ + 1) * e2e_frames].copy_(hx)
+            g_amp = torch.empty((world * e2e_frames, bins), dtype=tdt).pin_memory() if "amplitude" in outs else None
+            g_ph = torch.empty((world * e2e_frames, bins), dtype=tdt).pin_memory() if "phase" in outs else None
+            g_pk = torch.empty((world * e2e_frames, pk_bytes), dtype=torch.uint8).pin_memory() if want_peak else None
+            gdesc = SpectrumDesc(sample_dtype=desc.sample_dtype, frame_len=n, hop=hop, batch=world * e2e_frames, window=desc.window,
+                                 sides=desc.sides, sample_rate=48000.0, raw_magnitude=0)
+            grp = DeviceGroup(list(range(world)))
+            dp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+
+            def group_step():
+                check(L.pdsp_group_spectrum(grp._h, n, prec, C.byref(gdesc), dp(gx), dp(g_amp), dp(g_ph), dp(g_pk)))
+            for _ in range(2):
+                group_step()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                group_step()
+            g_s = time.perf_counter() - t0
+            grp.close()
+            g_fps = world * e2e_frames * e2e_steps / g_s
+            if h_amp is not None:  # the blocks were copies of rank 0's batch: same results expected in every block
+                assert torch.equal(g_amp[:e2e_frames], g_amp[(world - 1) * e2e_frames:]), "group blocks disagree"
+            e2e_fps, e2e_api = g_fps, "pdsp_group_spectrum (one host call, all GPUs, host pinned buffers)"
+            del gx, g_amp, g_ph, g_pk
+        barrier()
 
     # ---- ingestion ring: 65,536 of the frames pushed in blocks of 256 from pageable memory, results
     # popped in order - what a frame-at-a-time source (spectrumStream) sees
@@ -666,8 +703,10 @@ def run_b200(args, w):
                          "timed": f"CUDA events around each of the {args.steps} launches of the timed region, mean"},
             "burst": burst,
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "frames_per_step": e2e_frames, "api": "pdsp_spectrum (host pinned buffers)"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d * (world if e2e_per_rank else 1),
+                    "d2h_bytes_per_step": d2h * (world if e2e_per_rank else 1),
+                    "steps": e2e_steps, "frames_per_step": e2e_frames * (world if e2e_per_rank else 1), "api": e2e_api,
+                    "per_rank_processes": e2e_per_rank},
             "ingest": ingest,
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None,
@@ -850,6 +889,11 @@ def run_b200_latency(args, w):
             fn()
         return (time.perf_counter() - t0) / k * 1e6
 
+    ping_us = time_calls(lambda: check(L.pdsp_ctx_ping(ctx.h)), calls)  # empty launch + doorbell: the floor
+    ctx.tune("doorbell", 0)  # the same with a stream synchronisation instead of the doorbell
+    ping_sync_us = time_calls(lambda: check(L.pdsp_ctx_ping(ctx.h)), calls)
+    fwd_sync_us = time_calls(lambda: check(L.pdsp_fft_forward_real(plan, vp(x), F64, 1, vp(ore), vp(oim))), calls)
+    ctx.tune("doorbell", None)
     fwd_us = time_calls(lambda: check(L.pdsp_fft_forward_real(plan, vp(x), F64, 1, vp(ore), vp(oim))), calls)
     bins = n // 2 + 1
     amp, ph, pk = np.empty(bins), np.empty(bins), np.zeros(1, dtype=PEAK_F64)
@@ -881,7 +925,8 @@ def run_b200_latency(args, w):
         "metric": "us_per_call", "value": fwd_us, "unit": "us", "n_gpus": 1, "steps": calls, "warmup": max(10, args.warmup * 4),
         "ms_per_step": fwd_us / 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": args.workload, "description": w["desc"], "fft_size": n},
-        "latency": {"Radix2Fft.forward_us": fwd_us, "spectrum_us": spec_us, "cpu_port_forward_us": cpu_fwd_us,
+        "latency": {"empty_launch_and_doorbell_us": ping_us, "empty_launch_and_stream_sync_us": ping_sync_us,
+                    "Radix2Fft.forward_stream_sync_us": fwd_sync_us, "Radix2Fft.forward_us": fwd_us, "spectrum_us": spec_us, "cpu_port_forward_us": cpu_fwd_us,
                     "cpu_port_spectrum_us": cpu_spec_us, "gpu_overtakes_cpu_at_frames_per_call": cross,
                     "cpu_port_us_per_frame_batched": per_frame_cpu, "by_batch": table,
                     "api": "pdsp_fft_forward_real / pdsp_spectrum, pageable host arrays, one call = H2D + kernel + D2H + sync"},

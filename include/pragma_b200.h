@@ -69,7 +69,7 @@ int pdsp_ctx_destroy(pdsp_ctx* ctx);
 int pdsp_ctx_sync(pdsp_ctx* ctx);
 int pdsp_ctx_device(const pdsp_ctx* ctx);
 /* Tuning / test hook: sets one tunable of the context ("staged", "chunk_bytes", "big_tma", "big_interleave",
- * "big_prefetch", "big_chunk", "big_factors", "big_resident", "fast", "copy_threads", "variant"); value NULL or "" restores the default.  The same
+ * "big_prefetch", "big_chunk", "big_factors", "big_resident", "fast", "doorbell", "copy_threads", "big_v2", "variant"); value NULL or "" restores the default.  The same
  * tunables are read ONCE from the environment (PDSP_<KEY>) when the context is created; nothing on the launch
  * path reads the environment.  Results do not depend on them (parity tests run every setting). */
 int pdsp_ctx_tune(pdsp_ctx* ctx, const char* key, const char* value);
@@ -79,6 +79,8 @@ int64_t pdsp_ctx_launch_count(const pdsp_ctx* ctx);
 /* number of host calls served by the single-call fast lane (small jobs: one launch through a host-mapped pinned
  * buffer, completion by doorbell; see "host entry points" above) */
 int64_t pdsp_ctx_fast_call_count(const pdsp_ctx* ctx);
+/* an empty launch through the fast lane (launch + doorbell round trip): the floor under any one-frame call's latency */
+int pdsp_ctx_ping(pdsp_ctx* ctx);
 
 /* ---- pure host helpers (no device work) -------------------------------------------------- */
 /* src/core/fft.ts:16 isPowerOfTwo, :18-23 nextPowerOfTwo */

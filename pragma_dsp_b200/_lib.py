@@ -46,6 +46,7 @@ SYMBOLS = {
     "pdsp_ctx_sm_count": (C.c_int, [_vp]),
     "pdsp_ctx_launch_count": (_i64, [_vp]),
     "pdsp_ctx_fast_call_count": (_i64, [_vp]),
+    "pdsp_ctx_ping": (C.c_int, [_vp]),
     "pdsp_is_power_of_two": (C.c_int, [_i32]),
     "pdsp_next_power_of_two": (_i32, [_i32]),
     "pdsp_create_window": (C.c_int, [C.c_int, _i32, _dp]),

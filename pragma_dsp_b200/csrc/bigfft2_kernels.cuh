@@ -42,6 +42,8 @@ struct BigTileParams {
   int swap_in, swap_out;  // inverse transform = swap(FFT(swap(x))) / N
   double scale;
   int has_im;  // planar input with an imaginary plane (0: real input, zeros)
+  int l2_prefetch;  // 1: pull the CTA's next tile into L2 while the current one is transformed (the mbarrier wait on
+                    // the tile load was half of all stall samples without it: profiles/r2/ncu_digest_c4_2e24.txt)
 };
 
 // IO bit 0: input is the interleaved work buffer; bit 1: output is; bit 2: last pass (row tile in, transposed box out)
@@ -90,6 +92,17 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
           if (!IN_CPLX && p.has_im) simt::tma_load_3d(base + PLANE + (size_t)j * p.in_box_bytes, &tm_in_im, co[0], co[1], co[2], bar);
           co[p.in_box_dim] += p.in_box_step;
         }
+        if (p.l2_prefetch && w + simt::nblocks() < total) {
+          const long long w2 = w + simt::nblocks();
+          const long long fb2 = w2 / p.n_groups, g2 = w2 % p.n_groups;
+          const long long h2 = g2 / p.n_lo, l2 = g2 % p.n_lo;
+          for (int d = 0; d < 3; ++d) co[d] = (int)(l2 * p.in_lo[d] + h2 * p.in_hi[d] + fb2 * p.in_fr[d]);
+          for (int j = 0; j < p.in_boxes; ++j) {
+            simt::tma_prefetch_3d(&tm_in_re, co[0], co[1], co[2]);
+            if (!IN_CPLX && p.has_im) simt::tma_prefetch_3d(&tm_in_im, co[0], co[1], co[2]);
+            co[p.in_box_dim] += p.in_box_step;
+          }
+        }
       }
       simt::mbar_wait(bar, phase);
       phase ^= 1u;
@@ -131,6 +144,19 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
       }
       simt::sync_block();
       static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[E::pad(t + TF * decltype(q)::value)]; });
+      if (p.l2_prefetch && w + simt::nblocks() < total && tid < C) {
+        // the next tile's rows (C runs of L contiguous elements), one bulk L2 prefetch per row
+        const long long w2 = w + simt::nblocks();
+        const long long fb2 = w2 / p.n_groups, g2 = w2 % p.n_groups;
+        const long long a2 = fb2 * p.in_frame + (g2 / p.n_lo) * p.in_g_hi + (g2 % p.n_lo) * p.in_g_lo + tid * p.in_c;
+        const unsigned row_bytes = (unsigned)(L * sizeof(T)) * (IN_CPLX ? 2u : 1u);
+        if constexpr (IN_CPLX) {
+          simt::prefetch_l2_bulk(icx + a2, row_bytes);
+        } else {
+          simt::prefetch_l2_bulk(ire + a2, row_bytes);
+          if (iim != nullptr) simt::prefetch_l2_bulk(iim + a2, row_bytes);
+        }
+      }
       simt::sync_block();
     }
 

@@ -139,6 +139,20 @@ constexpr double cos16(int k) {
 constexpr double w32_re(int K) { return K <= 8 ? cos16(K) : -cos16(16 - K); }
 constexpr double w32_im(int K) { return K <= 8 ? -cos16(8 - K) : -cos16(K - 8); }
 
+#if defined(__CUDACC__) && !defined(PDSP_EMU)
+// fp32: the 32nd roots of unity as operand pairs in the constant bank - (wr, wi) and (-wi, wr) - so that a packed complex
+// multiply by a compile-time root is FMUL2 + FFMA2 with c[][] operands.  As immediates every use had to assemble both
+// 64-bit pairs in registers first (MOV pairs: 45 of ~700 warp instructions per frame in the fp32 N = 1024 kernel).
+#define PDSP_W32F(K) {{(float)w32_re(K), (float)w32_im(K)}, {-(float)w32_im(K), (float)w32_re(K)}}
+static __constant__ float2 kW32f[16][2] = {PDSP_W32F(0),  PDSP_W32F(1),  PDSP_W32F(2),  PDSP_W32F(3), PDSP_W32F(4),  PDSP_W32F(5),
+                                           PDSP_W32F(6),  PDSP_W32F(7),  PDSP_W32F(8),  PDSP_W32F(9), PDSP_W32F(10), PDSP_W32F(11),
+                                           PDSP_W32F(12), PDSP_W32F(13), PDSP_W32F(14), PDSP_W32F(15)};
+#undef PDSP_W32F
+#endif
+#ifndef PDSP_F32_CONST_TWIDDLES
+#define PDSP_F32_CONST_TWIDDLES 1
+#endif
+
 // d * W32^K with the trivial cases folded
 template <int K, typename T>
 PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
@@ -148,10 +162,14 @@ PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
   } else if constexpr (K == 8) {  // -i
     return cx<T>{d.y, -d.x};
   } else if constexpr (sizeof(T) == 4) {
-    // fp32: every non-trivial constant twiddle is one packed multiply + one packed fma (cmul overload)
+    // fp32: every non-trivial constant twiddle is one packed multiply + one packed fma
+#if defined(__CUDACC__) && !defined(PDSP_EMU) && PDSP_F32_CONST_TWIDDLES
+    return as_cx(__ffma2_rn(make_float2(d.x, d.x), kW32f[K][0], __fmul2_rn(make_float2(d.y, d.y), kW32f[K][1])));
+#else
     constexpr T wr = (T)w32_re(K);
     constexpr T wi = (T)w32_im(K);
     return cmul(d, cx<T>{wr, wi});
+#endif
   } else if constexpr (K == 4) {  // (1-i)/sqrt2
     constexpr T c = (T)cos16(4);
     return cx<T>{(d.x + d.y) * c, (d.y - d.x) * c};

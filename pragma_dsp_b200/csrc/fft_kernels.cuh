@@ -41,12 +41,14 @@ struct Doorbell {
 };
 PDSP_DEVICE void ring_doorbell(const Doorbell& d) {
   if (d.flag == nullptr) return;
-  simt::fence_system();
+  simt::fence_system();  // this thread's results are visible to the host before anything ordered after the barrier
   simt::sync_block();
   if (simt::tid() == 0) {
-    if (simt::atomic_add(d.count, 1u) == (unsigned)simt::nblocks() - 1u) {
-      *d.count = 0u;
-      simt::fence_system();
+    // one-CTA launches (a single frame) ring at once; otherwise the CTA that completes the count does.  Every CTA's
+    // fence precedes its increment, so when the last increment is observed all results are out (fence cumulativity).
+    const unsigned nb = (unsigned)simt::nblocks();
+    if (nb == 1u || simt::atomic_add(d.count, 1u) == nb - 1u) {
+      if (nb != 1u) *d.count = 0u;  // device memory, next used by a later launch on the same stream
       simt::store_volatile(d.flag, d.seq);
     }
   }

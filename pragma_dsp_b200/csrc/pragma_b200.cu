@@ -79,6 +79,7 @@ struct Tune {
   int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
   int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
+  int doorbell = 1;           // PDSP_DOORBELL: 0 = the fast lane waits with cudaStreamSynchronize instead of the in-kernel doorbell
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
 };
 static int tune_set(Tune& t, const char* key, const char* val) {
@@ -111,6 +112,8 @@ static int tune_set(Tune& t, const char* key, const char* val) {
     t.big_v2 = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
+  } else if (!strcmp(key, "doorbell")) {
+    t.doorbell = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "copy_threads")) {
     t.copy_threads = unset ? 3 : (atoi(v) < 0 ? 0 : atoi(v));
   } else {
@@ -123,7 +126,7 @@ static void tune_from_env(Tune& t) {
                                         {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
                                         {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
                                         {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
-                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}};
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}, {"doorbell", "PDSP_DOORBELL"}};
   for (auto& k : keys)
     if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
@@ -1020,6 +1023,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       void* out_re = last ? (void*)gre : wk->re;
       void* out_im = last ? (void*)gim : (il ? nullptr : wk->im);
       p.has_im = in_im != nullptr ? 1 : 0;
+      p.l2_prefetch = c->tune.big_prefetch;
       int io;
       if (!last) {
         // view [nf*O][L][I]: tile = C adjacent columns (box {C, BR, 1}, L / BR boxes down the transformed axis)
@@ -1571,6 +1575,7 @@ static int fast_init(pdsp_ctx* c) {
 }
 static Doorbell fast_door(pdsp_ctx* c) {
   FastLane& f = c->fast;
+  if (!c->tune.doorbell) return Doorbell{nullptr, nullptr, 0};
   ++f.seq;
   if (f.seq == 0) f.seq = 1;
   return Doorbell{reinterpret_cast<unsigned*>(f.d + kFastBytes), f.d_count, f.seq};
@@ -1578,7 +1583,7 @@ static Doorbell fast_door(pdsp_ctx* c) {
 // Waits for the launch that carries doorbell `seq` (door_used), or for the lane's stream otherwise.
 static int fast_wait(pdsp_ctx* c, bool door_used) {
   FastLane& f = c->fast;
-  if (!door_used) {
+  if (!door_used || !c->tune.doorbell) {
     CU(cudaStreamSynchronize(f.stream));
     return 0;
   }
@@ -1600,6 +1605,20 @@ static int fast_wait(pdsp_ctx* c, bool door_used) {
   }
   std::atomic_thread_fence(std::memory_order_acquire);
   return 0;
+}
+
+// An empty launch through the fast lane: what a one-frame call costs before any transform work (launch latency +
+// doorbell over PCIe).  bench.py's c1 workload reports it next to the call latencies.
+PDSP_GLOBAL void k_ping(const Doorbell door) { ring_doorbell(door); }
+PDSP_EXPORT int pdsp_ctx_ping(pdsp_ctx* c) {
+  if (!c) return fail("null context");
+  if (set_device(c)) return 1;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const Doorbell door = fast_door(c);
+  PDSP_LAUNCH(k_ping, 1, 32, 0, c->fast.stream, door);
+  CU(cudaGetLastError());
+  c->launches++;
+  return fast_wait(c, true);
 }
 
 // ---- host-buffer spectrum: chunked, pipelined over kSlots streams

@@ -83,6 +83,9 @@ PDSP_DEVICE void tma_store_3d(const TensorMap* map, int x, int y, int z, const v
                "r"(smem_u32(smem_src))
                : "memory");
 }
+PDSP_DEVICE void tma_prefetch_3d(const TensorMap* map, int x, int y, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
 PDSP_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 PDSP_DEVICE void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 PDSP_DEVICE void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -242,6 +245,7 @@ inline void tma_store_3d(const TensorMap* m, int x, int y, int z, const void* sm
                  (size_t)m->esize);
       }
 }
+inline void tma_prefetch_3d(const TensorMap*, int, int, int) {}
 inline void bulk_commit() {}
 inline void bulk_wait_read() {}
 inline void bulk_wait_all() {}

@@ -13,6 +13,9 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from pragma_dsp_b200 import _lib  # noqa: E402
+
+if os.environ.get("PDSP_LIB"):  # time another build of the library (scripts/build_exp.sh)
+    _lib.LIB_PATH = os.path.abspath(os.environ["PDSP_LIB"])
 from pragma_dsp_b200._lib import F64, check, lib  # noqa: E402
 
 ctx = _lib.Context(0)
@@ -21,9 +24,11 @@ peak, _ = bench.measured_hbm_peak()
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev)
 vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-cases = [(20, 8), (24, 1), (22, 2), (16, 64)]
-settings = [dict(big_v2=0), dict(big_v2=1), dict(big_v2=1, big_chunk=1), dict(big_v2=1, big_chunk=2), dict(big_v2=1, big_chunk=4),
-            dict(big_v2=1, big_interleave=0), dict(big_v2=0, big_chunk=1)]
+cases = [(20, 8), (24, 1), (22, 2), (16, 64), (18, 16)]
+settings = [dict(), dict(big_v2=0), dict(big_v2=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
+if "--only20" in sys.argv:
+    cases = [(20, 8)]
+    settings = [dict(big_v2=0), dict(big_v2=0, big_chunk=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
 for log2n, frames in cases:
     n = 1 << log2n
     plan = ctx.plan(n, F64)
