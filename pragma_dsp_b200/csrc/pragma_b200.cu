@@ -76,7 +76,7 @@ struct Tune {
   int n_big_factors = 0;
   long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
   int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
-  int big_resident = -1;      // PDSP_BIG_RESIDENT: -1 auto, 0 / 1 keep inter-pass data L2-resident (per-transform passes)
+  int big_resident = -1;      // PDSP_BIG_RESIDENT: three-pass transforms, passes 1+2 in L2-sized k1 groups: -1 / 1 automatic, 0 off, n > 1 blocks per group
   int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int doorbell = 1;           // PDSP_DOORBELL: 0 = the fast lane waits with cudaStreamSynchronize instead of the in-kernel doorbell
@@ -107,7 +107,7 @@ static int tune_set(Tune& t, const char* key, const char* val) {
   } else if (!strcmp(key, "staged")) {
     t.staged = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_resident")) {
-    t.big_resident = unset ? -1 : (v[0] != '0');
+    t.big_resident = unset ? -1 : atoi(v);  // 0 off, 1 on (automatic group size), > 1: k1 blocks per group
   } else if (!strcmp(key, "big_v2")) {
     t.big_v2 = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
@@ -953,6 +953,91 @@ static int make_tensor_map3(simt::TensorMap* tm, const void* base, bool f64, con
 #endif
 }
 
+// One pass of the second-generation path (bigfft2_kernels.cuh) over `nf` transforms whose planes start at the given
+// pointers.  k_cnt > 0 (three-pass plans, passes 1 and 2, nf == 1) restricts the pass to the k1 range [k0, k0 + k_cnt):
+// the caller then runs passes 1 and 2 group by group so that a group's work-buffer slice never leaves the L2.
+static int launch_pass_v2(pdsp_plan* pl, BigPlan* bp, int j, long long O, long long I, long long nf, const void* in_re,
+                          const void* in_im, bool in_cplx, void* out_re, void* out_im, bool out_cplx, int inverse,
+                          const LaunchCtx& lc, long long k0, long long k_cnt) {
+  pdsp_ctx* c = pl->ctx;
+  const bool f64 = pl->precision == PDSP_F64;
+  const size_t es = esize(pl->precision);
+  const long long N = 1LL << pl->log2n;
+  const int np = bp->npass;
+  long long Ls[3] = {1, 1, 1};
+  for (int k = 0; k < np; ++k) Ls[k] = 1LL << bp->lg[k];
+  const long long L = Ls[j];
+  const int C = big2_pass_c(bp->lg[j]);
+  const bool last = j == np - 1;
+  const int BR = (int)(L < 256 ? L : 256);
+  BigTileParams p;
+  memset(&p, 0, sizeof p);
+  simt::TensorMap maps[4];
+  p.n_frames = nf;
+  p.swap_in = (j == 0 && inverse) ? 1 : 0;
+  p.swap_out = (last && inverse) ? 1 : 0;
+  p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
+  p.has_im = in_im != nullptr ? 1 : 0;
+  p.l2_prefetch = c->tune.big_prefetch;
+  const size_t ies = es * (in_cplx ? 2 : 1), oes = es * (out_cplx ? 2 : 1);  // bytes per element of the in / out buffers
+  int io;
+  if (!last) {
+    // view [nf*O][L][I]: tile = C adjacent columns (box {C, BR, 1}, L / BR boxes down the transformed axis)
+    if (I % C) return fail("internal: pass %d of 2^%d has %lld columns, not a multiple of the tile width %d", j, pl->log2n, I, C);
+    p.n_lo = I / C;
+    const long long o_cnt = k_cnt > 0 ? k_cnt : O;
+    p.n_groups = o_cnt * p.n_lo;
+    p.tw_hi = bp->tw_hi[j];
+    p.tw_lo = bp->tw_lo[j];
+    p.log_b = bp->log_b[j];
+    const int wi = in_cplx ? 2 : 1, wo = out_cplx ? 2 : 1;  // scalars per element in the mapped buffer
+    const size_t skip = (size_t)k0 * (size_t)(L * I);      // elements before the first k1 block of the range
+    const char* bin_re = static_cast<const char*>(in_re) + skip * ies;
+    const char* bin_im = in_im ? static_cast<const char*>(in_im) + skip * ies : bin_re;
+    char* bout_re = static_cast<char*>(out_re) + skip * oes;
+    char* bout_im = out_im ? static_cast<char*>(out_im) + skip * oes : bout_re;
+    const long long din[3] = {wi * I, L, nf * o_cnt}, dout[3] = {wo * I, L, nf * o_cnt};
+    const int bin[3] = {wi * C, BR, 1}, bout[3] = {wo * C, BR, 1};
+    if (make_tensor_map3(&maps[0], bin_re, f64, din, wi * I, wi * I * L, bin)) return 1;
+    if (make_tensor_map3(&maps[1], bin_im, f64, din, wi * I, wi * I * L, bin)) return 1;
+    if (make_tensor_map3(&maps[2], bout_re, f64, dout, wo * I, wo * I * L, bout)) return 1;
+    if (make_tensor_map3(&maps[3], bout_im, f64, dout, wo * I, wo * I * L, bout)) return 1;
+    p.in_lo[0] = wi * C, p.in_hi[2] = 1, p.in_fr[2] = (int)o_cnt;
+    p.in_box_dim = 1, p.in_box_step = BR, p.in_boxes = (int)(L / BR);
+    p.in_box_bytes = (unsigned)(wi * C * BR * es);
+    p.out_lo[0] = wo * C, p.out_hi[2] = 1, p.out_fr[2] = (int)o_cnt;
+    p.out_box_dim = 1, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
+    p.out_box_bytes = (unsigned)(wo * C * BR * es);
+    io = (in_cplx ? 1 : 0) | (out_cplx ? 2 : 0);
+  } else {
+    // rows (k1[, k2]), L contiguous elements each; output X[k1 + L1*k2 (+ L1*L2*k3)]: view {L1, L2', nf*L}, box {C, 1, BR}
+    const long long L1 = Ls[0], L2 = np == 3 ? Ls[1] : 1;
+    const long long k1_cnt = k_cnt > 0 ? k_cnt : L1;
+    if (k1_cnt % C || k0 % C) return fail("internal: last pass of 2^%d: k1 range [%lld, +%lld) is not a multiple of the tile height %d", pl->log2n, k0, k1_cnt, C);
+    p.n_lo = L2;
+    p.n_groups = (k1_cnt / C) * L2;
+    p.in_re = static_cast<const char*>(in_re) + (size_t)k0 * (size_t)(L2 * L) * ies;
+    p.in_im = in_im ? static_cast<const char*>(in_im) + (size_t)k0 * (size_t)(L2 * L) * ies : nullptr;
+    p.in_frame = N;
+    p.in_g_hi = C * L2 * L;
+    p.in_g_lo = np == 3 ? L : 0;
+    p.in_c = L2 * L;
+    const long long dout[3] = {L1 - k0, L2, nf * L};
+    const int bout[3] = {C, 1, BR};
+    if (make_tensor_map3(&maps[2], static_cast<char*>(out_re) + (size_t)k0 * es, f64, dout, L1, L1 * L2, bout)) return 1;
+    if (make_tensor_map3(&maps[3], static_cast<char*>(out_im) + (size_t)k0 * es, f64, dout, L1, L1 * L2, bout)) return 1;
+    maps[0] = maps[2], maps[1] = maps[3];
+    p.out_lo[1] = 1, p.out_hi[0] = C, p.out_fr[2] = (int)L;
+    p.out_box_dim = 2, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
+    p.out_box_bytes = (unsigned)(C * BR * es);
+    io = 4 | (in_cplx ? 1 : 0);
+  }
+  const cudaError_t e = launch_big_tile(f64, bp->lg[j], io, p, maps, lc);
+  if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d, TMA tiles): %s", j, pl->log2n, cudaGetErrorString(e));
+  c->launches++;
+  return 0;
+}
+
 // Multi-pass transform.  Each pass runs on the generation that is faster for its length (both exchange the same work
 // buffer): the second (bigfft2_kernels.cuh: TMA box loads and box stores, two CTAs per SM, transposed box stores in the
 // last pass) wherever its tiles have rows of at least 64 bytes - passes of up to 256 points; measured 3-10 % ahead at
@@ -996,82 +1081,58 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
     char* gre = static_cast<char*>(d_ore) + (size_t)f0 * N * es;
     char* gim = static_cast<char*>(d_oim) + (size_t)f0 * N * es;
     long long O = 1, I = N;
+    // generation of each pass: tunable big_v2 = 0 / 1 forces the first / second (where TMA can take the shape at all)
+    bool pass_v2[3] = {false, false, false};
+    for (int j = 0; j < np; ++j) {
+      const int Cj = big2_pass_c(bp->lg[j]);
+      pass_v2[j] = v2_allowed && (size_t)Cj * es >= 16 && (c->tune.big_v2 < 0 ? (size_t)Cj * es >= 64 : c->tune.big_v2 != 0);
+    }
+    // Three-pass transforms whose work buffer exceeds the L2 (2^24: 256 MB): after pass 0, passes 1 and 2 run over GROUPS
+    // of k1 blocks - pass 1 writes a group's slice of the work buffer (<= 32 MB), pass 2 reads it back while it is still
+    // in the L2 and stores the final (transposed) output.  DRAM then sees the work buffer once between passes 0 and 1
+    // only: 4 x N*16 bytes instead of 6 (tunable big_resident = 0 restores the pass-by-pass schedule).
+    long long group = 0;
+    if (np == 3 && il && pass_v2[0] && pass_v2[1] && pass_v2[2] && c->tune.big_resident != 0) {
+      const size_t block = (size_t)Ls[1] * (size_t)Ls[2] * 2 * es;  // one k1 block of the interleaved work buffer
+      const long long c_last = big2_pass_c(bp->lg[2]);
+      long long g = c_last;
+      while (g * 2 <= Ls[0] && (size_t)(g * 2) * block <= ((size_t)32 << 20)) g *= 2;
+      if ((size_t)Ls[0] * block > ((size_t)64 << 20) && g < Ls[0] && Ls[0] % g == 0) group = g;
+      if (c->tune.big_resident > 1 && Ls[0] % c->tune.big_resident == 0 && c->tune.big_resident % c_last == 0)
+        group = c->tune.big_resident;  // explicit group size (k1 blocks)
+    }
+    if (group > 0) {
+      for (long long f = 0; f < nf; ++f) {
+        const char* xre = fre + (size_t)f * N * es;
+        const char* xim = fim ? fim + (size_t)f * N * es : nullptr;
+        char* yre = gre + (size_t)f * N * es;
+        char* yim = gim + (size_t)f * N * es;
+        char* wbuf = static_cast<char*>(wk->re) + (size_t)f * N * 2 * es;
+        const long long I0 = N / Ls[0], I1 = I0 / Ls[1];
+        if (launch_pass_v2(pl, bp, 0, 1, I0, 1, xre, xim, false, wbuf, nullptr, true, inverse, lc, 0, 0)) return 1;
+        for (long long k0 = 0; k0 < Ls[0]; k0 += group) {
+          if (launch_pass_v2(pl, bp, 1, Ls[0], I1, 1, wbuf, nullptr, true, wbuf, nullptr, true, inverse, lc, k0, group)) return 1;
+          if (launch_pass_v2(pl, bp, 2, Ls[0] * Ls[1], 1, 1, wbuf, nullptr, true, yre, yim, false, inverse, lc, k0, group)) return 1;
+        }
+      }
+      continue;
+    }
     for (int j = 0; j < np; ++j) {
       const long long L = Ls[j];
       I /= L;
-      const int C = big2_pass_c(bp->lg[j]);
       const bool last = j == np - 1;
-      // generation of this pass: tunable big_v2 = 0 / 1 forces the first / second (where TMA can take the shape at all)
-      const bool wide = (size_t)C * es >= 64;
-      const bool v2 = v2_allowed && (size_t)C * es >= 16 && (c->tune.big_v2 < 0 ? wide : c->tune.big_v2 != 0);
+      const bool v2 = pass_v2[j];
       if (!v2) {
         if (launch_pass_v1(pl, bp, wk, j, O, I, nf, fre, fim, gre, gim, inverse, lc)) return 1;
         O *= L;
         continue;
       }
       const bool in_cplx = il && j != 0, out_cplx = il && !last;
-      const int BR = (int)(L < 256 ? L : 256);
-      BigTileParams p;
-      memset(&p, 0, sizeof p);
-      simt::TensorMap maps[4];
-      p.n_frames = nf;
-      p.swap_in = (j == 0 && inverse) ? 1 : 0;
-      p.swap_out = (last && inverse) ? 1 : 0;
-      p.scale = (last && inverse) ? 1.0 / (double)N : 1.0;
       const void* in_re = j == 0 ? (const void*)fre : wk->re;
       const void* in_im = j == 0 ? (const void*)fim : (il ? nullptr : wk->im);
       void* out_re = last ? (void*)gre : wk->re;
       void* out_im = last ? (void*)gim : (il ? nullptr : wk->im);
-      p.has_im = in_im != nullptr ? 1 : 0;
-      p.l2_prefetch = c->tune.big_prefetch;
-      int io;
-      if (!last) {
-        // view [nf*O][L][I]: tile = C adjacent columns (box {C, BR, 1}, L / BR boxes down the transformed axis)
-        if (I % C) return fail("internal: pass %d of 2^%d has %lld columns, not a multiple of the tile width %d", j, pl->log2n, I, C);
-        p.n_lo = I / C;
-        p.n_groups = O * p.n_lo;
-        p.tw_hi = bp->tw_hi[j];
-        p.tw_lo = bp->tw_lo[j];
-        p.log_b = bp->log_b[j];
-        const int wi = in_cplx ? 2 : 1, wo = out_cplx ? 2 : 1;  // scalars per element in the mapped buffer
-        const long long din[3] = {wi * I, L, nf * O}, dout[3] = {wo * I, L, nf * O};
-        const int bin[3] = {wi * C, BR, 1}, bout[3] = {wo * C, BR, 1};
-        if (make_tensor_map3(&maps[0], in_re, f64, din, wi * I, wi * I * L, bin)) return 1;
-        if (make_tensor_map3(&maps[1], in_im ? in_im : in_re, f64, din, wi * I, wi * I * L, bin)) return 1;
-        if (make_tensor_map3(&maps[2], out_re, f64, dout, wo * I, wo * I * L, bout)) return 1;
-        if (make_tensor_map3(&maps[3], out_im ? out_im : out_re, f64, dout, wo * I, wo * I * L, bout)) return 1;
-        p.in_lo[0] = wi * C, p.in_hi[2] = 1, p.in_fr[2] = (int)O;
-        p.in_box_dim = 1, p.in_box_step = BR, p.in_boxes = (int)(L / BR);
-        p.in_box_bytes = (unsigned)(wi * C * BR * es);
-        p.out_lo[0] = wo * C, p.out_hi[2] = 1, p.out_fr[2] = (int)O;
-        p.out_box_dim = 1, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
-        p.out_box_bytes = (unsigned)(wo * C * BR * es);
-        io = (in_cplx ? 1 : 0) | (out_cplx ? 2 : 0);
-      } else {
-        // rows (k1[, k2]), L contiguous elements each; output X[k1 + L1*k2 (+ L1*L2*k3)]: view {L1, L2', nf*L}, box {C, 1, BR}
-        const long long L1 = Ls[0], L2 = np == 3 ? Ls[1] : 1;
-        if (L1 % C) return fail("internal: last pass of 2^%d: %lld rows, not a multiple of the tile height %d", pl->log2n, L1, C);
-        p.n_lo = L2;
-        p.n_groups = (L1 / C) * L2;
-        p.in_re = in_re;
-        p.in_im = in_im;
-        p.in_frame = N;
-        p.in_g_hi = C * L2 * L;
-        p.in_g_lo = np == 3 ? L : 0;
-        p.in_c = L2 * L;
-        const long long dout[3] = {L1, L2, nf * L};
-        const int bout[3] = {C, 1, BR};
-        if (make_tensor_map3(&maps[2], out_re, f64, dout, L1, L1 * L2, bout)) return 1;
-        if (make_tensor_map3(&maps[3], out_im, f64, dout, L1, L1 * L2, bout)) return 1;
-        maps[0] = maps[2], maps[1] = maps[3];
-        p.out_lo[1] = 1, p.out_hi[0] = C, p.out_fr[2] = (int)L;
-        p.out_box_dim = 2, p.out_box_step = BR, p.out_boxes = (int)(L / BR);
-        p.out_box_bytes = (unsigned)(C * BR * es);
-        io = 4 | (in_cplx ? 1 : 0);
-      }
-      const cudaError_t e = launch_big_tile(f64, bp->lg[j], io, p, maps, lc);
-      if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d, TMA tiles): %s", j, pl->log2n, cudaGetErrorString(e));
-      c->launches++;
+      if (launch_pass_v2(pl, bp, j, O, I, nf, in_re, in_im, in_cplx, out_re, out_im, out_cplx, inverse, lc, 0, 0)) return 1;
       O *= L;
     }
   }

@@ -178,6 +178,8 @@ def test_launch_and_plan_accounting(emu_api):
                                            ("7,6", 8192, {"big_interleave": "0"}),
                                            ("6,6,6", 1 << 18, {"big_interleave": "0"}),
                                            ("7,6", 8192, {"big_chunk": "1"}),
+                                           # three passes, passes 1 + 2 run over groups of 32 k1 blocks (the L2-resident schedule of 2^24)
+                                           ("6,6,6", 1 << 18, {"big_resident": "32"}),
                                            # first generation, its switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
                                            ("6,6", 4096, {"big_v2": "0"}),
                                            ("6,6,6", 1 << 18, {"big_v2": "0"}),
