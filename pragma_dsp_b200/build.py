@@ -70,7 +70,8 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True, tu
     objs = []
     units = [(os.path.join(CSRC, "pragma_b200.cu"), os.path.join(OBJ, "pragma_b200.o"), []),
              (os.path.join(CSRC, "bigfft.cu"), os.path.join(OBJ, "bigfft.o"), []),
-             (os.path.join(CSRC, "bigfft2.cu"), os.path.join(OBJ, "bigfft2.o"), [])]
+             (os.path.join(CSRC, "bigfft2.cu"), os.path.join(OBJ, "bigfft2.o"), []),
+             (os.path.join(CSRC, "bigfft3.cu"), os.path.join(OBJ, "bigfft3.o"), [])]
     for kind, ctype, lo, hi, name in groups():
         defs = [f"-DPDSP_INST_KIND={kind}", f"-DPDSP_INST_T={ctype}", f"-DPDSP_INST_LO={lo}", f"-DPDSP_INST_HI={hi}",
                 f"-DPDSP_INST_NAME={name}"]

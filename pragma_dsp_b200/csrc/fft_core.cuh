@@ -295,7 +295,11 @@ struct FftEngine {
   // large-N path), so every exchange is a __syncthreads.
   // after_smem(): called once, as soon as the frame's threads are done with the shared-memory buffer (after the last
   // exchange that goes through it, or straight away when there is none) - the staged kernels refill it from there.
-  template <bool BLOCKSYNC = false, class Hook = NoHook>
+  // SPLITX: the exchange buffer holds ONE scalar plane (T elements, same padded indexing): the real parts go through it
+  // first, then the imaginary parts - half the shared memory for two more barriers per exchange.  The large-FFT
+  // pipeline kernel (bigfft3_kernels.cuh) uses it to keep a whole second tile landing while the current one is
+  // transformed.  `sm` then points at the sequence's slot of T elements (passed as cx<T>* for one signature).
+  template <bool BLOCKSYNC = false, class Hook = NoHook, bool SPLITX = false>
   PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int slot,
                               int slots_per_cta, Hook after_smem = Hook{}) {
     if constexpr (last_smem_pass<BLOCKSYNC>() < 0) after_smem();
@@ -383,13 +387,40 @@ struct FftEngine {
             v[i] = h ? got : e;
             v[8 + i] = h ? o : got;
           });
+        } else if constexpr (SPLITX) {
+          // outputs stay in the registers their inputs came from until both planes have been exchanged below
+          static_for<0, R>([&](auto k) { v[u + decltype(k)::value * BPT] = a[bitrev(decltype(k)::value, b)]; });
         } else {
           const int base = ((j >> NSL) << (NSL + b)) + (j & (NS - 1));
           static_for<0, R>(
               [&](auto k) { sm[pad(base + (decltype(k)::value << NSL))] = a[bitrev(decltype(k)::value, b)]; });
         }
       });
-      if constexpr (!last && !SHUF) {
+      if constexpr (!last && !SHUF && SPLITX) {
+        T* PDSP_RESTRICT smt = reinterpret_cast<T*>(sm);
+        static_for<0, 2>([&](auto pl) {
+          constexpr bool IM = decltype(pl)::value == 1;
+          static_for<0, BPT>([&](auto ui) {
+            constexpr int u = decltype(ui)::value;
+            const int j = t + TF * u;
+            const int base = ((j >> NSL) << (NSL + b)) + (j & (NS - 1));
+            static_for<0, R>([&](auto k) {
+              const cx<T> o = v[u + decltype(k)::value * BPT];
+              smt[pad(base + (decltype(k)::value << NSL))] = IM ? o.y : o.x;
+            });
+          });
+          sync();
+          static_for<0, P>([&](auto q) {
+            const T g = smt[pad(t + TF * decltype(q)::value)];
+            if constexpr (IM)
+              v[decltype(q)::value].y = g;
+            else
+              v[decltype(q)::value].x = g;
+          });
+          sync();
+        });
+        if constexpr (pass == last_smem_pass<BLOCKSYNC>()) after_smem();
+      } else if constexpr (!last && !SHUF) {
         sync();
         static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
         sync();

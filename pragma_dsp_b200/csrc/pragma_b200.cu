@@ -49,6 +49,9 @@ cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, con
                                 const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
 // second generation (bigfft2.cu): TMA tile loads and stores
 int big2_pass_c(int log2l);
+bool big_pipe_supported(bool f64, int log2l);
+cudaError_t launch_big_pipe(bool f64, int log2l, bool last, const BigPassParams& p, const simt::TensorMap2D& tm_re,
+                            const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
 cudaError_t launch_big_tile(bool f64, int log2l, int io, const BigTileParams& p, const simt::TensorMap* maps, const LaunchCtx& lc);
 
 // tuning variants (inst_var.cu), one symbol per (type, variant): only in -DPDSP_TUNING builds
@@ -76,8 +79,9 @@ struct Tune {
   int n_big_factors = 0;
   long long chunk_bytes = 0;  // PDSP_CHUNK_BYTES: staging chunk size of the host pipeline (0 = default)
   int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
-  int big_resident = -1;      // PDSP_BIG_RESIDENT: three-pass transforms, passes 1+2 in L2-sized k1 groups: -1 / 1 automatic, 0 off, n > 1 blocks per group
+  int big_resident = -1;      // PDSP_BIG_RESIDENT: three-pass transforms, passes 1+2 in L2-sized k1 groups: -1 / 0 off (measured slower), 1 on (automatic group size), n > 1 blocks per group
   int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
+  int big_pipe = -1;          // PDSP_BIG_PIPE: third-generation (pipeline) large-FFT passes: -1 automatic (1024-point passes), 0 off, 1 every pass length it exists for (256 / 512 / 1024, fp64)
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int doorbell = 1;           // PDSP_DOORBELL: 0 = the fast lane waits with cudaStreamSynchronize instead of the in-kernel doorbell
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
@@ -110,6 +114,8 @@ static int tune_set(Tune& t, const char* key, const char* val) {
     t.big_resident = unset ? -1 : atoi(v);  // 0 off, 1 on (automatic group size), > 1: k1 blocks per group
   } else if (!strcmp(key, "big_v2")) {
     t.big_v2 = unset ? -1 : (v[0] != '0');
+  } else if (!strcmp(key, "big_pipe")) {
+    t.big_pipe = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "doorbell")) {
@@ -126,7 +132,7 @@ static void tune_from_env(Tune& t) {
                                         {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
                                         {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
                                         {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
-                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}, {"doorbell", "PDSP_DOORBELL"}};
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}, {"doorbell", "PDSP_DOORBELL"}, {"big_pipe", "PDSP_BIG_PIPE"}};
   for (auto& k : keys)
     if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
@@ -827,7 +833,8 @@ static int big_plan(pdsp_plan* pl, BigPlan** out) {
 // One pass of the first-generation path (bigfft_kernels.cuh: per-thread tile loads and stores, or TMA tile loads) over the
 // `nf` transforms of a group.  fre/fim, gre/gim: the group's caller-facing input / output planes; wk: its work buffer.
 static int launch_pass_v1(pdsp_plan* pl, BigPlan* bp, BigPlan::Work* wk, int j, long long O, long long I, long long nf,
-                          const char* fre, const char* fim, char* gre, char* gim, int inverse, const LaunchCtx& lc) {
+                          const char* fre, const char* fim, char* gre, char* gim, int inverse, const LaunchCtx& lc,
+                          bool pipe = false) {
   pdsp_ctx* c = pl->ctx;
   const size_t es = esize(pl->precision);
   const long long N = 1LL << pl->log2n;
@@ -893,7 +900,13 @@ static int launch_pass_v1(pdsp_plan* pl, BigPlan* bp, BigPlan::Work* wk, int j, 
   // TMA tile loads for the strided passes while one group's planes fit the L2 (2^20: 0.158 vs 0.169 ms per 8
   // transforms); per-thread loads beyond that (2^24: 0.353 vs 0.373 ms).  Tunable big_tma forces either.
   const bool tma = c->tune.big_tma >= 0 ? c->tune.big_tma != 0 : (2 * es * (size_t)N * (size_t)nf <= ((size_t)128 << 20));
-  if (!last && tma) {
+  if (pipe && last) {
+    // third generation (bigfft3_kernels.cuh): the rows of the next tile land in shared memory by bulk copies while the
+    // current one is transformed; same parameter block, the tensor maps are unused
+    simt::TensorMap2D none;
+    memset(&none, 0, sizeof none);
+    e = launch_big_pipe(pl->precision == PDSP_F64, bp->lg[j], true, p, none, none, lc);
+  } else if (!last && (tma || pipe)) {
     // TMA-staged tile gather: planes viewed as [frames*O*L rows][I cols], box {C, min(L, 256)}
     simt::TensorMap2D tm_re, tm_im;
     int bc = 0, br = 0;
@@ -907,7 +920,7 @@ static int launch_pass_v1(pdsp_plan* pl, BigPlan* bp, BigPlan::Work* wk, int j, 
       if (make_tensor_map(&tm_re, p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
       if (make_tensor_map(&tm_im, p.in_im ? p.in_im : p.in_re, f64p, I, nf * O * L, bc, br)) return 1;
     }
-    e = launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
+    e = pipe ? launch_big_pipe(f64p, bp->lg[j], false, p, tm_re, tm_im, lc) : launch_big_pass_tma(f64p, bp->lg[j], p, tm_re, tm_im, lc);
   } else {
     e = launch_big_pass(pl->precision == PDSP_F64, bp->lg[j], p, lc);
   }
@@ -1087,12 +1100,25 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       const int Cj = big2_pass_c(bp->lg[j]);
       pass_v2[j] = v2_allowed && (size_t)Cj * es >= 16 && (c->tune.big_v2 < 0 ? (size_t)Cj * es >= 64 : c->tune.big_v2 != 0);
     }
+    // third generation (pipeline passes, bigfft3_kernels.cuh): fp64 passes of 256 / 512 / 1024 points over the
+    // interleaved work buffer.  Automatic for 1024-point passes, whose tiles are too large for two CTAs per SM;
+    // tunable big_pipe = 0 / 1 turns it off / on for every length it exists for.
+    bool pass_v3[3] = {false, false, false};
+    for (int j = 0; j < np; ++j) {
+      pass_v3[j] = il && v2_allowed && big_pipe_supported(f64, bp->lg[j]) &&
+                   (c->tune.big_pipe < 0 ? bp->lg[j] == 10 : c->tune.big_pipe != 0);
+      if (pass_v3[j]) pass_v2[j] = false;
+    }
     // Three-pass transforms whose work buffer exceeds the L2 (2^24: 256 MB): after pass 0, passes 1 and 2 run over GROUPS
     // of k1 blocks - pass 1 writes a group's slice of the work buffer (<= 32 MB), pass 2 reads it back while it is still
     // in the L2 and stores the final (transposed) output.  DRAM then sees the work buffer once between passes 0 and 1
-    // only: 4 x N*16 bytes instead of 6 (tunable big_resident = 0 restores the pass-by-pass schedule).
+    // only: 4 x N*16 bytes instead of 6.  MEASURED SLOWER and therefore off unless the tunable big_resident asks for it
+    // (2^24: 0.331 ms pass by pass, 0.404-0.510 ms in groups of 64-16 blocks; 2^26: 1.40 vs 1.55-1.96 ms -
+    // profiles/r2/sweep_big_resident.txt): a group launch moves only 16-64 MB, so every CTA handles 1-2 tiles and the ramp
+    // and tail of 2 x (L1 / group) launches cost more than the saved DRAM round trip - the passes are bound by the
+    // per-tile latency chain, not by DRAM.
     long long group = 0;
-    if (np == 3 && il && pass_v2[0] && pass_v2[1] && pass_v2[2] && c->tune.big_resident != 0) {
+    if (np == 3 && il && pass_v2[0] && pass_v2[1] && pass_v2[2] && c->tune.big_resident > 0) {
       const size_t block = (size_t)Ls[1] * (size_t)Ls[2] * 2 * es;  // one k1 block of the interleaved work buffer
       const long long c_last = big2_pass_c(bp->lg[2]);
       long long g = c_last;
@@ -1123,7 +1149,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       const bool last = j == np - 1;
       const bool v2 = pass_v2[j];
       if (!v2) {
-        if (launch_pass_v1(pl, bp, wk, j, O, I, nf, fre, fim, gre, gim, inverse, lc)) return 1;
+        if (launch_pass_v1(pl, bp, wk, j, O, I, nf, fre, fim, gre, gim, inverse, lc, pass_v3[j])) return 1;
         O *= L;
         continue;
       }

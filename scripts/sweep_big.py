@@ -24,8 +24,18 @@ peak, _ = bench.measured_hbm_peak()
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev)
 vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+KEYS = ("big_v2", "big_chunk", "big_interleave", "big_resident", "big_pipe", "big_factors")
 cases = [(20, 8), (24, 1), (22, 2), (16, 64), (18, 16)]
 settings = [dict(), dict(big_v2=0), dict(big_v2=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
+if "--resident" in sys.argv:  # 2^24 / 2^26: passes 1+2 in L2-sized k1 groups (big_resident = blocks per group), against pass-by-pass
+    cases = [(24, 1), (26, 1)]
+    settings = [dict(big_resident=0), dict(), dict(big_resident=16), dict(big_resident=32), dict(big_resident=64)]
+if "--pipe" in sys.argv:  # third generation (pipeline passes) against the per-pass defaults, and factorisations that favour it
+    cases = [(20, 8), (24, 1), (22, 2), (18, 16), (16, 64), (26, 1)]
+    settings = [dict(big_pipe=0), dict(), dict(big_pipe=1), dict(big_pipe=1, big_factors="10,7,7"), dict(big_pipe=1, big_factors="9,9,6"),
+                dict(big_pipe=1, big_factors="10,8,6"), dict(big_pipe=1, big_factors="10,6,6"), dict(big_pipe=1, big_factors="10,8"),
+                dict(big_pipe=1, big_factors="9,9"), dict(big_pipe=1, big_factors="10,6"), dict(big_pipe=1, big_factors="10,9,7"),
+                dict(big_pipe=1, big_factors="9,9,8"), dict(big_pipe=1, big_factors="10,10,6")]
 if "--only20" in sys.argv:
     cases = [(20, 8)]
     settings = [dict(big_v2=0), dict(big_v2=0, big_chunk=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
@@ -40,8 +50,13 @@ for log2n, frames in cases:
     for s in settings:
         if frames == 1 and s.get("big_chunk", 0) > 1:
             continue
-        for k in ("big_v2", "big_chunk", "big_interleave"):
-            ctx.tune(k, s.get(k))
+        if s.get("big_factors") and sum(int(x) for x in s["big_factors"].split(",")) != log2n:
+            continue
+        # the pass structure is fixed when a plan is first used: forced factors get a context (and plan cache) of their own
+        cx = _lib.Context(0) if s.get("big_factors") else ctx
+        for k in KEYS:
+            cx.tune(k, s.get(k))
+        plan = cx.plan(n, F64)
 
         def go():
             check(L.pdsp_fft_complex_dev(plan, vp(re), vp(im), frames, vp(ore), vp(oim), 0, C.c_void_p(st.cuda_stream)))
@@ -66,5 +81,8 @@ for log2n, frames in cases:
         ms = e0.elapsed_time(e1) / reps
         frac = 32.0 * n * frames / (ms * 1e-3) / 1e9 / peak
         print(f"2^{log2n} x{frames} {s}: {ms:.4f} ms/step  {ms / frames * 1e3:.2f} us/transform  frac {frac:.3f}  rel-L2 {err:.2e}", flush=True)
-    for k in ("big_v2", "big_chunk", "big_interleave"):
+        if cx is not ctx:
+            torch.cuda.synchronize()
+            cx.close()
+    for k in KEYS:
         ctx.tune(k, None)

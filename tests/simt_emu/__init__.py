@@ -91,7 +91,7 @@ def build_cabi_emulated():
     TEST ONLY - loaded by tests/test_host_pipeline_emulated.py through a monkeypatched LIB_PATH."""
     import concurrent.futures as cf
     import re
-    srcs = _headers() + [os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(_CSRC, "inst.cu"), os.path.join(_CSRC, "bigfft.cu"), os.path.join(_CSRC, "bigfft2.cu"),
+    srcs = _headers() + [os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(_CSRC, "inst.cu"), os.path.join(_CSRC, "bigfft.cu"), os.path.join(_CSRC, "bigfft2.cu"), os.path.join(_CSRC, "bigfft3.cu"),
                          os.path.join(_ROOT, "include", "pragma_b200.h")]
     if not _stale(CABI_EMU_SO, srcs):
         return CABI_EMU_SO
@@ -102,6 +102,7 @@ def build_cabi_emulated():
     units = [(os.path.join(_CSRC, "pragma_b200.cu"), os.path.join(objdir, "pragma_b200.o"), []),
              (os.path.join(_CSRC, "bigfft.cu"), os.path.join(objdir, "bigfft.o"), []),
              (os.path.join(_CSRC, "bigfft2.cu"), os.path.join(objdir, "bigfft2.o"), []),
+             (os.path.join(_CSRC, "bigfft3.cu"), os.path.join(objdir, "bigfft3.o"), []),
              (os.path.join(_HERE, "emu_runtime.cc"), os.path.join(objdir, "emu_runtime.o"), [])]
     for kind, tag, ctype, lo, hi in re.findall(r"X\((\d), (\w+), (\w+), (\d+), (\d+)\)", txt):
         name = f"launch_{'r2c' if kind == '0' else 'c2c'}_{tag}_{lo}_{hi}"

@@ -180,6 +180,13 @@ def test_launch_and_plan_accounting(emu_api):
                                            ("7,6", 8192, {"big_chunk": "1"}),
                                            # three passes, passes 1 + 2 run over groups of 32 k1 blocks (the L2-resident schedule of 2^24)
                                            ("6,6,6", 1 << 18, {"big_resident": "32"}),
+                                           # third generation (pipeline passes: split-plane exchange, next tile landing during the
+                                           # transform): 256 / 512 / 1024-point passes, two and three passes, mixed with the others
+                                           ("8,8", 1 << 16, {"big_pipe": "1"}),
+                                           ("10,8", 1 << 18, {"big_pipe": "1"}),
+                                           ("8,9", 1 << 17, {"big_pipe": "1"}),
+                                           ("6,8,6", 1 << 20, {"big_pipe": "1"}),
+                                           ("10,6", 1 << 16, {}),
                                            # first generation, its switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
                                            ("6,6", 4096, {"big_v2": "0"}),
                                            ("6,6,6", 1 << 18, {"big_v2": "0"}),
