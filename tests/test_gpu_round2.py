@@ -179,3 +179,97 @@ def test_out_validation_before_native_code(ctx):
         fft.forward(x, ComplexArray(np.zeros(64, dtype=np.float32), np.zeros(64)))
     out = ComplexArray(np.zeros(64), np.zeros(64))
     assert fft.forward(x, out) is out and out.real[0] == x.sum()      # `out` identity (src/core/fft.ts:106,150)
+
+
+def test_c5_full_size_peak_indices_are_exact(ctx):
+    """BASELINE config C5 at its full size on one GPU: 2^20 frames x N=1024 fp64, Hann window, peak only.  Every frame is
+    a pure tone on an integer bin (known answer: peak index == that bin, frequency == bin * fs / N); a strided subset is also compared with
+    the oracle record for record."""
+    import torch
+    from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+    L = lib()
+    n, frames, fs = 1024, 1 << 20, 48000.0
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    bins = torch.randint(1, n // 2, (frames,), generator=g, device=dev)
+    amp = torch.rand(frames, generator=g, device=dev, dtype=torch.float64) + 0.5
+    ph = torch.rand(frames, generator=g, device=dev, dtype=torch.float64) * 6.283185307179586
+    t = torch.arange(n, device=dev, dtype=torch.float64)
+    x = torch.empty((frames, n), dtype=torch.float64, device=dev)
+    for f0 in range(0, frames, 1 << 17):  # built in slices: the phase matrix of all frames at once would be 8 GB
+        sl = slice(f0, f0 + (1 << 17))
+        x[sl] = amp[sl, None] * torch.cos(2 * torch.pi * bins[sl, None].double() * t[None, :] / n + ph[sl, None])
+    peaks = torch.zeros(frames * PEAK_F64.itemsize, dtype=torch.uint8, device=dev)
+    d = SpectrumDesc(sample_rate=fs, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
+                     sample_dtype=F64, raw_magnitude=0, fft_shift=0)  # outputs = the non-null pointers: peaks only
+    plan = ctx.plan(n, F64)
+    check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()), None, None, C.c_void_p(peaks.data_ptr()),
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    rec = peaks.cpu().numpy().view(PEAK_F64).reshape(-1)
+    want = bins.cpu().numpy()
+    assert (rec["index"] == want).all()
+    assert np.abs(rec["frequency"] - want * fs / n).max() == 0.0
+    idx = np.arange(0, frames, 4099)
+    ref = oracle.spectrum_batch(x[torch.as_tensor(idx, device=dev)].cpu().numpy(), fftSize=n, sampleRate=fs, window="hann")
+    assert (rec["index"][idx] == ref["peaks"]["index"]).all()
+    assert np.abs(rec["amplitude"][idx] - ref["peaks"]["amplitude"]).max() <= 1e-12
+
+
+def test_c3_full_size_stft_against_oracle_subset(ctx):
+    """BASELINE config C3 at its full size: 10 min at 48 kHz (28,800,000 samples), N=4096, hop 1024, Hann, amplitude +
+    phase in fp64 = 28,122 overlapping frames read straight from the stream (no frame matrix).  Frame count and the
+    frames' positions are checked through a strided subset against the oracle; Parseval holds for every frame."""
+    import torch
+    from pragma_dsp_b200 import stft
+    n, hop, total = 4096, 1024, 28_800_000
+    rng = np.random.default_rng(3)
+    t = np.arange(total)
+    sig = np.zeros(total)
+    for k in range(4):  # slowly drifting tones: every frame has a different spectrum
+        f0, f1 = rng.uniform(200, 8000, 2)
+        sig += rng.uniform(0.2, 1.0) * np.sin(2 * np.pi * (f0 + (f1 - f0) * t / (2 * total)) * t / 48000.0 + rng.uniform(0, 6.28))
+    got = stft(sig, fftSize=n, hopSize=hop, window="hann", sampleRate=48000.0, outputs=("amplitude", "phase", "peak"))
+    frames = (total - n) // hop + 1
+    assert frames == 28122 and got["amplitude"].shape == (frames, n // 2 + 1) and got["phase"].shape == (frames, n // 2 + 1)
+    idx = np.arange(0, frames, 997)
+    sub = np.stack([sig[i * hop:i * hop + n] for i in idx])
+    ref = oracle.spectrum_batch(sub, fftSize=n, sampleRate=48000.0, window="hann")
+    assert np.abs(got["amplitude"][idx] - ref["amplitude"]).max() <= 1e-12
+    strong = ref["amplitude"] > 1e-6  # phase is compared where |X| is not noise, wrap-aware (test/reallife/signals.test.ts:34-49)
+    dphi = np.angle(np.exp(1j * (got["phase"][idx] - ref["phase"])))
+    assert np.abs(dphi[strong]).max() <= 1e-8
+    assert (got["peaks"]["index"][idx] == ref["peaks"]["index"]).all()
+    # Parseval on the windowed frames: sum over the one-sided bins of (scaled amplitude)^2 recovers 2/N * sum (w*x)^2
+    w = oracle.createWindow("hann", n)
+    a = got["amplitude"][idx]
+    lhs = (a[:, 1:-1] ** 2).sum(1) / 2 + a[:, 0] ** 2 + a[:, -1] ** 2
+    rhs = ((sub * w) ** 2).sum(1) / n
+    assert np.abs(lhs - rhs).max() <= 1e-10 * rhs.max()
+
+
+@pytest.mark.parametrize("log2n", [16, 18, 20, 24])
+def test_large_fft_pass_generations_agree(ctx, log2n):
+    """K2 has three generations of the pass kernel (per-thread / TMA loads; TMA loads + stores, two CTAs per SM; pipeline
+    passes with the split-plane exchange).  Forced one at a time through the tunables, all give the same transform."""
+    from pragma_dsp_b200.core import ComplexArray, Radix2Fft
+    n = 1 << log2n
+    rng = np.random.default_rng(log2n)
+    re, im = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    ref = np.fft.fft(re + 1j * im)
+    outs = []
+    try:
+        for pipe, v2 in (("0", "0"), ("0", "1"), ("1", "0"), (None, None)):
+            ctx.tune("big_pipe", pipe)
+            ctx.tune("big_v2", v2)
+            out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
+            z = out.real + 1j * out.imag
+            assert np.linalg.norm(z - ref) / np.linalg.norm(ref) <= 1e-12 * log2n
+            outs.append(z)
+            back = Radix2Fft(n).inverse(out)
+            assert np.abs(back.real - re).max() <= 1e-12 and np.abs(back.imag - im).max() <= 1e-12
+    finally:
+        ctx.tune("big_pipe", None)
+        ctx.tune("big_v2", None)
+    for z in outs[1:]:  # same butterflies, same twiddles: the generations differ in data movement only
+        assert np.linalg.norm(z - outs[0]) / np.linalg.norm(outs[0]) <= 1e-15
