@@ -688,9 +688,42 @@ def run_b200(args, w):
                                       f"oracle/pragma_oracle.c (single thread, like the single-threaded JS reference); all {thr} "
                                       f"host threads: {allc:.0f} frames/s"}
 
+    # ---- library comparator, CONTEXT ONLY (SURVEY 8d "optional sanity comparator"): the same batch through cuFFT as a user
+    # of a stock library would write it - window multiply, torch.fft.rfft (cuFFT D2Z / R2C), abs() - three library kernels and
+    # three passes over HBM.  Not a product path, not a target, never part of `value`; it says what fusing is worth.
+    # Opt-in (--comparator): the default run, which the driver measures, never touches a library FFT.
+    comparator = None
+    if args.comparator and rank == 0 and world == 1 and hop == n and tuple(w["outputs"]) == ("amplitude",):
+        try:
+            cb = min(frames, 1 << 18)
+            wt = torch.from_numpy(__import__("oracle").createWindow(w["window"], n)).to(dev).to(tdt)
+            xs = x[:cb].to(tdt)
+
+            def lib_step():
+                return torch.fft.rfft(xs * wt, dim=1).abs() * (2.0 / n)
+            for _ in range(3):
+                lib_step()
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            c0.record()
+            for _ in range(reps):
+                lib_step()
+            c1.record()
+            torch.cuda.synchronize(dev)
+            lib_fps = cb * reps / (c0.elapsed_time(c1) * 1e-3)
+            comparator = {"what": "torch.fft.rfft (cuFFT) pipeline: x * window -> rfft -> abs * 2/N, device-resident, "
+                                  f"{cb} frames per call; context only, not a product path", "value": lib_fps, "unit": "frames/s",
+                          "this_over_library": None}
+            del xs
+        except Exception as e:  # the comparator must never cost the bench line
+            comparator = {"what": "torch.fft.rfft (cuFFT) pipeline", "error": str(e)[:200]}
+
     if rank == 0:
         total_frames = frames * world
         fps = total_frames * args.steps / (elapsed_ms * 1e-3)
+        if comparator and comparator.get("value"):
+            comparator["this_over_library"] = fps / comparator["value"]
         bpf = algorithmic_bytes_per_frame(w)
         peak, peak_src = measured_hbm_peak()
         achieved = bpf * frames / (kern_ms * 1e-3) / 1e9
@@ -711,6 +744,7 @@ def run_b200(args, w):
                          "timed": f"CUDA events around each of the {args.steps} launches of the timed region, mean"},
             "burst": burst,
             "cpu_baseline": cpu_baseline,
+            "library_comparator": comparator,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d * (world if e2e_per_rank else 1),
                     "d2h_bytes_per_step": d2h * (world if e2e_per_rank else 1),
                     "steps": e2e_steps, "frames_per_step": e2e_frames * (world if e2e_per_rank else 1), "api": e2e_api,
@@ -976,6 +1010,8 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how per-frame peaks reach every rank - peer stores fused into the kernel epilogue (p2p) "
                          "or a side-stream NCCL all_gather")
+    ap.add_argument("--comparator", action="store_true",
+                    help="also time the same batch through torch.fft.rfft (cuFFT) + abs as context (amplitude-only workloads, 1 GPU)")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the clock probe, CPU baseline, shorten e2e")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
