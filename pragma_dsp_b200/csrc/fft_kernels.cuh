@@ -96,6 +96,9 @@ struct C2CParams {
   Doorbell door;
 };
 
+#ifndef PDSP_NEXT_PREFETCH
+#define PDSP_NEXT_PREFETCH 0
+#endif
 template <typename T>
 PDSP_DEVICE T t_sqrt(T v);
 template <>
@@ -457,6 +460,21 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           load_frame(static_cast<const float*>(p.samples) + base);
         else
           load_frame(static_cast<const double*>(p.samples) + base);
+#if PDSP_NEXT_PREFETCH
+        // experiment: hint the slot's NEXT frame into L1 (1) / L2 (2), one 128-byte line per lane and instruction,
+        // behind this frame's own loads - the wait on those is 30 % of the north-star kernel's stall samples
+        if (f + SLOTS < p.batch) {
+          const size_t ssz = p.sample_dtype == DT_F32 ? 4 : 8;
+          const char* nx = static_cast<const char*>(p.samples) + (size_t)((f + SLOTS) * p.hop) * ssz;
+          const int lines = (int)((N * ssz) >> 7);
+          for (int l = tl; l < lines; l += TF) {
+            if (PDSP_NEXT_PREFETCH == 1)
+              simt::prefetch_l1(nx + ((size_t)l << 7));
+            else
+              simt::prefetch_l2(nx + ((size_t)l << 7));
+          }
+        }
+#endif
       }
       if (win != nullptr) {
         static_for<0, P>([&](auto qi) {

@@ -112,6 +112,9 @@ PDSP_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::c
 PDSP_DEVICE void prefetch_l2_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// per-line prefetch hints (experiment PDSP_NEXT_PREFETCH in the framed kernels): one 128-byte line per lane
+PDSP_DEVICE void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PDSP_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // completion doorbell (low-latency host entry points): the last CTA to finish writes a sequence number into
 // host-mapped pinned memory; the host spins on it instead of going through a stream synchronisation
 PDSP_DEVICE void fence_system() { __threadfence_system(); }
@@ -252,6 +255,8 @@ inline void bulk_wait_all() {}
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu_mbar_wait(bar, parity); }
 inline void fence_proxy_async() {}
 inline void prefetch_l2_bulk(const void*, unsigned) {}
+inline void prefetch_l1(const void*) {}
+inline void prefetch_l2(const void*) {}
 inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over the warp's lanes
   int acc = pred ? 1 : 0;
   for (int m = 16; m >= 1; m >>= 1) acc |= shfl_xor(acc, m, 32);
