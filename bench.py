@@ -400,6 +400,7 @@ def run_b200(args, w):
                         window=WINDOWS[w["window"]], sides=SIDES["one"], sample_rate=48000.0, raw_magnitude=0)
     compute = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev) if gathered else None
+    torch.cuda.synchronize(dev)  # inputs and zero fills were produced on torch's stream: done before anything runs on `compute`
     L = lib()
 
     def vp(t):
@@ -791,6 +792,7 @@ def run_b200_c2c(args, w):
     im = None if real_in else torch.rand((frames, n), generator=g, device=dev, dtype=torch.float64) * 2 - 1
     ore, oim = torch.empty_like(re), torch.empty_like(re)
     st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize(dev)  # the inputs were generated on torch's stream
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     def step():

@@ -131,7 +131,9 @@ int pdsp_spectrum(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* s
                   void* phase, void* peaks);
 
 /* ---- device-resident variants: pointers are device memory, work is enqueued on `stream`
- *      (a cudaStream_t passed as void*; NULL = the context's stream).  Scratch planes of the large
+ *      (a cudaStream_t passed as void*; NULL = the context's own stream, which is created non-blocking and is therefore
+ *      NOT ordered with work on the legacy default stream - whose handle is also 0.  A caller working on the default
+ *      stream passes cudaStreamLegacy ((void*)0x1) or cudaStreamPerThread ((void*)0x2), or synchronises first).  Scratch planes of the large
  *      transforms are kept per (plan, stream): calls on different streams may overlap, calls on one
  *      stream are ordered by it. ------------------------------------------------------------- */
 int pdsp_spectrum_dev(pdsp_plan* plan, const pdsp_spectrum_desc* desc, const void* d_samples, void* d_amplitude,

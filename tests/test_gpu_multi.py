@@ -122,6 +122,7 @@ def _ipc_worker(rank, world, port, frames, q):
         desc = SpectrumDesc(sample_dtype=F32, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
                             sample_rate=48000.0, raw_magnitude=0, fft_shift=0)
         st = torch.cuda.Stream(device=dev)
+        st.wait_stream(torch.cuda.current_stream())  # ordered behind the generators / fills on torch's stream
         check(L.pdsp_spectrum_dev_gather(plan, C.byref(desc), C.c_void_p(x.data_ptr()), None, None, C.c_void_p(local.data_ptr()),
                                          peers, world, rank * frames, C.c_void_p(st.cuda_stream)))
         st.synchronize()

@@ -148,6 +148,9 @@ def test_device_resident_entry_points(ctx):
     plan = ctx.plan(n, F64)
     d = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
                      sample_rate=48000.0, raw_magnitude=0)
+    # torch's current stream is the legacy default stream (handle 0 = NULL = "the context's stream" to the library, a
+    # non-blocking stream that is not ordered behind torch's work): finish the uploads and fills first
+    torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
     check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(dx.data_ptr()), C.c_void_p(amp.data_ptr()), None,
                               C.c_void_p(pk.data_ptr()), C.c_void_p(st)))
@@ -182,6 +185,7 @@ def test_full_size_properties(ctx, prec, frames):
     x = torch.randn((frames, n), generator=g, device="cuda", dtype=torch.float64).to(tdt)
     y = torch.randn((frames, n), generator=g, device="cuda", dtype=torch.float64).to(tdt)
     plan = ctx.plan(n, P)
+    torch.cuda.synchronize()  # handle 0 below = the context's own non-blocking stream: not ordered behind torch's generators
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def fwd(t):
@@ -260,6 +264,7 @@ def test_large_multipass_fft_fp32_device(ctx):
     ore, oim = torch.empty_like(re), torch.empty_like(re)
     plan = ctx.plan(n, F32)
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())  # ordered behind the generators / fills on torch's stream
     check(L.pdsp_fft_complex_dev(plan, C.c_void_p(re.data_ptr()), C.c_void_p(im.data_ptr()), 1, C.c_void_p(ore.data_ptr()),
                                  C.c_void_p(oim.data_ptr()), 0, C.c_void_p(st.cuda_stream)))
     st.synchronize()
@@ -286,6 +291,7 @@ def test_fused_peer_scatter_single_gpu(ctx):
     d = SpectrumDesc(sample_dtype=F32, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
                      sample_rate=48000.0, raw_magnitude=0)
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())  # ordered behind the generators / fills on torch's stream
     check(L.pdsp_spectrum_dev_gather(plan, C.byref(d), C.c_void_p(dx.data_ptr()), None, None, C.c_void_p(local.data_ptr()),
                                      peers, 2, offset, C.c_void_p(st.cuda_stream)))
     st.synchronize()
@@ -358,6 +364,7 @@ def test_device_resident_fft_convolution(ctx):
     b = torch.randn((batch, n), generator=g, device="cuda", dtype=torch.float64)
     plan = ctx.plan(n, F64)
     st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())  # ordered behind the generators / fills on torch's stream
     s = C.c_void_p(st.cuda_stream)
     vp = lambda t_: C.c_void_p(t_.data_ptr())  # noqa: E731
     bufs = [torch.empty((batch, n), dtype=torch.float64, device="cuda") for _ in range(8)]

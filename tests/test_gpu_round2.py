@@ -203,8 +203,10 @@ def test_c5_full_size_peak_indices_are_exact(ctx):
     d = SpectrumDesc(sample_rate=fs, frame_len=n, hop=n, batch=frames, window=WINDOWS["hann"], sides=SIDES["one"],
                      sample_dtype=F64, raw_magnitude=0, fft_shift=0)  # outputs = the non-null pointers: peaks only
     plan = ctx.plan(n, F64)
+    st = torch.cuda.Stream(device=dev)
+    st.wait_stream(torch.cuda.current_stream())  # the library's launch is ordered behind the generation and the zero fill
     check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(x.data_ptr()), None, None, C.c_void_p(peaks.data_ptr()),
-                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                              C.c_void_p(st.cuda_stream)))
     torch.cuda.synchronize()
     rec = peaks.cpu().numpy().view(PEAK_F64).reshape(-1)
     want = bins.cpu().numpy()
