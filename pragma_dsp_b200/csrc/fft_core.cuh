@@ -63,13 +63,28 @@ PDSP_DEVICE cx<float> ew_mul(cx<float> a, cx<float> s) { return as_cx(__fmul2_rn
 
 // read-only (non-coherent) load of a table entry
 #if defined(__CUDACC__) && !defined(PDSP_EMU)
+#ifndef PDSP_TABLE_LD
+#define PDSP_TABLE_LD 0  // experiment: 1 = table loads ask the L1 to evict their lines last (ld.global.nc.L1::evict_last)
+#endif
 PDSP_DEVICE cx<double> ldg_cx(const cx<double>* p) {
+#if PDSP_TABLE_LD
+  cx<double> v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
   const double2 v = __ldg(reinterpret_cast<const double2*>(p));
   return cx<double>{v.x, v.y};
+#endif
 }
 PDSP_DEVICE cx<float> ldg_cx(const cx<float>* p) {
+#if PDSP_TABLE_LD
+  cx<float> v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#else
   const float2 v = __ldg(reinterpret_cast<const float2*>(p));
   return cx<float>{v.x, v.y};
+#endif
 }
 #else
 template <typename T>

@@ -331,6 +331,47 @@ PDSP_DEVICE cx<T> load_pair(const S* PDSP_RESTRICT s, int i0) {
   const cx<S> pr = *reinterpret_cast<const cx<S>*>(s + i0);
   return cx<T>{(T)pr.x, (T)pr.y};
 }
+// Sample loads from GLOBAL memory (read exactly once) with a cache policy (experiment switch PDSP_SAMPLE_LD): 0 plain
+// ld.global (allocates in L1: 128 KB of samples stream through the L1 of an SM per 16 resident frames, and 6.7 % of the
+// twiddle / window table sectors then miss it - profiles/r2/ncu_summary_north_star.json), 1 ld.global.cs (streaming),
+// 2 ld.global.L1::no_allocate, 3 ld.global.lu (last use).
+#ifndef PDSP_SAMPLE_LD
+#define PDSP_SAMPLE_LD 0
+#endif
+#ifndef PDSP_OUT_ST
+#define PDSP_OUT_ST 0  // amplitude row stores: 0 plain st.global, 1 st.global.cs (streaming)
+#endif
+template <typename T, typename S>
+PDSP_DEVICE cx<T> load_pair_global(const S* PDSP_RESTRICT s, int i0) {
+#if defined(__CUDACC__) && !defined(PDSP_EMU) && PDSP_SAMPLE_LD
+  cx<S> pr;
+  const cx<S>* a = reinterpret_cast<const cx<S>*>(s + i0);
+#if PDSP_SAMPLE_LD == 1
+#define PDSP_LDQ "ld.global.cs"
+#elif PDSP_SAMPLE_LD == 2
+#define PDSP_LDQ "ld.global.L1::no_allocate"
+#else
+#define PDSP_LDQ "ld.global.lu"
+#endif
+  if constexpr (sizeof(S) == 8) {
+    asm volatile(PDSP_LDQ ".v2.f64 {%0, %1}, [%2];" : "=d"(pr.x), "=d"(pr.y) : "l"(a));
+  } else {
+    asm volatile(PDSP_LDQ ".v2.f32 {%0, %1}, [%2];" : "=f"(pr.x), "=f"(pr.y) : "l"(a));
+  }
+#undef PDSP_LDQ
+  return cx<T>{(T)pr.x, (T)pr.y};
+#else
+  return load_pair<T>(s, i0);
+#endif
+}
+template <typename T>
+PDSP_DEVICE void store_stream(T* a, T v) {
+#if defined(__CUDACC__) && !defined(PDSP_EMU) && PDSP_OUT_ST
+  __stcs(a, v);
+#else
+  *a = v;
+#endif
+}
 
 template <typename T, int LOG2M, int LOG2P, int MAXRB, int THREADS, int MODE>
 PDSP_DEVICE void r2c_body(const R2CParams& p) {
@@ -428,7 +469,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
     cx<T> v[P];
     if constexpr (!GEN) {
       // whole aligned frames: one vector load per complex point; a tail slot re-reads the last frame
-      auto load_frame = [&](auto* s) {
+      auto load_frame = [&](auto* s, auto from_global) {
+        constexpr bool G = decltype(from_global)::value;
         if constexpr ((MODE & MD_PAD) != 0) {
           // buildFrame's zero padding (spectrum.ts:36-43): pairs at or beyond frame_len read as 0, the pair that
           // straddles an odd frame_len would keep its first sample (generic kernel only).  A separate compile-time mode: the same test as a
@@ -438,11 +480,14 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
           static_for<0, P>([&](auto qi) {
             const int i0 = 2 * (t + TF * decltype(qi)::value);
             cx<T> pr{(T)0, (T)0};
-            if (i0 < lim) pr = load_pair<T>(s, i0);
+            if (i0 < lim) pr = G ? load_pair_global<T>(s, i0) : load_pair<T>(s, i0);
             v[decltype(qi)::value] = pr;
           });
         } else {
-          static_for<0, P>([&](auto qi) { v[decltype(qi)::value] = load_pair<T>(s, 2 * (t + TF * decltype(qi)::value)); });
+          static_for<0, P>([&](auto qi) {
+            const int i0 = 2 * (t + TF * decltype(qi)::value);
+            v[decltype(qi)::value] = G ? load_pair_global<T>(s, i0) : load_pair<T>(s, i0);
+          });
         }
       };
       if constexpr (STAGED) {
@@ -450,16 +495,16 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         simt::mbar_wait(bar, stage_phase);
         stage_phase ^= 1u;
         if (p.sample_dtype == DT_F32)
-          load_frame(reinterpret_cast<const float*>(sm));
+          load_frame(reinterpret_cast<const float*>(sm), std::false_type{});
         else
-          load_frame(reinterpret_cast<const double*>(sm));
+          load_frame(reinterpret_cast<const double*>(sm), std::false_type{});
         frame_sync<TF>(slot, SLOTS);  // every lane holds its samples: the exchanges may overwrite the buffer
       } else {
         const long long base = (valid ? f : p.batch - 1) * p.hop;
         if (p.sample_dtype == DT_F32)
-          load_frame(static_cast<const float*>(p.samples) + base);
+          load_frame(static_cast<const float*>(p.samples) + base, std::true_type{});
         else
-          load_frame(static_cast<const double*>(p.samples) + base);
+          load_frame(static_cast<const double*>(p.samples) + base, std::true_type{});
 #if PDSP_NEXT_PREFETCH
         // experiment: hint the slot's NEXT frame into L1 (1) / L2 (2), one 128-byte line per lane and instruction,
         // behind this frame's own loads - the wait on those is 30 % of the north-star kernel's stall samples
@@ -673,8 +718,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
             }
           }
           if (want_amp && o_amp != nullptr) {
-            (o_amp + b0 + ((EDGE && k == M) ? -sh : sh))[OFF] = a;  // shifted: k < M -> k + M, the Nyquist bin M -> 0
-            if (two_sided && (!EDGE || (k != 0 && k != M))) (o_amp + m0 - sh)[-OFF] = a;
+            store_stream(o_amp + b0 + ((EDGE && k == M) ? -sh : sh) + OFF, a);  // shifted: k < M -> k + M, the Nyquist bin M -> 0
+            if (two_sided && (!EDGE || (k != 0 && k != M))) store_stream(o_amp + m0 - sh - OFF, a);
           }
           if (want_peak) {
             bool is_dc = false;
