@@ -167,6 +167,18 @@ static __constant__ float2 kW32f[16][2] = {PDSP_W32F(0),  PDSP_W32F(1),  PDSP_W3
 #ifndef PDSP_F32_CONST_TWIDDLES
 #define PDSP_F32_CONST_TWIDDLES 1
 #endif
+// fp64: the same roots as c[][] operands of DMUL / DFMA instead of 64-bit literals (each literal costs two moves into a
+// register pair wherever the compiler does not keep it live).  Experiment switch.
+#ifndef PDSP_F64_CONST_TWIDDLES
+#define PDSP_F64_CONST_TWIDDLES 0
+#endif
+#if defined(__CUDACC__) && !defined(PDSP_EMU) && PDSP_F64_CONST_TWIDDLES
+#define PDSP_W32D(K) {w32_re(K), w32_im(K)}
+static __constant__ double kW32d[16][2] = {PDSP_W32D(0),  PDSP_W32D(1),  PDSP_W32D(2),  PDSP_W32D(3), PDSP_W32D(4),  PDSP_W32D(5),
+                                           PDSP_W32D(6),  PDSP_W32D(7),  PDSP_W32D(8),  PDSP_W32D(9), PDSP_W32D(10), PDSP_W32D(11),
+                                           PDSP_W32D(12), PDSP_W32D(13), PDSP_W32D(14), PDSP_W32D(15)};
+#undef PDSP_W32D
+#endif
 
 // d * W32^K with the trivial cases folded
 template <int K, typename T>
@@ -185,6 +197,19 @@ PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
     constexpr T wi = (T)w32_im(K);
     return cmul(d, cx<T>{wr, wi});
 #endif
+#if defined(__CUDACC__) && !defined(PDSP_EMU) && PDSP_F64_CONST_TWIDDLES
+  } else if constexpr (K == 4) {  // (1-i)/sqrt2
+    const T c = kW32d[4][0];
+    return cx<T>{(d.x + d.y) * c, (d.y - d.x) * c};
+  } else if constexpr (K == 12) {  // (-1-i)/sqrt2
+    const T c = kW32d[4][0];
+    return cx<T>{(d.y - d.x) * c, -(d.x + d.y) * c};
+  } else {
+    const T wr = kW32d[K][0];
+    const T wi = kW32d[K][1];
+    return cx<T>{d.x * wr - d.y * wi, d.x * wi + d.y * wr};
+  }
+#else
   } else if constexpr (K == 4) {  // (1-i)/sqrt2
     constexpr T c = (T)cos16(4);
     return cx<T>{(d.x + d.y) * c, (d.y - d.x) * c};
@@ -196,6 +221,7 @@ PDSP_DEVICE cx<T> mul_w32(cx<T> d) {
     constexpr T wi = (T)w32_im(K);
     return cx<T>{d.x * wr - d.y * wi, d.x * wi + d.y * wr};
   }
+#endif
 }
 
 // d * W32^K for any K in [0, 32)
@@ -285,6 +311,20 @@ struct FftEngine {
   }
   static constexpr int TW_ELEMS = tw_offset(NPASS);
   PDSP_DEVICE static int pad(int i) { return i + (i >> PAD_SHIFT); }
+  // Index of element t + TF*q in the padded buffer.  When TF is a multiple of the padding unit, TF*q contributes no carry
+  // into (t + TF*q) >> PAD_SHIFT, so pad(t + TF*q) = pad(t) + q*(TF + TF/PAD_UNIT): one base register and an immediate
+  // offset per access.  (ptxas does not see this: the fp64 N = 1024 kernel recomputed LOP3 + LEA.HI + IMAD in front of
+  // each of its 16 LDS.128 - 45 of 1,285 warp instructions per frame.)
+  static constexpr bool LINEAR_GATHER = (TF % PAD_UNIT) == 0;
+  static constexpr int GATHER_STEP = TF + (TF >> PAD_SHIFT);
+  PDSP_DEVICE static int gather_base(int t) { return pad(t); }
+  template <int Q>
+  PDSP_DEVICE static int gather_index(int t, int base) {
+    if constexpr (LINEAR_GATHER)
+      return base + Q * GATHER_STEP;
+    else
+      return pad(t + TF * Q);
+  }
 
   // Exchange by shuffle instead of shared memory (see fft()): fp64, M = 512 = 16 x 16 x 2, one warp per frame, pass 1.
   template <bool BLOCKSYNC>
@@ -425,8 +465,9 @@ struct FftEngine {
             });
           });
           sync();
+          const int gb = gather_base(t);
           static_for<0, P>([&](auto q) {
-            const T g = smt[pad(t + TF * decltype(q)::value)];
+            const T g = smt[gather_index<decltype(q)::value>(t, gb)];
             if constexpr (IM)
               v[decltype(q)::value].y = g;
             else
@@ -437,7 +478,8 @@ struct FftEngine {
         if constexpr (pass == last_smem_pass<BLOCKSYNC>()) after_smem();
       } else if constexpr (!last && !SHUF) {
         sync();
-        static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[pad(t + TF * decltype(q)::value)]; });
+        const int gb = gather_base(t);
+        static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[gather_index<decltype(q)::value>(t, gb)]; });
         sync();
         if constexpr (pass == last_smem_pass<BLOCKSYNC>()) after_smem();
       }
