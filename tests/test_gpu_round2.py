@@ -312,3 +312,34 @@ def test_edge_frames_in_one_batch_match_the_oracle(ctx, n):
         err = np.abs(got["amplitude"][finite] - ref["amplitude"][finite]) / scale[finite]
         assert err.max() <= 1e-12, (window, err.max(), np.unravel_index(err.argmax(), err.shape))
         assert (got["amplitude"][7] == 0).all() and got["peaks"]["index"][7] == 0
+
+
+def test_legacy_default_stream_handle(ctx):
+    """A caller that works on CUDA's legacy default stream passes cudaStreamLegacy ((void*)1): the launch is then ordered
+    behind the producer of its inputs on that stream without any synchronisation (handle 0 would select the context's own,
+    non-blocking stream - include/pragma_b200.h)."""
+    import torch
+    from pragma_dsp_b200._lib import F64, PEAK_F64, SIDES, WINDOWS, SpectrumDesc, check, lib
+    L = lib()
+    n, batch = 1024, 50_000
+    rng = np.random.default_rng(21)
+    host = multitone(rng, 64, n)
+    x = torch.from_numpy(host).cuda().repeat(batch // 64 + 1, 1)[:batch].contiguous()
+    big = torch.empty((batch, n), dtype=torch.float64, device="cuda")
+    amp = torch.empty((batch, n // 2 + 1), dtype=torch.float64, device="cuda")
+    pk = torch.zeros((batch, 32), dtype=torch.uint8, device="cuda")
+    d = SpectrumDesc(sample_dtype=F64, frame_len=n, hop=n, batch=batch, window=WINDOWS["hann"], sides=SIDES["one"],
+                     sample_rate=48000.0, raw_magnitude=0, fft_shift=0)
+    plan = ctx.plan(n, F64)
+    torch.cuda.synchronize()
+    for _ in range(4):  # a queue of default-stream work the library's launch has to wait for
+        big.copy_(x).mul_(1.0)
+    amp.zero_()
+    check(L.pdsp_spectrum_dev(plan, C.byref(d), C.c_void_p(big.data_ptr()), C.c_void_p(amp.data_ptr()), None,
+                              C.c_void_p(pk.data_ptr()), C.c_void_p(1)))
+    torch.cuda.synchronize()
+    ref = oracle.spectrum_batch(host, fftSize=n, sampleRate=48000.0, window="hann")
+    got = amp.cpu().numpy()
+    assert np.abs(got[:64] - ref["amplitude"]).max() <= 1e-12
+    assert np.array_equal(got[:64], got[batch - batch % 64 - 64:batch - batch % 64])  # the same 64 frames further down the batch
+    assert (pk.cpu().numpy().view(PEAK_F64).reshape(-1)["index"][:64] == ref["peaks"]["index"]).all()
