@@ -81,7 +81,7 @@ struct Tune {
   int staged = -1;            // PDSP_STAGED: 1 = bulk-staged sample loads where a staged kernel exists (default: direct loads)
   int big_resident = -1;      // PDSP_BIG_RESIDENT: three-pass transforms, passes 1+2 in L2-sized k1 groups: -1 / 0 off (measured slower), 1 on (automatic group size), n > 1 blocks per group
   int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
-  int big_pipe = -1;          // PDSP_BIG_PIPE: third-generation (pipeline) large-FFT passes: -1 automatic (1024-point passes), 0 off, 1 every pass length it exists for (256 / 512 / 1024, fp64)
+  int big_pipe = -1;          // PDSP_BIG_PIPE: third-generation (pipeline) large-FFT passes: -1 automatic (1024-point passes), 0 off, 1 every pass length it exists for (256 / 512 / 1024, fp64), 2 + m: the passes whose bit is set in m
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int doorbell = 1;           // PDSP_DOORBELL: 0 = the fast lane waits with cudaStreamSynchronize instead of the in-kernel doorbell
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
@@ -115,7 +115,7 @@ static int tune_set(Tune& t, const char* key, const char* val) {
   } else if (!strcmp(key, "big_v2")) {
     t.big_v2 = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_pipe")) {
-    t.big_pipe = unset ? -1 : (v[0] != '0');
+    t.big_pipe = unset ? -1 : atoi(v);  // 0 off, 1 every supported length, 2 + mask: passes whose bit is set in mask (bit j = pass j)
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "doorbell")) {
@@ -1101,12 +1101,14 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       pass_v2[j] = v2_allowed && (size_t)Cj * es >= 16 && (c->tune.big_v2 < 0 ? (size_t)Cj * es >= 64 : c->tune.big_v2 != 0);
     }
     // third generation (pipeline passes, bigfft3_kernels.cuh): fp64 passes of 256 / 512 / 1024 points over the
-    // interleaved work buffer.  Automatic for 1024-point passes, whose tiles are too large for two CTAs per SM;
-    // tunable big_pipe = 0 / 1 turns it off / on for every length it exists for.
+    // interleaved work buffer.  Automatic for 1024-point passes, whose tiles are too large for two CTAs per SM, and for
+    // the first pass of three-pass transforms (planar caller input: the full-width tile reads 256-byte rows where the
+    // second generation's half tile reads 128 - 2^24 330 -> 328 us, 2^26 1.40 -> 1.36 ms, profiles/r2/sweep_big_pipe_mask.txt);
+    // tunable big_pipe = 0 / 1 turns it off / on for every length it exists for, 2 + m selects passes by bit mask.
     bool pass_v3[3] = {false, false, false};
     for (int j = 0; j < np; ++j) {
       pass_v3[j] = il && v2_allowed && big_pipe_supported(f64, bp->lg[j]) &&
-                   (c->tune.big_pipe < 0 ? bp->lg[j] == 10 : c->tune.big_pipe != 0);
+                   (c->tune.big_pipe < 0 ? (bp->lg[j] == 10 || (j == 0 && np == 3)) : (c->tune.big_pipe >= 2 ? (((c->tune.big_pipe - 2) >> j) & 1) != 0 : c->tune.big_pipe != 0));
       if (pass_v3[j]) pass_v2[j] = false;
     }
     // Three-pass transforms whose work buffer exceeds the L2 (2^24: 256 MB): after pass 0, passes 1 and 2 run over GROUPS

@@ -36,6 +36,9 @@ if "--pipe" in sys.argv:  # third generation (pipeline passes) against the per-p
                 dict(big_pipe=1, big_factors="10,8,6"), dict(big_pipe=1, big_factors="10,6,6"), dict(big_pipe=1, big_factors="10,8"),
                 dict(big_pipe=1, big_factors="9,9"), dict(big_pipe=1, big_factors="10,6"), dict(big_pipe=1, big_factors="10,9,7"),
                 dict(big_pipe=1, big_factors="9,9,8"), dict(big_pipe=1, big_factors="10,10,6")]
+if "--pipemask" in sys.argv:  # which passes of a three-pass transform gain from the pipeline form (big_pipe = 2 + mask)
+    cases = [(24, 1), (26, 1), (22, 2)]
+    settings = [dict(big_pipe=0)] + [dict(big_pipe=2 + m) for m in range(1, 8)] + [dict(big_pipe=0)]
 if "--only20" in sys.argv:
     cases = [(20, 8)]
     settings = [dict(big_v2=0), dict(big_v2=0, big_chunk=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
