@@ -1,4 +1,5 @@
 #!/bin/bash
+# K2 first generation: ncu full captures of the 2^24 passes with per-thread (PDSP_BIG_TMA=0) and TMA (=1) tile loads.
 set -u
 mkdir -p gpurun_out
 CMD="python bench.py --workload c4_2e24 --steps 2 --warmup 3 --quick"

@@ -1,4 +1,5 @@
 #!/bin/bash
+# Round-2 sixth GPU pass: staged-load north-star capture, C1 latency and C2 bench lines.
 set -u
 mkdir -p gpurun_out
 export PDSP_STAGED=1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# Round-2 GPU pass: large-FFT parity with the final per-pass selection, C4 bench lines, launch list + full capture of the 2^24 passes.
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --timeout 300 -k "large or multipass or generations or c4" 2>&1 | tail -3
