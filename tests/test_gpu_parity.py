@@ -498,5 +498,7 @@ def test_randomised_shapes_against_oracle_gpu(ctx):
             gi, ri = got["peaks"]["index"], ref["peaks"]["index"]
             for f in np.nonzero(gi != ri)[0]:  # only last-bit ties (noise bins, mirror bins) may differ
                 a = ref["amplitude"][f]
+                if precision == "f32" and min(a[gi[f]], a[ri[f]]) * n < 1e-18:
+                    continue  # a bin whose |X|^2 is below the fp32 normal range flushes to 0 (sqrt.approx.ftz) and cannot win
                 assert abs(a[gi[f]] - a[ri[f]]) <= (1e-12 if precision == "f64" else 1e-5) * max(a[ri[f]], 1e-30), tag
             assert np.abs(got["peaks"]["amplitude"] - ref["peaks"]["amplitude"]).max() <= atol, tag
