@@ -45,6 +45,53 @@ int big2_pass_c(int log2l) {
   }
 }
 
+// ---- fused middle + last pass (bigfft_fused_kernel): fp64, interleaved work buffer, both passes of 256 or 512 points
+template <int LA, int LB>
+static cudaError_t launch_fused_t(const BigTileParams& pa, const BigTileParams& pb, const BigFusedSync& fs, const simt::TensorMap* ma,
+                                  const simt::TensorMap* mb, const LaunchCtx& lc) {
+  using A = BigCfg2<double, LA>;
+  using B = BigCfg2<double, LB>;
+  using EA = FftEngine<double, LA, A::LOG2P, A::MAXRB>;
+  using EB = FftEngine<double, LB, B::LOG2P, B::MAXRB>;
+  static_assert(A::LOG2P == B::LOG2P, "one CTA shape for both passes");
+  constexpr int THREADS = A::TF * A::C;
+  constexpr size_t SMEM = A::SMEM > B::SMEM ? A::SMEM : B::SMEM;
+  auto kern = bigfft_fused_kernel<double, LA, LB, A::LOG2P, A::MAXRB, B::MAXRB, A::C, B::C>;
+  static int bps[kMaxDevices] = {0};
+  const long long total = fs.n_groups * (fs.n1g + fs.n2g);
+  if (total <= 0) return cudaSuccess;
+  int grid = 0;
+  cudaError_t e = persistent_grid(kern, THREADS, SMEM, lc, bps, total, &grid);
+  if (e != cudaSuccess) return e;
+#ifdef PDSP_EMU
+  grid = 1;  // the emulator runs CTAs one after another: a single CTA takes the items in list order (producers first)
+#endif
+  BigTileParams qa = pa, qb = pb;
+  qa.tw = lc.pass_twiddles(lc.owner, true, LA, EA::RB);
+  qb.tw = lc.pass_twiddles(lc.owner, true, LB, EB::RB);
+  if (!qa.tw || !qb.tw) return cudaErrorInvalidValue;
+  PDSP_LAUNCH(kern, grid, THREADS, SMEM, lc.stream, qa, qb, fs, ma[0], ma[2], mb[2], mb[3]);
+  return cudaGetLastError();
+}
+bool big_fused_supported(bool f64, int la, int lb) {
+#ifdef PDSP_EMU
+  if (f64 && la == 6 && lb == 6) return true;  // test build only: the same list / counter logic at a size the emulator can run
+#endif
+  return f64 && (la == 8 || la == 9) && (lb == 8 || lb == 9);
+}
+// ma / mb: the {in_re, in_im, out_re, out_im} maps of the middle / last pass as launch_big_tile takes them
+cudaError_t launch_big_fused(int la, int lb, const BigTileParams& pa, const BigTileParams& pb, const BigFusedSync& fs,
+                             const simt::TensorMap* ma, const simt::TensorMap* mb, const LaunchCtx& lc) {
+#ifdef PDSP_EMU
+  if (la == 6 && lb == 6) return launch_fused_t<6, 6>(pa, pb, fs, ma, mb, lc);
+#endif
+  if (la == 8 && lb == 8) return launch_fused_t<8, 8>(pa, pb, fs, ma, mb, lc);
+  if (la == 9 && lb == 8) return launch_fused_t<9, 8>(pa, pb, fs, ma, mb, lc);
+  if (la == 8 && lb == 9) return launch_fused_t<8, 9>(pa, pb, fs, ma, mb, lc);
+  if (la == 9 && lb == 9) return launch_fused_t<9, 9>(pa, pb, fs, ma, mb, lc);
+  return cudaErrorInvalidValue;
+}
+
 // maps: {in_re, in_im, out_re, out_im} (unused entries may repeat a valid map)
 cudaError_t launch_big_tile(bool f64, int log2l, int io, const BigTileParams& p, const simt::TensorMap* maps, const LaunchCtx& lc) {
   switch (log2l) {

@@ -47,12 +47,23 @@ struct BigTileParams {
 };
 
 // IO bit 0: input is the interleaved work buffer; bit 1: output is; bit 2: last pass (row tile in, transposed box out)
-template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO>
-PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
-    bigfft_tile_kernel(const BigTileParams p, const PDSP_GRID_CONSTANT simt::TensorMap tm_in_re,
-                       const PDSP_GRID_CONSTANT simt::TensorMap tm_in_im, const PDSP_GRID_CONSTANT simt::TensorMap tm_out_re,
-                       const PDSP_GRID_CONSTANT simt::TensorMap tm_out_im) {
+//
+// One work item (tile) of a pass.  `w` is the item's index in the pass' own list, `w_next` the item of the SAME pass this CTA
+// will take next (or -1: nothing to prefetch), `phase` the CTA's mbarrier phase bit (carried across items of any kind).
+struct BigNoHook {
+  PDSP_DEVICE void operator()() const {}
+};
+// after_load(): called by every thread once the item's input is in registers (the fused kernel publishes the previous
+// item's stores there: by then they have long completed, so waiting for them costs nothing)
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO, class Hook = BigNoHook>
+PDSP_DEVICE void big_tile_item(const BigTileParams& p, const simt::TensorMap* tm_in_re, const simt::TensorMap* tm_in_im,
+                               const simt::TensorMap* tm_out_re, const simt::TensorMap* tm_out_im, unsigned char* base,
+                               unsigned long long* bar, unsigned& phase, long long w, long long w_next, Hook after_load = Hook{}) {
   constexpr bool IN_CPLX = (IO & 1) != 0, OUT_CPLX = (IO & 2) != 0, LAST = (IO & 4) != 0;
+  // bit 3 (last pass of the fused kernel): the input rows were written by other CTAs of this very launch - read them
+  // through the L2 (ld.global.cg), not through the non-coherent path.  Compile time: a run-time test inside the unrolled
+  // row loads is what cost the first generation 25-50 %.
+  constexpr bool COHERENT_IN = (IO & 8) != 0;
   using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
   constexpr int L = E::M, P = E::P, TF = E::TF;
   constexpr int THREADS = TF * C;
@@ -61,20 +72,10 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
   const int tid = simt::tid();
   const int c = tid % C;
   const int t = tid / C;
-  // one 128-byte aligned region: landing zone of the tile, exchange buffer, staging of the outgoing tile
-  unsigned char* base = simt::smem();
-  base += (128 - (reinterpret_cast<uintptr_t>(base) & 127)) & 127;
   cx<T>* smem = reinterpret_cast<cx<T>*>(base);
   cx<T>* sm = smem + (size_t)c * SLOT;
-  constexpr size_t REGION = sizeof(cx<T>) * (size_t)SLOT * C > 2 * PLANE ? sizeof(cx<T>) * (size_t)SLOT * C : 2 * PLANE;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + ((REGION + 15) & ~(size_t)15));
   const T scale = (T)p.scale;
-  const long long total = p.n_groups * p.n_frames;
-  if (tid == 0) simt::mbar_init(bar, 1);
-  simt::sync_block();
-  unsigned phase = 0u;
-
-  for (long long w = simt::bid(); w < total; w += simt::nblocks()) {
+  {
     const long long fb = w / p.n_groups, g = w % p.n_groups;
     const long long g_hi = g / p.n_lo, g_lo = g % p.n_lo;
     cx<T> v[P];
@@ -88,18 +89,17 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
         const int planes = IN_CPLX ? 1 : (p.has_im ? 2 : 1);
         simt::mbar_expect_tx(bar, (unsigned)planes * p.in_box_bytes * (unsigned)p.in_boxes);
         for (int j = 0; j < p.in_boxes; ++j) {
-          simt::tma_load_3d(base + (size_t)j * p.in_box_bytes, &tm_in_re, co[0], co[1], co[2], bar);
-          if (!IN_CPLX && p.has_im) simt::tma_load_3d(base + PLANE + (size_t)j * p.in_box_bytes, &tm_in_im, co[0], co[1], co[2], bar);
+          simt::tma_load_3d(base + (size_t)j * p.in_box_bytes, tm_in_re, co[0], co[1], co[2], bar);
+          if (!IN_CPLX && p.has_im) simt::tma_load_3d(base + PLANE + (size_t)j * p.in_box_bytes, tm_in_im, co[0], co[1], co[2], bar);
           co[p.in_box_dim] += p.in_box_step;
         }
-        if (p.l2_prefetch && w + simt::nblocks() < total) {
-          const long long w2 = w + simt::nblocks();
-          const long long fb2 = w2 / p.n_groups, g2 = w2 % p.n_groups;
+        if (p.l2_prefetch && w_next >= 0) {
+          const long long fb2 = w_next / p.n_groups, g2 = w_next % p.n_groups;
           const long long h2 = g2 / p.n_lo, l2 = g2 % p.n_lo;
           for (int d = 0; d < 3; ++d) co[d] = (int)(l2 * p.in_lo[d] + h2 * p.in_hi[d] + fb2 * p.in_fr[d]);
           for (int j = 0; j < p.in_boxes; ++j) {
-            simt::tma_prefetch_3d(&tm_in_re, co[0], co[1], co[2]);
-            if (!IN_CPLX && p.has_im) simt::tma_prefetch_3d(&tm_in_im, co[0], co[1], co[2]);
+            simt::tma_prefetch_3d(tm_in_re, co[0], co[1], co[2]);
+            if (!IN_CPLX && p.has_im) simt::tma_prefetch_3d(tm_in_im, co[0], co[1], co[2]);
             co[p.in_box_dim] += p.in_box_step;
           }
         }
@@ -120,6 +120,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
         }
       });
       simt::sync_block();  // tile consumed: the exchanges may overwrite it
+      after_load();
     } else {
       // ---- last pass: C contiguous rows, element index fastest across the CTA, parked in the padded exchange layout.
       // (the region may still be read by the previous item's stores)
@@ -135,7 +136,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
         const int cc = idx >> LOG2L, e = idx & (L - 1);
         const long long a = in_base + cc * p.in_c + e;
         if constexpr (IN_CPLX) {
-          smem[(size_t)cc * SLOT + E::pad(e)] = ldg_cx(icx + a);
+          smem[(size_t)cc * SLOT + E::pad(e)] = COHERENT_IN ? ldcg_cx(icx + a) : ldg_cx(icx + a);
         } else {
           const T re = ire[a];
           const T im = iim != nullptr ? iim[a] : (T)0;
@@ -144,10 +145,9 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
       }
       simt::sync_block();
       static_for<0, P>([&](auto q) { v[decltype(q)::value] = sm[E::pad(t + TF * decltype(q)::value)]; });
-      if (p.l2_prefetch && w + simt::nblocks() < total && tid < C) {
+      if (p.l2_prefetch && w_next >= 0 && tid < C) {
         // the next tile's rows (C runs of L contiguous elements), one bulk L2 prefetch per row
-        const long long w2 = w + simt::nblocks();
-        const long long fb2 = w2 / p.n_groups, g2 = w2 % p.n_groups;
+        const long long fb2 = w_next / p.n_groups, g2 = w_next % p.n_groups;
         const long long a2 = fb2 * p.in_frame + (g2 / p.n_lo) * p.in_g_hi + (g2 % p.n_lo) * p.in_g_lo + tid * p.in_c;
         const unsigned row_bytes = (unsigned)(L * sizeof(T)) * (IN_CPLX ? 2u : 1u);
         if constexpr (IN_CPLX) {
@@ -158,6 +158,7 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
         }
       }
       simt::sync_block();
+      after_load();
     }
 
     E::template fft<true>(v, t, sm, static_cast<const cx<T>*>(p.tw), 0, 1);
@@ -200,14 +201,156 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
       int co[3];
       for (int d = 0; d < 3; ++d) co[d] = (int)(g_lo * p.out_lo[d] + g_hi * p.out_hi[d] + fb * p.out_fr[d]);
       for (int j = 0; j < p.out_boxes; ++j) {
-        simt::tma_store_3d(&tm_out_re, co[0], co[1], co[2], base + (size_t)j * p.out_box_bytes);
-        if (!OUT_CPLX) simt::tma_store_3d(&tm_out_im, co[0], co[1], co[2], base + PLANE + (size_t)j * p.out_box_bytes);
+        simt::tma_store_3d(tm_out_re, co[0], co[1], co[2], base + (size_t)j * p.out_box_bytes);
+        if (!OUT_CPLX) simt::tma_store_3d(tm_out_im, co[0], co[1], co[2], base + PLANE + (size_t)j * p.out_box_bytes);
         co[p.out_box_dim] += p.out_box_step;
       }
       simt::bulk_commit();
     }
   }
+}
+
+// shared-memory carve-up shared by the kernels below: the 128-byte aligned region and the mbarrier behind it
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C>
+struct BigTileSmem {
+  using E = FftEngine<T, LOG2L, LOG2P, MAXRB>;
+  static constexpr size_t PLANE = sizeof(T) * (size_t)E::M * C;
+  static constexpr size_t EXCH = sizeof(cx<T>) * (size_t)(E::SMEM_ELEMS | 1) * C;
+  static constexpr size_t REGION = EXCH > 2 * PLANE ? EXCH : 2 * PLANE;
+  static constexpr size_t BAR_OFF = (REGION + 15) & ~(size_t)15;
+};
+
+template <typename T, int LOG2L, int LOG2P, int MAXRB, int C, int IO>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2L) >> LOG2P) * C, 2)
+    bigfft_tile_kernel(const BigTileParams p, const PDSP_GRID_CONSTANT simt::TensorMap tm_in_re,
+                       const PDSP_GRID_CONSTANT simt::TensorMap tm_in_im, const PDSP_GRID_CONSTANT simt::TensorMap tm_out_re,
+                       const PDSP_GRID_CONSTANT simt::TensorMap tm_out_im) {
+  using S = BigTileSmem<T, LOG2L, LOG2P, MAXRB, C>;
+  const int tid = simt::tid();
+  // one 128-byte aligned region: landing zone of the tile, exchange buffer, staging of the outgoing tile
+  unsigned char* base = simt::smem();
+  base += (128 - (reinterpret_cast<uintptr_t>(base) & 127)) & 127;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + S::BAR_OFF);
+  const long long total = p.n_groups * p.n_frames;
+  if (tid == 0) simt::mbar_init(bar, 1);
+  simt::sync_block();
+  unsigned phase = 0u;
+  for (long long w = simt::bid(); w < total; w += simt::nblocks()) {
+    const long long w_next = w + simt::nblocks() < total ? w + simt::nblocks() : -1;
+    big_tile_item<T, LOG2L, LOG2P, MAXRB, C, IO>(p, &tm_in_re, &tm_in_im, &tm_out_re, &tm_out_im, base, bar, phase, w, w_next);
+  }
   if (tid == 0) simt::bulk_wait_all();  // global writes complete before the kernel ends
+}
+
+// ---- Fused passes 1 + 2 of a three-pass transform in ONE persistent launch.
+// The last pass works on tiles of C2 rows with adjacent k1 (so that its transposed output leaves as C2*8-byte segments),
+// i.e. it needs the middle pass' results of C2 whole k1 blocks - a "k1 group".  The fused work list alternates, group by
+// group, the group's n1g middle-pass tiles and its n2g last-pass tiles; CTAs take items in order (bid, bid + grid, ...), a
+// last-pass item first waits until the group's counter shows all n1g middle tiles stored.  A group's slice of the work
+// buffer (C2 k1 blocks: 16 MB for 2^24) is then read back while it is still in the L2: the work buffer crosses HBM once
+// between passes 0 and 1 only, with none of the ramp and tail of the launch-per-group form (profiles/r2/README.md).
+// No deadlock: every producer of an item precedes it in the list, and the grid is never larger than what is resident.
+struct BigFusedSync {
+  unsigned* counters;   // one per k1 group, zeroed before the launch
+  unsigned* error;      // set when a wait gave up (watchdog) - the host reports it
+  long long n_groups;   // k1 groups
+  long long n1g, n2g;   // middle-pass / last-pass items per group
+};
+template <typename T, int LOG2LA, int LOG2LB, int LOG2P, int MAXRBA, int MAXRBB, int CA, int CB>
+PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2LA) >> LOG2P) * CA, 2)
+    bigfft_fused_kernel(const BigTileParams pa, const BigTileParams pb, const BigFusedSync fs,
+                        const PDSP_GRID_CONSTANT simt::TensorMap a_in, const PDSP_GRID_CONSTANT simt::TensorMap a_out,
+                        const PDSP_GRID_CONSTANT simt::TensorMap b_out_re, const PDSP_GRID_CONSTANT simt::TensorMap b_out_im) {
+  static_assert((((1 << LOG2LA) >> LOG2P) * CA) == (((1 << LOG2LB) >> LOG2P) * CB), "both passes run on the same CTA shape");
+  using SA = BigTileSmem<T, LOG2LA, LOG2P, MAXRBA, CA>;
+  using SB = BigTileSmem<T, LOG2LB, LOG2P, MAXRBB, CB>;
+  constexpr size_t BAR_OFF = SA::BAR_OFF > SB::BAR_OFF ? SA::BAR_OFF : SB::BAR_OFF;
+  const int tid = simt::tid();
+  unsigned char* base = simt::smem();
+  base += (128 - (reinterpret_cast<uintptr_t>(base) & 127)) & 127;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(base + BAR_OFF);
+  const long long per_group = fs.n1g + fs.n2g;
+  const long long total = fs.n_groups * per_group;
+  if (tid == 0) simt::mbar_init(bar, 1);
+  simt::sync_block();
+  unsigned phase = 0u;
+  long long pending = -1;  // thread 0: group whose counter still owes this CTA's last middle-pass tile
+  // List order: M0, M1, L0, M2, L1, ..., M(n-1), L(n-2), L(n-1) (M = a group's middle tiles, L = its last-pass tiles): a
+  // last-pass item then follows its producers by a whole group of other work, so in steady state nobody waits (with
+  // M0, L0, M1, L1, ... a third of the CTAs sat out a tile time in every round: 2^24 430 us against 327 pass by pass).
+  auto decode = [&](long long f, long long* G, long long* r) -> bool {  // true: middle-pass item
+    if (f < fs.n1g) {
+      *G = 0, *r = f;
+      return true;
+    }
+    const long long fp = f - fs.n1g, pair = fp / per_group, rem = fp % per_group;
+    if (pair >= fs.n_groups - 1) {
+      *G = fs.n_groups - 1, *r = rem;
+      return false;
+    }
+    if (rem < fs.n1g) {
+      *G = pair + 1, *r = rem;
+      return true;
+    }
+    *G = pair, *r = rem - fs.n1g;
+    return false;
+  };
+  for (long long f = simt::bid(); f < total; f += simt::nblocks()) {
+    long long G, r;
+    const bool middle = decode(f, &G, &r);
+    // publish this CTA's previous middle tile once its box stores have completed (release).  Done from inside the item,
+    // after its input has arrived: the stores have had a whole load latency to drain, so the wait is free - at the top
+    // of the item it exposed the drain of every middle tile.  (No deadlock: the wait below is on an EARLIER group's
+    // counter than the one this CTA still owes, and every CTA reaches its hook without waiting on anyone but producers
+    // of earlier groups.)
+    auto publish = [&]() {
+      if (tid == 0 && pending >= 0) {
+        simt::bulk_wait_all();
+        simt::fence_proxy_async_all();
+        simt::fence_gpu();
+        simt::atomic_add(fs.counters + pending, 1u);
+        pending = -1;
+      }
+    };
+    if (tid == 0) {
+      if (!middle && pending == G) publish();  // owing the very group it is about to wait for: settle first
+      if (!middle) {  // last-pass item: the group's middle tiles must all be in (acquire)
+        unsigned long long spins = 0;
+        while (simt::load_acquire(fs.counters + G) < (unsigned)fs.n1g) {
+          if (++spins > (1ull << 22)) {  // watchdog (seconds): never hang the device on a lost signal
+            simt::store_volatile(fs.error, 1u);
+            break;
+          }
+        }
+      }
+    }
+    if (middle) {
+      const long long w = G * fs.n1g + r;
+      // next middle-pass item of this CTA (for the L2 prefetch of its tile), if its next item is one
+      // the CTA's next MIDDLE item, whatever lies between (its tile comes from HBM: have it waiting in the L2)
+      long long w2 = -1;
+      for (long long f2 = f + simt::nblocks(), k = 0; f2 < total && k < 4; f2 += simt::nblocks(), ++k) {
+        long long G2, r2;
+        if (decode(f2, &G2, &r2)) {
+          w2 = G2 * fs.n1g + r2;
+          break;
+        }
+      }
+      big_tile_item<T, LOG2LA, LOG2P, MAXRBA, CA, 3>(pa, &a_in, &a_in, &a_out, &a_out, base, bar, phase, w, w2, publish);
+      if (tid == 0) pending = G;
+    } else {
+      const long long w = G * fs.n2g + r;
+      big_tile_item<T, LOG2LB, LOG2P, MAXRBB, CB, 5 | 8>(pb, &b_out_re, &b_out_im, &b_out_re, &b_out_im, base, bar, phase, w, -1, publish);
+    }
+  }
+  if (tid == 0) {
+    simt::bulk_wait_all();  // global writes complete before the kernel ends
+    if (pending >= 0) {
+      simt::fence_proxy_async_all();
+      simt::fence_gpu();
+      simt::atomic_add(fs.counters + pending, 1u);
+    }
+  }
 }
 
 // Tile configuration of the second generation: half the sequences of BigCfg, two CTAs per SM

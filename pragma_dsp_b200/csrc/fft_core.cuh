@@ -86,9 +86,22 @@ PDSP_DEVICE cx<float> ldg_cx(const cx<float>* p) {
   return cx<float>{v.x, v.y};
 #endif
 }
+// L2-coherent load (ld.global.cg): data another CTA of the same launch has just published
+PDSP_DEVICE cx<double> ldcg_cx(const cx<double>* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cx<double>{v.x, v.y};
+}
+PDSP_DEVICE cx<float> ldcg_cx(const cx<float>* p) {
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return cx<float>{v.x, v.y};
+}
 #else
 template <typename T>
 PDSP_DEVICE cx<T> ldg_cx(const cx<T>* p) {
+  return *p;
+}
+template <typename T>
+PDSP_DEVICE cx<T> ldcg_cx(const cx<T>* p) {
   return *p;
 }
 #endif

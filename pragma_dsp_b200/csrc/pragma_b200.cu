@@ -50,6 +50,9 @@ cudaError_t launch_big_pass_tma(bool f64, int log2l, const BigPassParams& p, con
 // second generation (bigfft2.cu): TMA tile loads and stores
 int big2_pass_c(int log2l);
 bool big_pipe_supported(bool f64, int log2l);
+bool big_fused_supported(bool f64, int la, int lb);
+cudaError_t launch_big_fused(int la, int lb, const BigTileParams& pa, const BigTileParams& pb, const BigFusedSync& fs,
+                             const simt::TensorMap* ma, const simt::TensorMap* mb, const LaunchCtx& lc);
 cudaError_t launch_big_pipe(bool f64, int log2l, bool last, const BigPassParams& p, const simt::TensorMap2D& tm_re,
                             const simt::TensorMap2D& tm_im, const LaunchCtx& lc);
 cudaError_t launch_big_tile(bool f64, int log2l, int io, const BigTileParams& p, const simt::TensorMap* maps, const LaunchCtx& lc);
@@ -82,6 +85,7 @@ struct Tune {
   int big_resident = -1;      // PDSP_BIG_RESIDENT: three-pass transforms, passes 1+2 in L2-sized k1 groups: -1 / 0 off (measured slower), 1 on (automatic group size), n > 1 blocks per group
   int big_v2 = -1;            // PDSP_BIG_V2: large-FFT pass generation: -1 per pass (second where its box rows are >= 64 bytes), 0 first, 1 second
   int big_pipe = -1;          // PDSP_BIG_PIPE: third-generation (pipeline) large-FFT passes: -1 automatic (1024-point passes), 0 off, 1 every pass length it exists for (256 / 512 / 1024, fp64), 2 + m: the passes whose bit is set in m
+  int big_fused = -1;         // PDSP_BIG_FUSED: three-pass transforms, middle + last pass in one persistent launch with tile-level hand-over through the L2: -1 automatic, 0 off, 1 on
   int fast = 1;               // PDSP_FAST: 0 disables the single-call fast lane (small host jobs then use the staging pipeline)
   int doorbell = 1;           // PDSP_DOORBELL: 0 = the fast lane waits with cudaStreamSynchronize instead of the in-kernel doorbell
   int copy_threads = 3;       // PDSP_COPY_THREADS: helper threads of an ingestion ring's host copies (0 = the caller alone)
@@ -116,6 +120,8 @@ static int tune_set(Tune& t, const char* key, const char* val) {
     t.big_v2 = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "big_pipe")) {
     t.big_pipe = unset ? -1 : atoi(v);  // 0 off, 1 every supported length, 2 + mask: passes whose bit is set in mask (bit j = pass j)
+  } else if (!strcmp(key, "big_fused")) {
+    t.big_fused = unset ? -1 : (v[0] != '0');
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "doorbell")) {
@@ -132,7 +138,7 @@ static void tune_from_env(Tune& t) {
                                         {"big_interleave", "PDSP_BIG_INTERLEAVE"}, {"big_prefetch", "PDSP_BIG_PREFETCH"},
                                         {"big_chunk", "PDSP_BIG_CHUNK"},       {"big_factors", "PDSP_BIG_FACTORS"},
                                         {"chunk_bytes", "PDSP_CHUNK_BYTES"},   {"staged", "PDSP_STAGED"},
-                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}, {"doorbell", "PDSP_DOORBELL"}, {"big_pipe", "PDSP_BIG_PIPE"}};
+                                        {"big_resident", "PDSP_BIG_RESIDENT"}, {"fast", "PDSP_FAST"}, {"copy_threads", "PDSP_COPY_THREADS"}, {"big_v2", "PDSP_BIG_V2"}, {"doorbell", "PDSP_DOORBELL"}, {"big_pipe", "PDSP_BIG_PIPE"}, {"big_fused", "PDSP_BIG_FUSED"}};
   for (auto& k : keys)
     if (const char* e = getenv(k[1])) tune_set(t, k[0], e);
 }
@@ -410,6 +416,7 @@ struct BigPlan {
     void* im = nullptr;
     long long frames = 0;
     bool interleaved = false;
+    unsigned* sync = nullptr;  // fused middle + last pass: 1024 group counters + 1 error word (device memory)
     // large-N spectrum(): windowed frames and their full complex spectra (spec_frames transforms each)
     void* spec_x = nullptr;
     void* spec_re = nullptr;
@@ -971,7 +978,8 @@ static int make_tensor_map3(simt::TensorMap* tm, const void* base, bool f64, con
 // the caller then runs passes 1 and 2 group by group so that a group's work-buffer slice never leaves the L2.
 static int launch_pass_v2(pdsp_plan* pl, BigPlan* bp, int j, long long O, long long I, long long nf, const void* in_re,
                           const void* in_im, bool in_cplx, void* out_re, void* out_im, bool out_cplx, int inverse,
-                          const LaunchCtx& lc, long long k0, long long k_cnt) {
+                          const LaunchCtx& lc, long long k0, long long k_cnt, BigTileParams* cap_p = nullptr,
+                          simt::TensorMap* cap_maps = nullptr) {
   pdsp_ctx* c = pl->ctx;
   const bool f64 = pl->precision == PDSP_F64;
   const size_t es = esize(pl->precision);
@@ -1045,6 +1053,11 @@ static int launch_pass_v2(pdsp_plan* pl, BigPlan* bp, int j, long long O, long l
     p.out_box_bytes = (unsigned)(C * BR * es);
     io = 4 | (in_cplx ? 1 : 0);
   }
+  if (cap_p != nullptr) {  // the fused launch takes the parameter block and the maps instead
+    *cap_p = p;
+    for (int k = 0; k < 4; ++k) cap_maps[k] = maps[k];
+    return 0;
+  }
   const cudaError_t e = launch_big_tile(f64, bp->lg[j], io, p, maps, lc);
   if (e != cudaSuccess) return fail("big FFT pass %d (n=2^%d, TMA tiles): %s", j, pl->log2n, cudaGetErrorString(e));
   c->launches++;
@@ -1057,6 +1070,9 @@ static int launch_pass_v2(pdsp_plan* pl, BigPlan* bp, int j, long long O, long l
 // 2^16, 2^22 and 2^24 - and the first (bigfft_kernels.cuh) for the 512- and 1024-point passes, whose 4- and 8-column
 // tiles make 32-byte box rows (the TMA unit then spends its time on row requests: 2^20 = 1024 x 1024 ran 0.19 of the
 // roofline against 0.26).  `chunk` transforms go through all passes together.
+#ifndef PDSP_BIG_FUSED_DEFAULT
+#define PDSP_BIG_FUSED_DEFAULT false
+#endif
 static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* d_im, long long batch, void* d_ore,
                       void* d_oim, int inverse, cudaStream_t st, bool v2_allowed) {
   pdsp_ctx* c = pl->ctx;
@@ -1128,6 +1144,53 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
       if ((size_t)Ls[0] * block > ((size_t)64 << 20) && g < Ls[0] && Ls[0] % g == 0) group = g;
       if (c->tune.big_resident > 1 && Ls[0] % c->tune.big_resident == 0 && c->tune.big_resident % c_last == 0)
         group = c->tune.big_resident;  // explicit group size (k1 blocks)
+    }
+    // Fused form of the same idea: ONE persistent launch runs the middle and the last pass, a last-pass tile waiting
+    // (acquire on a per-group counter) until the middle tiles of its C2 k1 blocks have been stored - no launch per group,
+    // no ramp and tail (bigfft_fused_kernel).
+    const bool fused = np == 3 && il && pass_v2[1] && pass_v2[2] && big_fused_supported(f64, bp->lg[1], bp->lg[2]) &&
+                       (c->tune.big_fused < 0 ? PDSP_BIG_FUSED_DEFAULT : c->tune.big_fused != 0) && Ls[0] / big2_pass_c(bp->lg[2]) <= 1024;
+    if (fused) {
+      if (!wk->sync) {
+        std::lock_guard<std::recursive_mutex> lk(c->plan_mu);
+        if (!wk->sync) {
+          void* sp = nullptr;
+          CU(cudaMalloc(&sp, 1025 * sizeof(unsigned)));
+          wk->sync = static_cast<unsigned*>(sp);
+        }
+      }
+      for (long long f = 0; f < nf; ++f) {
+        const char* xre = fre + (size_t)f * N * es;
+        const char* xim = fim ? fim + (size_t)f * N * es : nullptr;
+        char* yre = gre + (size_t)f * N * es;
+        char* yim = gim + (size_t)f * N * es;
+        char* wbuf = static_cast<char*>(wk->re) + (size_t)f * N * 2 * es;
+        const long long I0 = N / Ls[0], I1 = I0 / Ls[1];
+        if (pass_v2[0]) {
+          if (launch_pass_v2(pl, bp, 0, 1, I0, 1, xre, xim, false, wbuf, nullptr, true, inverse, lc, 0, 0)) return 1;
+        } else {
+          // first or third generation: they address the group's work buffer through wk, so point a one-frame view at it
+          BigPlan::Work one = *wk;
+          one.re = wbuf;
+          if (launch_pass_v1(pl, bp, &one, 0, 1, I0, 1, xre, xim, yre, yim, inverse, lc, pass_v3[0])) return 1;
+        }
+        BigTileParams pa, pb;
+        simt::TensorMap ma[4], mb[4];
+        if (launch_pass_v2(pl, bp, 1, Ls[0], I1, 1, wbuf, nullptr, true, wbuf, nullptr, true, inverse, lc, 0, 0, &pa, ma)) return 1;
+        if (launch_pass_v2(pl, bp, 2, Ls[0] * Ls[1], 1, 1, wbuf, nullptr, true, yre, yim, false, inverse, lc, 0, 0, &pb, mb)) return 1;
+        BigFusedSync fs;
+        fs.n_groups = Ls[0] / big2_pass_c(bp->lg[2]);
+        fs.n1g = pa.n_groups / fs.n_groups;
+        fs.n2g = pb.n_groups / fs.n_groups;
+        fs.counters = wk->sync;
+        fs.error = wk->sync + 1024;
+        if (pa.n_groups % fs.n_groups || pb.n_groups % fs.n_groups) return fail("internal: fused passes of 2^%d do not tile into %lld groups", pl->log2n, fs.n_groups);
+        CU(cudaMemsetAsync(wk->sync, 0, 1025 * sizeof(unsigned), st));
+        const cudaError_t e = launch_big_fused(bp->lg[1], bp->lg[2], pa, pb, fs, ma, mb, lc);
+        if (e != cudaSuccess) return fail("big FFT fused passes (n=2^%d): %s", pl->log2n, cudaGetErrorString(e));
+        c->launches++;
+      }
+      continue;
     }
     if (group > 0) {
       for (long long f = 0; f < nf; ++f) {
@@ -1412,6 +1475,7 @@ PDSP_EXPORT int pdsp_ctx_destroy(pdsp_ctx* c) {
       for (auto& kv : pl->big->work) {
         cudaFree(kv.second.re);
         cudaFree(kv.second.im);
+        cudaFree(kv.second.sync);
         cudaFree(kv.second.spec_x);
         cudaFree(kv.second.spec_re);
         cudaFree(kv.second.spec_im);
@@ -1522,6 +1586,7 @@ static int release_stream_work(pdsp_plan* pl, cudaStream_t st) {
   BigPlan::Work& w = it->second;
   cudaFree(w.re);
   cudaFree(w.im);
+  cudaFree(w.sync);
   cudaFree(w.spec_x);
   cudaFree(w.spec_re);
   cudaFree(w.spec_im);

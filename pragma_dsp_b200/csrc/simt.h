@@ -119,6 +119,15 @@ PDSP_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [
 // host-mapped pinned memory; the host spins on it instead of going through a stream synchronisation
 PDSP_DEVICE void fence_system() { __threadfence_system(); }
 PDSP_DEVICE unsigned atomic_add(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+// inter-CTA hand-over inside one launch (fused large-FFT passes): release = bulk stores complete, proxy fence, gpu fence,
+// then the counter increment; acquire = ld.acquire.gpu on the counter
+PDSP_DEVICE void fence_gpu() { __threadfence(); }
+PDSP_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+PDSP_DEVICE unsigned load_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 PDSP_DEVICE void store_volatile(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
 PDSP_DEVICE unsigned char* smem() {
   extern __shared__ __align__(16) unsigned char pdsp_smem_[];
@@ -264,6 +273,9 @@ inline bool any(bool pred) {  // warp vote through the shuffle mailbox: OR over 
 }
 inline void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomic_add(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void fence_gpu() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void fence_proxy_async_all() {}
+inline unsigned load_acquire(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void store_volatile(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned char* smem() { return emu_self.smem; }
 template <typename T>

@@ -24,7 +24,7 @@ peak, _ = bench.measured_hbm_peak()
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev)
 vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-KEYS = ("big_v2", "big_chunk", "big_interleave", "big_resident", "big_pipe", "big_factors")
+KEYS = ("big_v2", "big_chunk", "big_interleave", "big_resident", "big_pipe", "big_factors", "big_fused")
 cases = [(20, 8), (24, 1), (22, 2), (16, 64), (18, 16)]
 settings = [dict(), dict(big_v2=0), dict(big_v2=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]
 if "--resident" in sys.argv:  # 2^24 / 2^26: passes 1+2 in L2-sized k1 groups (big_resident = blocks per group), against pass-by-pass
@@ -39,6 +39,9 @@ if "--pipe" in sys.argv:  # third generation (pipeline passes) against the per-p
 if "--pipemask" in sys.argv:  # which passes of a three-pass transform gain from the pipeline form (big_pipe = 2 + mask)
     cases = [(24, 1), (26, 1), (22, 2)]
     settings = [dict(big_pipe=0)] + [dict(big_pipe=2 + m) for m in range(1, 8)] + [dict(big_pipe=0)]
+if "--fused" in sys.argv:  # middle + last pass in one persistent launch (tile-level hand-over through the L2) against pass by pass
+    cases = [(24, 1), (26, 1), (25, 1), (27, 1)]
+    settings = [dict(big_fused=0), dict(big_fused=1), dict(big_fused=1, big_pipe=0), dict(big_fused=0)]
 if "--only20" in sys.argv:
     cases = [(20, 8)]
     settings = [dict(big_v2=0), dict(big_v2=0, big_chunk=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]

@@ -41,6 +41,7 @@ cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned flags);
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned flags);
 cudaError_t cudaMemset(void* p, int value, size_t bytes);
+inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t) { return cudaMemset(p, value, bytes); }
 cudaError_t cudaStreamQuery(cudaStream_t s);
 cudaError_t cudaEventQuery(cudaEvent_t e);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);

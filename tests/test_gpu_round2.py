@@ -253,7 +253,8 @@ def test_c3_full_size_stft_against_oracle_subset(ctx):
 @pytest.mark.parametrize("log2n", [16, 18, 20, 24])
 def test_large_fft_pass_generations_agree(ctx, log2n):
     """K2 has three generations of the pass kernel (per-thread / TMA loads; TMA loads + stores, two CTAs per SM; pipeline
-    passes with the split-plane exchange).  Forced one at a time through the tunables, all give the same transform."""
+    passes with the split-plane exchange) and a fused form of the middle + last pass (one persistent launch, tiles handed
+    over through per-group counters).  Forced one at a time through the tunables, all give the same transform."""
     from pragma_dsp_b200.core import ComplexArray, Radix2Fft
     n = 1 << log2n
     rng = np.random.default_rng(log2n)
@@ -261,9 +262,12 @@ def test_large_fft_pass_generations_agree(ctx, log2n):
     ref = np.fft.fft(re + 1j * im)
     outs = []
     try:
-        for pipe, v2 in (("0", "0"), ("0", "1"), ("1", "0"), (None, None)):
+        for pipe, v2, fused in (("0", "0", None), ("0", "1", None), ("1", "0", None), (None, None, None), (None, None, "1"), ("0", "1", "1")):
+            if fused and log2n < 22:
+                continue  # the fused middle + last pass exists for three-pass transforms
             ctx.tune("big_pipe", pipe)
             ctx.tune("big_v2", v2)
+            ctx.tune("big_fused", fused)
             out = Radix2Fft(n).forwardComplex(ComplexArray(re, im))
             z = out.real + 1j * out.imag
             assert np.linalg.norm(z - ref) / np.linalg.norm(ref) <= 1e-12 * log2n
@@ -273,6 +277,7 @@ def test_large_fft_pass_generations_agree(ctx, log2n):
     finally:
         ctx.tune("big_pipe", None)
         ctx.tune("big_v2", None)
+        ctx.tune("big_fused", None)
     for z in outs[1:]:  # same butterflies, same twiddles: the generations differ in data movement only
         assert np.linalg.norm(z - outs[0]) / np.linalg.norm(outs[0]) <= 1e-15
 

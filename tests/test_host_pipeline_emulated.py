@@ -187,6 +187,8 @@ def test_launch_and_plan_accounting(emu_api):
                                            ("8,9", 1 << 17, {"big_pipe": "1"}),
                                            ("6,8,6", 1 << 20, {"big_pipe": "1"}),
                                            ("10,6", 1 << 16, {}),
+                                           # middle + last pass fused into one persistent launch (tile-level hand-over through counters)
+                                           ("6,6,6", 1 << 18, {"big_fused": "1"}),
                                            # first generation, its switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
                                            ("6,6", 4096, {"big_v2": "0"}),
                                            ("6,6,6", 1 << 18, {"big_v2": "0"}),
