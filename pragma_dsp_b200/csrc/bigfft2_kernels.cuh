@@ -255,6 +255,7 @@ struct BigFusedSync {
   unsigned* error;      // set when a wait gave up (watchdog) - the host reports it
   long long n_groups;   // k1 groups
   long long n1g, n2g;   // middle-pass / last-pass items per group
+  long long skew;       // list order: a group's last-pass tiles follow its middle tiles by this many groups of middle tiles (>= 1)
 };
 template <typename T, int LOG2LA, int LOG2LB, int LOG2P, int MAXRBA, int MAXRBB, int CA, int CB>
 PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2LA) >> LOG2P) * CA, 2)
@@ -279,17 +280,19 @@ PDSP_GLOBAL void PDSP_LAUNCH_BOUNDS(((1 << LOG2LA) >> LOG2P) * CA, 2)
   // last-pass item then follows its producers by a whole group of other work, so in steady state nobody waits (with
   // M0, L0, M1, L1, ... a third of the CTAs sat out a tile time in every round: 2^24 430 us against 327 pass by pass).
   auto decode = [&](long long f, long long* G, long long* r) -> bool {  // true: middle-pass item
-    if (f < fs.n1g) {
-      *G = 0, *r = f;
+    const long long S = fs.skew < fs.n_groups ? fs.skew : fs.n_groups;  // groups of middle tiles ahead of the last-pass tiles
+    if (f < S * fs.n1g) {
+      *G = f / fs.n1g, *r = f % fs.n1g;
       return true;
     }
-    const long long fp = f - fs.n1g, pair = fp / per_group, rem = fp % per_group;
-    if (pair >= fs.n_groups - 1) {
-      *G = fs.n_groups - 1, *r = rem;
+    const long long fp = f - S * fs.n1g, pair = fp / per_group, rem = fp % per_group;
+    if (pair >= fs.n_groups - S) {  // tail: the last S groups' last-pass tiles
+      const long long ft = fp - (fs.n_groups - S) * per_group;
+      *G = fs.n_groups - S + ft / fs.n2g, *r = ft % fs.n2g;
       return false;
     }
     if (rem < fs.n1g) {
-      *G = pair + 1, *r = rem;
+      *G = pair + S, *r = rem;
       return true;
     }
     *G = pair, *r = rem - fs.n1g;

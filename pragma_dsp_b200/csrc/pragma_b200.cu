@@ -121,7 +121,7 @@ static int tune_set(Tune& t, const char* key, const char* val) {
   } else if (!strcmp(key, "big_pipe")) {
     t.big_pipe = unset ? -1 : atoi(v);  // 0 off, 1 every supported length, 2 + mask: passes whose bit is set in mask (bit j = pass j)
   } else if (!strcmp(key, "big_fused")) {
-    t.big_fused = unset ? -1 : (v[0] != '0');
+    t.big_fused = unset ? -1 : atoi(v);  // 0 off, n >= 1: on, with the last-pass tiles n groups behind the middle tiles
   } else if (!strcmp(key, "fast")) {
     t.fast = unset ? 1 : (v[0] != '0');
   } else if (!strcmp(key, "doorbell")) {
@@ -1182,6 +1182,7 @@ static int launch_big(pdsp_plan* pl, BigPlan* bp, const void* d_re, const void* 
         fs.n_groups = Ls[0] / big2_pass_c(bp->lg[2]);
         fs.n1g = pa.n_groups / fs.n_groups;
         fs.n2g = pb.n_groups / fs.n_groups;
+        fs.skew = c->tune.big_fused > 1 ? c->tune.big_fused : 1;
         fs.counters = wk->sync;
         fs.error = wk->sync + 1024;
         if (pa.n_groups % fs.n_groups || pb.n_groups % fs.n_groups) return fail("internal: fused passes of 2^%d do not tile into %lld groups", pl->log2n, fs.n_groups);

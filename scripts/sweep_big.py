@@ -41,7 +41,7 @@ if "--pipemask" in sys.argv:  # which passes of a three-pass transform gain from
     settings = [dict(big_pipe=0)] + [dict(big_pipe=2 + m) for m in range(1, 8)] + [dict(big_pipe=0)]
 if "--fused" in sys.argv:  # middle + last pass in one persistent launch (tile-level hand-over through the L2) against pass by pass
     cases = [(24, 1), (26, 1), (25, 1), (27, 1)]
-    settings = [dict(big_fused=0), dict(big_fused=1), dict(big_fused=1, big_pipe=0), dict(big_fused=0)]
+    settings = [dict(big_fused=0), dict(big_fused=1), dict(big_fused=2), dict(big_fused=3), dict(big_fused=0)]
 if "--only20" in sys.argv:
     cases = [(20, 8)]
     settings = [dict(big_v2=0), dict(big_v2=0, big_chunk=1), dict(big_v2=0, big_chunk=2), dict(big_v2=0, big_chunk=4)]

@@ -189,6 +189,7 @@ def test_launch_and_plan_accounting(emu_api):
                                            ("10,6", 1 << 16, {}),
                                            # middle + last pass fused into one persistent launch (tile-level hand-over through counters)
                                            ("6,6,6", 1 << 18, {"big_fused": "1"}),
+                                           ("7,6,6", 1 << 19, {"big_fused": "2"}),
                                            # first generation, its switchable paths: plain / TMA tile loads, no L2 prefetch, planar work planes
                                            ("6,6", 4096, {"big_v2": "0"}),
                                            ("6,6,6", 1 << 18, {"big_v2": "0"}),
