@@ -250,10 +250,11 @@ PDSP_DEVICE cx<T> mul_w32_full(cx<T> d) {
 
 // In-register radix-R DFT, decimation in frequency: natural order in, X[k] left in
 // a[bitrev(k, log2 R)].  R in {1, 2, 4, 8, 16, 32}.
-template <typename T, int R>
+// FIRST: first stage to run (1: the caller has already done stage 0 - the r2c kernels fuse the window multiply into it).
+template <typename T, int R, int FIRST = 0>
 PDSP_DEVICE void dif_butterfly(cx<T> (&a)[R]) {
   constexpr int LR = ilog2(R);
-  static_for<0, LR>([&](auto st) {
+  static_for<FIRST, LR>([&](auto st) {
     constexpr int h = R >> (decltype(st)::value + 1);
     static_for<0, R / 2>([&](auto bi) {
       constexpr int g = (decltype(bi)::value / h) * 2 * h;
@@ -367,9 +368,12 @@ struct FftEngine {
   // first, then the imaginary parts - half the shared memory for two more barriers per exchange.  The large-FFT
   // pipeline kernel (bigfft3_kernels.cuh) uses it to keep a whole second tile landing while the current one is
   // transformed.  `sm` then points at the sequence's slot of T elements (passed as cx<T>* for one signature).
-  template <bool BLOCKSYNC = false, class Hook = NoHook, bool SPLITX = false>
+  // PRE0: the caller has run stage 0 of the first pass' butterflies itself (only for P == R, one butterfly per thread).
+  static constexpr bool CAN_PRE0 = NPASS >= 1 && P == (1 << RB) && RB >= 1;
+  template <bool BLOCKSYNC = false, class Hook = NoHook, bool SPLITX = false, bool PRE0 = false>
   PDSP_DEVICE static void fft(cx<T> (&v)[P], int t, cx<T>* sm, const cx<T>* PDSP_RESTRICT tw, int slot,
                               int slots_per_cta, Hook after_smem = Hook{}) {
+    static_assert(!PRE0 || CAN_PRE0, "a pre-run first stage needs one full-radix butterfly per thread in pass 0");
     if constexpr (last_smem_pass<BLOCKSYNC>() < 0) after_smem();
     auto sync = [&]() {
       if constexpr (BLOCKSYNC)
@@ -439,7 +443,7 @@ struct FftEngine {
             });
           }
         }
-        dif_butterfly<T, R>(a);
+        dif_butterfly<T, R, (PRE0 && pass == 0) ? 1 : 0>(a);
         if constexpr (last) {
           static_for<0, R>([&](auto k) { v[u + decltype(k)::value * BPT] = a[bitrev(decltype(k)::value, b)]; });
         } else if constexpr (SHUF) {

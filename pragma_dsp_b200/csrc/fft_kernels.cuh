@@ -96,6 +96,9 @@ struct C2CParams {
   Doorbell door;
 };
 
+#ifndef PDSP_FUSE_WINDOW
+#define PDSP_FUSE_WINDOW 0
+#endif
 #ifndef PDSP_NEXT_PREFETCH
 #define PDSP_NEXT_PREFETCH 0
 #endif
@@ -396,6 +399,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
   // peak-only kernels rank bins by |X|^2 (no square root per bin); the winner's amplitude is computed
   // once, in the finishing loop.  Frames spanning several warps keep the linear key.
   constexpr bool KEYSQ = MODE == MD_PEAK && TF <= 32;
+  // window multiply fused into the first butterfly stage (specialised fp64 kernels with one radix-P butterfly per thread)
+  constexpr bool FUSE_WIN = PDSP_FUSE_WINDOW && !GEN && !STAGED && sizeof(T) == 8 && E::CAN_PRE0 && P >= 4;
 
   const int tid = simt::tid();
   const int slot = tid / TF;
@@ -521,7 +526,27 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
         }
 #endif
       }
-      if (win != nullptr) {
+      if constexpr (FUSE_WIN) {
+        // applyWindow fused into stage 0 of the first radix-P butterfly (pairs q, q + P/2): x = v[q]*w[q], then
+        // sum = fma(v[q+P/2], w[q+P/2], x) and diff = fma(-v[q+P/2], w[q+P/2], x) - 6 instead of 8 DP instructions per pair
+        // of complex points (the kernel is bound by the energy of its double-precision work: profiles/r2/README.md).  A
+        // rectangular window runs the same code with w = 1 (exact).
+        constexpr int H = P / 2;
+        static_for<0, H>([&](auto qi) {
+          constexpr int q = decltype(qi)::value;
+          cx<T> w0{(T)1, (T)1}, w1{(T)1, (T)1};
+          if (win != nullptr) {
+            w0 = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
+            w1 = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * (q + H)));
+          }
+          const cx<T> x = ew_mul(v[q], w0);
+          const cx<T> y = v[q + H];
+          const cx<T> sum{y.x * w1.x + x.x, y.y * w1.y + x.y};
+          const cx<T> dif{x.x - y.x * w1.x, x.y - y.y * w1.y};
+          v[q] = sum;
+          v[q + H] = mul_w32<(q * 16) / H>(dif);
+        });
+      } else if (win != nullptr) {
         static_for<0, P>([&](auto qi) {
           constexpr int q = decltype(qi)::value;
           const cx<T> w = ldg_cx(reinterpret_cast<const cx<T>*>(win) + (t + TF * q));
@@ -579,6 +604,8 @@ PDSP_DEVICE void r2c_body(const R2CParams& p) {
       E::fft(v, t, sm, tw, slot, SLOTS, [&]() {
         if (tl == 0 && it + 1 < n_iter) stage_issue(f + SLOTS);
       });
+    } else if constexpr (FUSE_WIN) {
+      E::template fft<false, typename E::NoHook, false, true>(v, t, sm, tw, slot, SLOTS);
     } else {
       E::fft(v, t, sm, tw, slot, SLOTS);
     }
